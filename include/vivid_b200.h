@@ -1,0 +1,256 @@
+/*
+ * vivid_b200 — C ABI of libvividb200.so
+ *
+ * B200-native (sm_100a) kernels for VIVID's guided EDM2 denoising hot path.
+ * The reference (danielcodelavin/vivid) has no FFI of its own: its boundary is
+ * Python duck-typing.  This header is the boundary a maintainer
+ * would bind instead of the PyTorch library calls listed per entry point below;
+ * INTEGRATION.md shows the ctypes stub.  Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     stated otherwise; tensors are contiguous in the layout stated;
+ *   - every call returns 0 on success, a negative vb_status otherwise, never
+ *     throws or aborts; vb_last_error() returns a thread-local message;
+ *   - all work is enqueued on the caller's CUDA stream (cudaStream_t passed as
+ *     void*), no implicit synchronisation, no allocation on the hot path;
+ *   - the library is GPU-only: there is no CPU fallback.
+ *
+ * Activation layout inside the library is NHWC ("pixels x channels"), bf16 for
+ * GEMM operands and fp32 for the residual stream.  Channel counts of GEMM
+ * operands are padded to multiples of 64 (inputs) / 16 (outputs).
+ */
+#ifndef VIVID_B200_H_
+#define VIVID_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB_ABI_VERSION 1
+
+typedef enum vb_status {
+  VB_OK = 0,
+  VB_ERR_INVALID = -1,  /* bad argument / unsupported shape */
+  VB_ERR_CUDA = -2,     /* CUDA runtime / driver error (message has details) */
+  VB_ERR_NO_DEVICE = -3 /* no sm_100 device is current */
+} vb_status;
+
+typedef enum vb_dtype { VB_F32 = 0, VB_F16 = 1, VB_BF16 = 2 } vb_dtype;
+
+const char* vb_last_error(void);
+int vb_abi_version(void);
+/* 0 when the current CUDA device is compute capability 10.x, VB_ERR_NO_DEVICE otherwise. */
+int vb_device_check(void);
+
+/* ------------------------------------------------------------------------
+ * Weight preparation — replaces the per-call prologue of MPConv.forward
+ * (reference training/models.py:115-121 + normalize :37-42):
+ *   w_eff = gain * w / (eps*sqrt(K) + ||w||_2 per out-channel),  K = cin*taps, eps = 1e-4
+ * computed in fp32 from fp32/fp16 parameters, rounded once to bf16 and
+ * repacked OIHW -> [cout_pad][tap][cin_pad] (K-major GEMM B operand).
+ * Optional: fold the two mp_cat scale factors (models.py:78-84) into the
+ * input-channel segments [0,split) and [split,cin); de-interleave the qkv /
+ * kv output-channel order c = h*P*D + d*P + j  ->  h*P*D + j*D + d
+ * (models.py:192,285) so one (head, q|k|v) vector is contiguous.
+ * dst_dtype VB_F32 writes the unpadded fp32 matrix [cout][cin*taps] instead
+ * (used by the small embedding linears, models.py:123).
+ * ------------------------------------------------------------------------ */
+typedef struct vb_weight_prep_desc {
+  const void* src; /* [cout][cin][taps] contiguous */
+  void* dst;
+  int32_t src_dtype; /* vb_dtype */
+  int32_t dst_dtype; /* VB_BF16 (padded, repacked) or VB_F32 (plain) */
+  int32_t cout, cin, taps;
+  int32_t cout_pad; /* rows of dst (>= cout, extra rows zero) */
+  int32_t split;    /* = cin when there is a single input segment */
+  int32_t seg_a_pad, seg_b_pad; /* padded channel extents of the two segments in dst */
+  int32_t perm_parts, perm_dim; /* 0,0 = keep order; (3,D) qkv; (2,D) kv */
+  float gain;
+  float scale_a, scale_b;
+} vb_weight_prep_desc;
+int vb_weight_prep(const vb_weight_prep_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Implicit-GEMM convolution (3x3 same-pad or 1x1) on tcgen05/TMEM fed by TMA —
+ * replaces F.conv2d in MPConv.forward (models.py:126) together with the
+ * pointwise ops the reference runs around it (Block.forward, models.py:165-206):
+ *   flags VB_F_MODSILU : v = mp_silu(v * mod[b][c])                 (:175-176)
+ *   flags VB_F_RESIDUAL: v = mp_sum(res, v, res_t)                  (:184,202)
+ *   flags VB_F_CLIP    : v = clamp(v, -clip, clip)                  (:204-205)
+ *   epi  VB_EPI_QKVNORM: per-(token, head, q|k|v) normalize over D and scatter
+ *                        to [B][heads][seq][D] bf16 tensors         (:192-193,283-297)
+ * GEMM view: M = B*H*W pixels, N = cout, K = taps*(cin_pad+cin2_pad).
+ * ------------------------------------------------------------------------ */
+enum { VB_EPI_PLAIN = 0, VB_EPI_QKVNORM = 1 };
+enum { VB_F_MODSILU = 1, VB_F_RESIDUAL = 2, VB_F_CLIP = 4 };
+
+typedef struct vb_conv_desc {
+  const void* x;  /* bf16 NHWC [B][H][W][cin_pad] */
+  const void* x2; /* optional second channel segment (mp_cat folded into K), bf16 NHWC [B][H][W][cin2_pad] */
+  const void* w;  /* bf16 [cout_pad][taps*(cin_pad+cin2_pad)] from vb_weight_prep */
+  const float* mod; /* fp32 [B][mod_stride], pre-offset to this layer's first channel */
+  const float* res; /* fp32 [B*H*W][ld_res] */
+  float* out_f32;   /* optional fp32 [B*H*W][ld_f32] */
+  void* out_bf16;   /* optional bf16 [B*H*W][ld_bf16] */
+  void* out_silu;   /* optional bf16 [B*H*W][ld_silu] = mp_silu(result) */
+  void* part_out[3]; /* QKVNORM: q,k,v (or k,v) bf16 [B/seg_div][heads][part_seq[j]][head_dim] */
+  int32_t B, H, W;
+  int32_t cin_pad, cin2_pad;
+  int32_t cout_pad; /* multiple of block_n */
+  int32_t taps;     /* 1 or 9 */
+  int32_t block_n;  /* 16..256, multiple of 16 */
+  int32_t epi_mode, flags;
+  int32_t mod_stride, ld_res, ld_f32, ld_bf16, ld_silu;
+  int32_t head_dim, parts, seg_div;
+  int32_t part_seq[3]; /* total sequence length of each destination */
+  int32_t part_off[3]; /* first sequence slot written by image segment 0 */
+  float res_t, clip;
+} vb_conv_desc;
+int vb_conv(const vb_conv_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Fused cosine attention — replaces einsum/softmax/einsum (snapshot
+ * experiments/code/training/models.py:190-191,274-280) and
+ * F.scaled_dot_product_attention (current tree training/models.py:198,305):
+ *   y[b][s][h*D+d] = sum_k softmax_k(q.k/sqrt(D)) v ; q,k,v already normalised.
+ * zero_keys extra keys with k = v = 0 are accounted for analytically (the
+ * unconditional gnet's all-zero source features, snapshot models.py:616-625).
+ * ------------------------------------------------------------------------ */
+typedef struct vb_attn_desc {
+  const void* q; /* bf16 [B][heads][sq][D] */
+  const void* k; /* bf16 [B][heads][sk][D] */
+  const void* v; /* bf16 [B][heads][sk][D] */
+  void* y;       /* bf16 [B][sq][heads*D] (NHWC) */
+  int32_t B, heads, sq, sk, head_dim;
+  int32_t zero_keys;
+} vb_attn_desc;
+int vb_attn(const vb_attn_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Fused elementwise passes (vectorised, coalesced; warp-shuffle reductions).
+ * kind selects the pass; unused fields are ignored.  N = pixels, C = channels.
+ *   VB_EW_PIXNORM   out_f32 = x/(eps+||x||_C/sqrt(C)); out_silu = mp_silu(out)   (models.py:171, :37-42)
+ *   VB_EW_DOWN_PIXNORM  2x2 mean pool (resample 'down', :48-61) then PIXNORM
+ *   VB_EW_UP        nearest x2 (resample 'up'); out_f32 = up(x); out_silu = mp_silu(up(x))
+ *   VB_EW_CAT       mp_cat(a,b,t) (:78-84): out_bf16 = cat; out_silu = mp_silu(cat)
+ *   VB_EW_SILU      out_silu = mp_silu(x) (+ optional bf16 copy)
+ * ------------------------------------------------------------------------ */
+enum { VB_EW_PIXNORM = 0, VB_EW_DOWN_PIXNORM = 1, VB_EW_UP = 2, VB_EW_CAT = 3, VB_EW_SILU = 4 };
+typedef struct vb_ew_desc {
+  const float* a; /* fp32 [pixels_in][ca] */
+  const float* b; /* fp32 [pixels][cb] (CAT) */
+  float* out_f32;
+  void* out_bf16;
+  void* out_silu;
+  int32_t kind;
+  int32_t B, H, W; /* OUTPUT spatial extent */
+  int32_t ca, cb;
+  float wa, wb; /* CAT scale factors */
+} vb_ew_desc;
+int vb_eltwise(const vb_ew_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Embedding path — MPFourier (models.py:96-101), emb_noise / emb_label linears
+ * (:123), mp_sum(.., label_balance) and mp_silu (UNet.forward :388-391), then
+ * every block's  c = emb_linear(emb, gain=emb_gain) + 1  (:175) in one pass:
+ *   emb[b] = mp_silu(mp_sum(Wn . fourier(c_noise[b]), Wl . geom[b], t))
+ *   mod[b][j] = Wmod[j] . emb[b] + 1          (Wmod = all blocks' emb_linear, stacked)
+ * ------------------------------------------------------------------------ */
+typedef struct vb_emb_desc {
+  const float* sigma;  /* [B] or [1] (sigma_n) */
+  const float* geom;   /* [B][label_dim] or NULL */
+  const float* freqs;  /* [cnoise] */
+  const float* phases; /* [cnoise] */
+  const float* w_noise; /* fp32 [cemb][cnoise] prepared */
+  const float* w_label; /* fp32 [cemb][label_dim] prepared, or NULL */
+  const float* w_mod;   /* fp32 [mod_total][cemb] prepared */
+  float* emb;           /* scratch [B][cemb] */
+  float* mod;           /* out [B][mod_total] */
+  int32_t B, sigma_n, sigma_stride, cnoise, cemb, label_dim, mod_total;
+  int32_t geom_rows;    /* rows available in geom (1 => broadcast) */
+  float label_balance;
+  float noise_scale;    /* 1 normally; 0 for no_time_enc encoders (c_noise*0) */
+  float geom_scale;     /* 1 normally; 0 for uncond (geometry*0) */
+} vb_emb_desc;
+int vb_embed(const vb_emb_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------
+ * EDM preconditioning (NVPrecond.forward, snapshot models.py:588-595,608-611,632)
+ *   vb_precond_in : x_in = c_in(sigma)*x  -> NHWC bf16, + ones channel, + SR
+ *                   conditioning channels (cond + noisy_sr*noise), zero padded to cpad
+ *   vb_precond_out: D = c_skip*x + c_out*F   (fp32 NCHW)
+ * ------------------------------------------------------------------------ */
+typedef struct vb_precond_in_desc {
+  const float* x;     /* fp32 NCHW [B][3][R][R] (image stride img_stride floats) */
+  const float* cond;  /* optional fp32 NCHW [B][3][R][R] */
+  const float* noise; /* optional fp32 NCHW [B][3][R][R], added as noisy_sr*noise */
+  const float* sigma; /* [B] or [1]; NULL => no c_in scaling (encoder input) */
+  void* out;          /* bf16 NHWC [B][R][R][cpad] */
+  int32_t B, R, cpad, sigma_n, sigma_stride;
+  int64_t img_stride; /* elements between consecutive images of x (allows x[::2]) */
+  float sigma_data, noisy_sr;
+} vb_precond_in_desc;
+int vb_precond_in(const vb_precond_in_desc* d, void* stream);
+
+typedef struct vb_precond_out_desc {
+  const float* x;     /* fp32 NCHW noisy input */
+  const float* f;     /* fp32 NHWC [B][R][R][ldf] raw network output (3 valid channels) */
+  const float* sigma; /* [B] or [1] */
+  float* d_out;       /* fp32 NCHW [B][3][R][R] */
+  int32_t B, R, ldf, sigma_n, sigma_stride;
+  int64_t img_stride;
+  float sigma_data;
+} vb_precond_out_desc;
+int vb_precond_out(const vb_precond_out_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Heun step + autoguidance (edm_sampler, generate_images.py:62,93-114):
+ *   D  = lerp(D_g, D_n, guidance)              (D_g may be NULL)
+ *   phase 0 (Euler):  d_cur = (x_hat - D)/t_hat;  x_next = x_hat + (t_next-t_hat)*d_cur
+ *   phase 1 (2nd order): d' = (x_next - D)/t_next; x_next = x_hat + (t_next-t_hat)*(d_cur+d')/2
+ * all fp32, elementwise over n values.
+ * ------------------------------------------------------------------------ */
+typedef struct vb_heun_desc {
+  const float* d_net;
+  const float* d_gnet; /* or NULL */
+  const float* x_hat;
+  float* d_cur;  /* phase 0: written; phase 1: read */
+  float* x_next; /* phase 0: written; phase 1: read then overwritten */
+  int64_t n;
+  int32_t phase;
+  float guidance, t_hat, t_next;
+} vb_heun_desc;
+int vb_heun(const vb_heun_desc* d, void* stream);
+
+/* Pixel codec (training/encoders.py:58-62). */
+int vb_encode_u8(const uint8_t* src, float* dst, int64_t n, void* stream); /* x/127.5 - 1 */
+int vb_decode_u8(const float* src, uint8_t* dst, int64_t n, void* stream); /* clip(x*127.5+128) */
+
+/* ------------------------------------------------------------------------
+ * Plans: a recorded sequence of the ops above over fixed buffers, replayed per
+ * denoiser call (optionally as one CUDA graph).  TMA descriptors are encoded
+ * once when an op is added.
+ * ------------------------------------------------------------------------ */
+typedef struct vb_plan vb_plan;
+int vb_plan_create(vb_plan** out);
+void vb_plan_destroy(vb_plan* p);
+int vb_plan_add_conv(vb_plan* p, const vb_conv_desc* d);
+int vb_plan_add_attn(vb_plan* p, const vb_attn_desc* d);
+int vb_plan_add_eltwise(vb_plan* p, const vb_ew_desc* d);
+int vb_plan_add_embed(vb_plan* p, const vb_emb_desc* d);
+int vb_plan_add_precond_in(vb_plan* p, const vb_precond_in_desc* d);
+int vb_plan_add_precond_out(vb_plan* p, const vb_precond_out_desc* d);
+int vb_plan_add_heun(vb_plan* p, const vb_heun_desc* d);
+int vb_plan_num_ops(const vb_plan* p);
+/* Run ops [first, last) eagerly on stream. last < 0 means "to the end". */
+int vb_plan_run(vb_plan* p, int first, int last, void* stream);
+/* Capture the whole plan into a CUDA graph (once), then launch it. */
+int vb_plan_launch_graph(vb_plan* p, void* stream);
+/* Algorithmic work of one plan run: kind 0 = GEMM+attention FLOPs, 1 = kernel launches. */
+double vb_plan_query(const vb_plan* p, int kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIVID_B200_H_ */

@@ -1,0 +1,132 @@
+"""ctypes binding of libvividb200.so — the C ABI declared in include/vivid_b200.h.
+
+The library is GPU-only.  Importing this module never touches CUDA; `lib()` loads the
+shared object (building it first if the sources are newer) and raises if it is missing.
+There is deliberately no CPU fallback: a product call without the CUDA extension fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvividb200.so")
+
+VB_F32, VB_F16, VB_BF16 = 0, 1, 2
+VB_EPI_PLAIN, VB_EPI_QKVNORM = 0, 1
+VB_F_MODSILU, VB_F_RESIDUAL, VB_F_CLIP = 1, 2, 4
+VB_EW_PIXNORM, VB_EW_DOWN_PIXNORM, VB_EW_UP, VB_EW_CAT, VB_EW_SILU = 0, 1, 2, 3, 4
+
+i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+
+class WeightPrepDesc(C.Structure):
+    _fields_ = [("src", vp), ("dst", vp), ("src_dtype", i32), ("dst_dtype", i32), ("cout", i32), ("cin", i32),
+                ("taps", i32), ("cout_pad", i32), ("split", i32), ("seg_a_pad", i32), ("seg_b_pad", i32),
+                ("perm_parts", i32), ("perm_dim", i32), ("gain", f32), ("scale_a", f32), ("scale_b", f32)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("x", vp), ("x2", vp), ("w", vp), ("mod", vp), ("res", vp), ("out_f32", vp), ("out_bf16", vp),
+                ("out_silu", vp), ("part_out", vp * 3), ("B", i32), ("H", i32), ("W", i32), ("cin_pad", i32),
+                ("cin2_pad", i32), ("cout_pad", i32), ("taps", i32), ("block_n", i32), ("epi_mode", i32),
+                ("flags", i32), ("mod_stride", i32), ("ld_res", i32), ("ld_f32", i32), ("ld_bf16", i32),
+                ("ld_silu", i32), ("head_dim", i32), ("parts", i32), ("seg_div", i32), ("part_seq", i32 * 3),
+                ("part_off", i32 * 3), ("res_t", f32), ("clip", f32)]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [("q", vp), ("k", vp), ("v", vp), ("y", vp), ("B", i32), ("heads", i32), ("sq", i32), ("sk", i32),
+                ("head_dim", i32), ("zero_keys", i32)]
+
+
+class EwDesc(C.Structure):
+    _fields_ = [("a", vp), ("b", vp), ("out_f32", vp), ("out_bf16", vp), ("out_silu", vp), ("kind", i32),
+                ("B", i32), ("H", i32), ("W", i32), ("ca", i32), ("cb", i32), ("wa", f32), ("wb", f32)]
+
+
+class EmbDesc(C.Structure):
+    _fields_ = [("sigma", vp), ("geom", vp), ("freqs", vp), ("phases", vp), ("w_noise", vp), ("w_label", vp),
+                ("w_mod", vp), ("emb", vp), ("mod", vp), ("B", i32), ("sigma_n", i32), ("sigma_stride", i32),
+                ("cnoise", i32), ("cemb", i32), ("label_dim", i32), ("mod_total", i32), ("geom_rows", i32),
+                ("label_balance", f32), ("noise_scale", f32), ("geom_scale", f32)]
+
+
+class PrecondInDesc(C.Structure):
+    _fields_ = [("x", vp), ("cond", vp), ("noise", vp), ("sigma", vp), ("out", vp), ("B", i32), ("R", i32),
+                ("cpad", i32), ("sigma_n", i32), ("sigma_stride", i32), ("img_stride", i64), ("sigma_data", f32),
+                ("noisy_sr", f32)]
+
+
+class PrecondOutDesc(C.Structure):
+    _fields_ = [("x", vp), ("f", vp), ("sigma", vp), ("d_out", vp), ("B", i32), ("R", i32), ("ldf", i32),
+                ("sigma_n", i32), ("sigma_stride", i32), ("img_stride", i64), ("sigma_data", f32)]
+
+
+class HeunDesc(C.Structure):
+    _fields_ = [("d_net", vp), ("d_gnet", vp), ("x_hat", vp), ("d_cur", vp), ("x_next", vp), ("n", i64),
+                ("phase", i32), ("guidance", f32), ("t_hat", f32), ("t_next", f32)]
+
+
+# name -> (restype, argtypes); the smoke/CPU tests check that every one of these is exported.
+SIGNATURES = {
+    "vb_last_error": (C.c_char_p, []),
+    "vb_abi_version": (C.c_int, []),
+    "vb_device_check": (C.c_int, []),
+    "vb_weight_prep": (C.c_int, [C.POINTER(WeightPrepDesc), vp]),
+    "vb_conv": (C.c_int, [C.POINTER(ConvDesc), vp]),
+    "vb_attn": (C.c_int, [C.POINTER(AttnDesc), vp]),
+    "vb_eltwise": (C.c_int, [C.POINTER(EwDesc), vp]),
+    "vb_embed": (C.c_int, [C.POINTER(EmbDesc), vp]),
+    "vb_precond_in": (C.c_int, [C.POINTER(PrecondInDesc), vp]),
+    "vb_precond_out": (C.c_int, [C.POINTER(PrecondOutDesc), vp]),
+    "vb_heun": (C.c_int, [C.POINTER(HeunDesc), vp]),
+    "vb_encode_u8": (C.c_int, [vp, vp, i64, vp]),
+    "vb_decode_u8": (C.c_int, [vp, vp, i64, vp]),
+    "vb_plan_create": (C.c_int, [C.POINTER(vp)]),
+    "vb_plan_destroy": (None, [vp]),
+    "vb_plan_add_conv": (C.c_int, [vp, C.POINTER(ConvDesc)]),
+    "vb_plan_add_attn": (C.c_int, [vp, C.POINTER(AttnDesc)]),
+    "vb_plan_add_eltwise": (C.c_int, [vp, C.POINTER(EwDesc)]),
+    "vb_plan_add_embed": (C.c_int, [vp, C.POINTER(EmbDesc)]),
+    "vb_plan_add_precond_in": (C.c_int, [vp, C.POINTER(PrecondInDesc)]),
+    "vb_plan_add_precond_out": (C.c_int, [vp, C.POINTER(PrecondOutDesc)]),
+    "vb_plan_add_heun": (C.c_int, [vp, C.POINTER(HeunDesc)]),
+    "vb_plan_num_ops": (C.c_int, [vp]),
+    "vb_plan_run": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+    "vb_plan_launch_graph": (C.c_int, [vp, vp]),
+    "vb_plan_query": (C.c_double, [vp, C.c_int]),
+}
+
+_lib = None
+
+
+class VividB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle of libvividb200.so. Raises if it cannot be loaded."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VividB200Error(
+            f"{LIB_PATH} is missing: build it with `python -m vivid_b200.build` "
+            "(vivid_b200 has no CPU fallback; the CUDA extension is required)")
+    h = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(h, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = h
+    return h
+
+
+def check(rc, what="vivid_b200 call"):
+    if rc != 0:
+        msg = lib().vb_last_error()
+        raise VividB200Error(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
