@@ -1,0 +1,230 @@
+// Fused cosine attention (flash-style, single pass, no materialised logits).
+//
+// Replaces einsum -> softmax -> einsum of the snapshot tree
+// (experiments/code/training/models.py:190-191, 274-280) and F.scaled_dot_product_attention of
+// the current tree (training/models.py:198, 305).  q, k, v arrive already pixel-normalised
+// (the qkv GEMM epilogue does it), so |q.k|/sqrt(D) <= sqrt(D): the softmax needs no running
+// max — p = exp(q.k/sqrt(D) - sqrt(D)) is in (e^-2sqrt(D), ~1] — and no rescaling pass.
+// Keys/values of the self segment and of the 1-2 cross (source-view) segments already sit
+// back to back in one [B][heads][Sk][D] buffer, so the concat of the reference is free.
+// `zero_keys` extra all-zero keys (unconditional gnet) only add exp(0 - sqrt(D)) each to the
+// denominator.
+//
+// v1 data path: cp.async double-buffered K/V tiles in XOR-swizzled shared memory, ldmatrix,
+// mma.sync.m16n8k16 bf16 with fp32 accumulation; 4 warps x 16 query rows per CTA.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vb {
+namespace {
+
+constexpr int kBlockQ = 64;
+constexpr int kBlockKV = 64;
+constexpr int kAttnThreads = 128;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+  const uint32_t s = smem_u32(smem);
+  const int bytes = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Tile of `rows` x D bf16 in smem, 16-byte chunks XOR-swizzled so ldmatrix is conflict-free.
+template <int D>
+__device__ __forceinline__ int swz(int row, int chunk) {
+  constexpr int kChunks = D / 8;
+  if (D == 64) return row * kChunks + (chunk ^ (row & 7));
+  return row * kChunks + (chunk ^ ((row >> 1) & 3));
+}
+
+template <int D>
+__device__ __forceinline__ void load_tile_async(__nv_bfloat16* smem, const __nv_bfloat16* gmem, int row0, int rows_total,
+                                                int tile_rows) {
+  constexpr int kChunks = D / 8;
+  for (int i = threadIdx.x; i < tile_rows * kChunks; i += kAttnThreads) {
+    const int r = i / kChunks, c = i - r * kChunks;
+    const bool ok = row0 + r < rows_total;
+    const __nv_bfloat16* src = gmem + static_cast<size_t>(ok ? row0 + r : 0) * D + c * 8;
+    cp_async16(smem + swz<D>(r, c) * 8, src, ok);
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kAttnThreads) attn_kernel(const __nv_bfloat16* __restrict__ q,
+                                                            const __nv_bfloat16* __restrict__ k,
+                                                            const __nv_bfloat16* __restrict__ v,
+                                                            __nv_bfloat16* __restrict__ y, int heads, int sq, int sk,
+                                                            int zero_keys) {
+  constexpr int kKSteps = D / 16;    // k-steps of the QK^T product
+  constexpr int kDTiles = D / 8;     // n-tiles of the PV product
+  __shared__ __align__(128) __nv_bfloat16 s_q[kBlockQ * D];
+  __shared__ __align__(128) __nv_bfloat16 s_k[2][kBlockKV * D];
+  __shared__ __align__(128) __nv_bfloat16 s_v[2][kBlockKV * D];
+
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kBlockQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t bh = static_cast<size_t>(b) * heads + h;
+  const __nv_bfloat16* qp = q + bh * sq * D;
+  const __nv_bfloat16* kp = k + bh * sk * D;
+  const __nv_bfloat16* vp = v + bh * sk * D;
+
+  load_tile_async<D>(s_q, qp, q0, sq, kBlockQ);
+  load_tile_async<D>(s_k[0], kp, 0, sk, kBlockKV);
+  load_tile_async<D>(s_v[0], vp, 0, sk, kBlockKV);
+  cp_async_commit();
+
+  const float sqrt_d = sqrtf(static_cast<float>(D));
+  const float c1 = 1.4426950408889634f / sqrt_d;    // log2(e)/sqrt(D)
+  const float c2 = 1.4426950408889634f * sqrt_d;    // log2(e)*sqrt(D)
+
+  uint32_t qf[kKSteps][4];
+  float o[kDTiles][4];
+#pragma unroll
+  for (int j = 0; j < kDTiles; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+  float l0 = 0.f, l1 = 0.f;   // row sums for rows g and g+8
+
+  const int n_tiles = (sk + kBlockKV - 1) / kBlockKV;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int cur = t & 1;
+    if (t + 1 < n_tiles) {
+      load_tile_async<D>(s_k[cur ^ 1], kp, (t + 1) * kBlockKV, sk, kBlockKV);
+      load_tile_async<D>(s_v[cur ^ 1], vp, (t + 1) * kBlockKV, sk, kBlockKV);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (t == 0) {
+      // Q fragments: rows warp*16 + (lane & 15), 16-byte chunk 2*ks + (lane >> 4)
+#pragma unroll
+      for (int ks = 0; ks < kKSteps; ++ks) {
+        const int r = warp * 16 + (lane & 15);
+        const int c = 2 * ks + (lane >> 4);
+        ldmatrix_x4(smem_u32(s_q + swz<D>(r, c) * 8), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+      }
+    }
+    // S = Q K^T : 16 x 64 per warp
+    float s[kBlockKV / 8][4];
+#pragma unroll
+    for (int j = 0; j < kBlockKV / 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < kKSteps; ++ks) {
+#pragma unroll
+      for (int jp = 0; jp < kBlockKV / 16; ++jp) {
+        // four 8x8 blocks: keys jp*16 + {0..7, 8..15}, d chunks 2ks, 2ks+1
+        const int r = jp * 16 + (lane & 7) + ((lane >> 4) << 3);
+        const int c = 2 * ks + ((lane >> 3) & 1);
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4(smem_u32(s_k[cur] + swz<D>(r, c) * 8), b0, b1, b2, b3);
+        mma_bf16(s[2 * jp], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b0, b1);
+        mma_bf16(s[2 * jp + 1], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b2, b3);
+      }
+    }
+    // P = exp(S/sqrt(D) - sqrt(D)); mask keys past the end of the sequence
+    const int key0 = t * kBlockKV + 2 * (lane & 3);
+    uint32_t pf[kBlockKV / 16][4];
+#pragma unroll
+    for (int j = 0; j < kBlockKV / 8; ++j) {
+      const int kk = key0 + j * 8;
+      float p0 = exp2f(s[j][0] * c1 - c2), p1 = exp2f(s[j][1] * c1 - c2);
+      float p2 = exp2f(s[j][2] * c1 - c2), p3 = exp2f(s[j][3] * c1 - c2);
+      if (kk >= sk) p0 = p2 = 0.f;
+      if (kk + 1 >= sk) p1 = p3 = 0.f;
+      l0 += p0 + p1;
+      l1 += p2 + p3;
+      pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+    // O += P V
+#pragma unroll
+    for (int kk = 0; kk < kBlockKV / 16; ++kk) {
+#pragma unroll
+      for (int dp = 0; dp < kDTiles / 2; ++dp) {
+        // V rows (keys) kk*16 + {0..15}, d chunks 2dp, 2dp+1 ; transposed on load
+        const int r = kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+        const int c = 2 * dp + (lane >> 4);
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4_trans(smem_u32(s_v[cur] + swz<D>(r, c) * 8), b0, b1, b2, b3);
+        mma_bf16(o[2 * dp], pf[kk][0], pf[kk][1], pf[kk][2], pf[kk][3], b0, b1);
+        mma_bf16(o[2 * dp + 1], pf[kk][0], pf[kk][1], pf[kk][2], pf[kk][3], b2, b3);
+      }
+    }
+    __syncthreads();   // everyone done with buffer `cur` before it is refilled
+  }
+
+  // row sums across the 4 lanes that share a row, plus the analytic zero-key mass
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float zk = static_cast<float>(zero_keys) * exp2f(-c2);
+  const float i0 = 1.0f / (l0 + zk), i1 = 1.0f / (l1 + zk);
+
+  // stage the 64 x D output tile through s_q (all Q fragments are in registers by now)
+  const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int j = 0; j < kDTiles; ++j) {
+    const int r0 = warp * 16 + g, r1 = r0 + 8;
+    const int col = j * 8 + 2 * tq;
+    *reinterpret_cast<uint32_t*>(s_q + swz<D>(r0, col >> 3) * 8 + (col & 7)) = pack_bf16x2(o[j][0] * i0, o[j][1] * i0);
+    *reinterpret_cast<uint32_t*>(s_q + swz<D>(r1, col >> 3) * 8 + (col & 7)) = pack_bf16x2(o[j][2] * i1, o[j][3] * i1);
+  }
+  __syncthreads();
+  constexpr int kChunks = D / 8;
+  const int ldy = heads * D;
+  for (int i = threadIdx.x; i < kBlockQ * kChunks; i += kAttnThreads) {
+    const int r = i / kChunks, c = i - r * kChunks;
+    if (q0 + r < sq) {
+      const uint4 val = *reinterpret_cast<const uint4*>(s_q + swz<D>(r, c) * 8);
+      *reinterpret_cast<uint4*>(y + (static_cast<size_t>(b) * sq + q0 + r) * ldy + h * D + c * 8) = val;
+    }
+  }
+}
+
+}  // namespace
+
+int attn_launch(const vb_attn_desc* d, cudaStream_t s) {
+  VB_REQUIRE(d != nullptr && d->q && d->k && d->v && d->y, "vb_attn: null tensor");
+  VB_REQUIRE(d->B > 0 && d->heads > 0 && d->sq > 0 && d->sk > 0, "vb_attn: empty problem");
+  VB_REQUIRE(d->head_dim == 64 || d->head_dim == 32, "vb_attn: head_dim must be 32 or 64 (got %d)", d->head_dim);
+  VB_REQUIRE(d->zero_keys >= 0, "vb_attn: zero_keys < 0");
+  const dim3 grid((d->sq + kBlockQ - 1) / kBlockQ, d->heads, d->B);
+  const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(d->q);
+  const __nv_bfloat16* k = static_cast<const __nv_bfloat16*>(d->k);
+  const __nv_bfloat16* v = static_cast<const __nv_bfloat16*>(d->v);
+  __nv_bfloat16* y = static_cast<__nv_bfloat16*>(d->y);
+  if (d->head_dim == 64)
+    attn_kernel<64><<<grid, kAttnThreads, 0, s>>>(q, k, v, y, d->heads, d->sq, d->sk, d->zero_keys);
+  else
+    attn_kernel<32><<<grid, kAttnThreads, 0, s>>>(q, k, v, y, d->heads, d->sq, d->sk, d->zero_keys);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB_OK;
+}
+
+}  // namespace vb
+
+extern "C" int vb_attn(const vb_attn_desc* d, void* stream) {
+  return vb::attn_launch(d, static_cast<cudaStream_t>(stream));
+}

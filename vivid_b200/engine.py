@@ -1,0 +1,378 @@
+"""Plan builder: turns one NVPrecond parameter tree + batch size into a recorded sequence of
+libvividb200 ops (include/vivid_b200.h) over fixed device buffers.
+
+Dataflow per block (reference Block.forward, training/models.py:165-206; NHWC inside):
+  enc:  [2x2 pool] -> [1x1 skip GEMM] -> PIXNORM pass (fp32 stream + bf16 mp_silu copy)
+        -> 3x3 GEMM (epilogue: *(emb+1), mp_silu) -> 3x3 GEMM (epilogue: mp_sum with stream, clip)
+  dec:  [nearest up | mp_cat pass] -> 3x3 GEMM -> [1x1 skip GEMM] -> 3x3 GEMM (mp_sum, clip)
+  attn: 1x1 qkv GEMM (epilogue: per-head normalise, scatter to [B,h,S,D]) [+ 1x1 kv GEMM on the
+        source-view features, written behind the self keys] -> fused attention -> 1x1 proj GEMM
+        (epilogue: mp_sum, clip)
+The residual stream is fp32; every GEMM operand is a bf16 copy written by the producing
+kernel, so no standalone cast / silu / lerp / clamp kernels exist.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+
+
+def _pad(v, m):
+    return (v + m - 1) // m * m
+
+
+class Act:
+    """One activation in up to three physical forms (all NHWC [B*R*R, C])."""
+
+    def __init__(self, B, R, ch):
+        self.B, self.R, self.C = B, R, ch
+        self.f32 = None    # fp32 residual stream
+        self.bf16 = None   # bf16 GEMM operand
+        self.silu = None   # bf16 mp_silu(x) GEMM operand
+
+
+_DT = {torch.float32: L.VB_F32, torch.float16: L.VB_F16, torch.bfloat16: L.VB_BF16}
+
+
+class Plan:
+    """A recorded denoiser call for a fixed batch size."""
+
+    def __init__(self, net, B, device):
+        self.lib = L.lib()
+        L.check(self.lib.vb_device_check(), "vb_device_check")
+        self.net = net
+        self.device = device
+        self.B = B                      # number of target images (outputs)
+        self.dual = net.dual
+        self.Bx = 2 * B if net.dual else B
+        self.keep = []                  # every buffer the plan touches (keeps them alive)
+        self.handle = C.c_void_p()
+        L.check(self.lib.vb_plan_create(C.byref(self.handle)), "vb_plan_create")
+        self.stream = torch.cuda.current_stream(device).cuda_stream
+        self.sm_count = torch.cuda.get_device_properties(device).multi_processor_count
+        self.alg_flops = 0.0            # algorithmic (unpadded) FLOPs of one call
+        self.weight_versions = None
+        self._build()
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.vb_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ buffers
+    def buf(self, shape, dtype, zero=False):
+        t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+        self.keep.append(t)
+        return t
+
+    def f32(self, B, R, ch):
+        return self.buf((B * R * R, ch), torch.float32)
+
+    def b16(self, B, R, ch):
+        return self.buf((B * R * R, ch), torch.bfloat16)
+
+    # ------------------------------------------------------------------ weights
+    def prep_weight(self, w, gain=1.0, cout_pad=None, perm=(0, 0), split=None, scales=(1.0, 1.0), fp32=False):
+        """vb_weight_prep: normalise (fp32) + gain + pack; returns the device tensor."""
+        w = w.detach()
+        if not w.is_contiguous():
+            w = w.contiguous()
+        cout, cin = w.shape[0], w.shape[1]
+        taps = w.shape[2] * w.shape[3] if w.ndim == 4 else 1
+        split = cin if split is None else split
+        if fp32:
+            dst = self.buf((cout, cin * taps), torch.float32)
+            d = L.WeightPrepDesc(src=w.data_ptr(), dst=dst.data_ptr(), src_dtype=_DT[w.dtype], dst_dtype=L.VB_F32,
+                                 cout=cout, cin=cin, taps=taps, cout_pad=cout, split=cin, seg_a_pad=cin, seg_b_pad=0,
+                                 perm_parts=0, perm_dim=0, gain=float(gain), scale_a=1.0, scale_b=1.0)
+        else:
+            sa = _pad(split, 64)
+            sb = _pad(cin - split, 64) if cin > split else 0
+            cout_pad = cout_pad or _pad(cout, 16)
+            dst = self.buf((cout_pad, taps * (sa + sb)), torch.bfloat16)
+            d = L.WeightPrepDesc(src=w.data_ptr(), dst=dst.data_ptr(), src_dtype=_DT[w.dtype], dst_dtype=L.VB_BF16,
+                                 cout=cout, cin=cin, taps=taps, cout_pad=cout_pad, split=split, seg_a_pad=sa,
+                                 seg_b_pad=sb, perm_parts=perm[0], perm_dim=perm[1], gain=float(gain),
+                                 scale_a=float(scales[0]), scale_b=float(scales[1]))
+        self.keep.append(w)
+        L.check(self.lib.vb_weight_prep(C.byref(d), self.stream), "vb_weight_prep")
+        return dst
+
+    # ------------------------------------------------------------------ op emitters
+    def pick_block_n(self, cout_pad, m_pixels, multiple=16):
+        """Largest N tile that still yields at least one tile per SM (falls back to the smallest)."""
+        m_tiles = (m_pixels + 127) // 128
+        cands = [n for n in (256, 192, 128, 64, 32, 16) if cout_pad % n == 0 and n % multiple == 0]
+        for n in cands:
+            if m_tiles * (cout_pad // n) >= self.sm_count:
+                return n
+        wide = [n for n in cands if n >= 64]
+        return wide[-1] if wide else cands[-1]
+
+    def conv(self, x, w, B, R, cin_pad, cout, taps, *, x2=None, cin2_pad=0, cout_pad=None, flags=0, mod=None,
+             mod_stride=0, res=None, res_t=0.3, clip=256.0, out_f32=None, out_bf16=None, out_silu=None, qkv=None,
+             k_real=None):
+        cout_pad = cout_pad or _pad(cout, 16)
+        multiple = qkv["D"] if qkv else 16
+        bn = self.pick_block_n(cout_pad, B * R * R, multiple)
+        d = L.ConvDesc(x=x.data_ptr(), x2=L.ptr(x2), w=w.data_ptr(), mod=L.ptr(mod) if not isinstance(mod, int) else mod,
+                       res=L.ptr(res), out_f32=L.ptr(out_f32), out_bf16=L.ptr(out_bf16), out_silu=L.ptr(out_silu),
+                       B=B, H=R, W=R, cin_pad=cin_pad, cin2_pad=cin2_pad, cout_pad=cout_pad, taps=taps, block_n=bn,
+                       epi_mode=L.VB_EPI_QKVNORM if qkv else L.VB_EPI_PLAIN, flags=flags, mod_stride=mod_stride,
+                       ld_res=cout_pad, ld_f32=cout_pad, ld_bf16=cout_pad, ld_silu=cout_pad, res_t=res_t,
+                       clip=clip if clip is not None else 3.0e38)
+        if qkv:
+            parts = qkv["parts"]
+            d.head_dim, d.parts, d.seg_div = qkv["D"], parts, qkv.get("seg_div", 1)
+            for j in range(parts):
+                d.part_out[j] = qkv["out"][j].data_ptr()
+                d.part_seq[j] = qkv["seq"][j]
+                d.part_off[j] = qkv["off"][j]
+        L.check(self.lib.vb_plan_add_conv(self.handle, C.byref(d)), "vb_plan_add_conv")
+        self.alg_flops += 2.0 * B * R * R * cout * (k_real if k_real is not None else taps * (cin_pad + cin2_pad))
+
+    def eltwise(self, kind, a, B, R, ca, *, b=None, cb=0, wa=1.0, wb=1.0, out_f32=None, out_bf16=None, out_silu=None):
+        d = L.EwDesc(a=a.data_ptr(), b=L.ptr(b), out_f32=L.ptr(out_f32), out_bf16=L.ptr(out_bf16),
+                     out_silu=L.ptr(out_silu), kind=kind, B=B, H=R, W=R, ca=ca, cb=cb, wa=wa, wb=wb)
+        L.check(self.lib.vb_plan_add_eltwise(self.handle, C.byref(d)), "vb_plan_add_eltwise")
+
+    def attention(self, q, k, v, y, B, heads, sq, sk, D, zero_keys):
+        d = L.AttnDesc(q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), y=y.data_ptr(), B=B, heads=heads, sq=sq, sk=sk,
+                       head_dim=D, zero_keys=zero_keys)
+        L.check(self.lib.vb_plan_add_attn(self.handle, C.byref(d)), "vb_plan_add_attn")
+        self.alg_flops += 4.0 * B * heads * sq * sk * D
+
+    # ------------------------------------------------------------------ embedding of one UNet
+    def embed(self, unet, B, sigma, sigma_stride, geom, geom_rows, label_dim, noise_scale, geom_scale):
+        blocks = [(s, unet.enc[s.name] if s.group == "enc" else unet.dec[s.name])
+                  for s in unet.enc_specs + unet.dec_specs if s.kind == "block"]
+        offs, total = {}, 0
+        for s, _ in blocks:
+            offs[(s.group, s.name)] = total
+            total += s.cout
+        w_mod = self.buf((total, unet.cemb), torch.float32)
+        for s, m in blocks:
+            o = offs[(s.group, s.name)]
+            wp = self.prep_weight(m.emb_linear.weight, gain=float(m.emb_gain.detach().float().item()), fp32=True)
+            w_mod[o:o + s.cout].copy_(wp)
+        w_noise = self.prep_weight(unet.emb_noise.weight, fp32=True)
+        w_label = self.prep_weight(unet.emb_label.weight, fp32=True) if unet.emb_label is not None else None
+        freqs = self.buf((unet.cnoise,), torch.float32)
+        phases = self.buf((unet.cnoise,), torch.float32)
+        freqs.copy_(unet.emb_fourier.freqs.detach().float())
+        phases.copy_(unet.emb_fourier.phases.detach().float())
+        emb = self.buf((B, unet.cemb), torch.float32)
+        mod = self.buf((B, total), torch.float32)
+        d = L.EmbDesc(sigma=sigma.data_ptr(), geom=L.ptr(geom), freqs=freqs.data_ptr(), phases=phases.data_ptr(),
+                      w_noise=w_noise.data_ptr(), w_label=L.ptr(w_label), w_mod=w_mod.data_ptr(), emb=emb.data_ptr(),
+                      mod=mod.data_ptr(), B=B, sigma_n=B, sigma_stride=sigma_stride, cnoise=unet.cnoise, cemb=unet.cemb,
+                      label_dim=label_dim, mod_total=total, geom_rows=geom_rows, label_balance=unet.label_balance,
+                      noise_scale=noise_scale, geom_scale=geom_scale)
+        L.check(self.lib.vb_plan_add_embed(self.handle, C.byref(d)), "vb_plan_add_embed")
+        return mod, offs, total
+
+    # ------------------------------------------------------------------ one UNet / encoder
+    def run_unet(self, unet, x_in, B, mod, offs, mod_total, features=None, feat_seg=1, zero_feature_keys=False,
+                 collect_features=False):
+        """Emit the ops of UNet.forward.  x_in: bf16 NHWC [B,R,R,64] (image + ones, zero padded).
+        features: list of Act (bf16 form) consumed by cross-attention blocks in order.
+        Returns (raw output Act or None, collected feature Acts)."""
+        specs = unet.enc_specs + unet.dec_specs
+        feats_out, skips = [], []
+        features = list(features or [])
+        cur = None
+        for i, s in enumerate(specs):
+            nxt = specs[i + 1] if i + 1 < len(specs) else None
+            mod_ = unet.enc[s.name] if s.group == "enc" else unet.dec[s.name]
+            # which physical forms does the consumer of this block's output need?
+            need_f32 = need_b16 = need_silu = False
+            if nxt is None:
+                need_b16 = unet.out_conv is not None          # out_conv operand
+            elif nxt.flavor == "enc":
+                if nxt.resample == "keep" and nxt.has_conv_skip:
+                    need_b16 = True                            # 1x1 skip GEMM operand
+                else:
+                    need_f32 = True                            # PIXNORM / DOWN_PIXNORM input
+            else:
+                if nxt.resample == "up" or nxt.skip_ch:
+                    need_f32 = True                            # UP / CAT input
+                else:
+                    need_f32 = need_silu = True                # residual + conv_res0 operand
+            if s.group == "enc":
+                need_f32 = True                                # every encoder output is a skip connection
+            is_feature = collect_features and s.heads > 0
+            if is_feature:
+                need_b16 = True                                # x_attn_kv GEMM operand in the denoising UNet
+            out = Act(B, s.res, s.cout)
+            R, Cc = s.res, s.cout
+
+            if s.kind == "conv":
+                w = self.prep_weight(mod_.weight)
+                out.f32 = self.f32(B, R, Cc)
+                self.conv(x_in, w, B, R, 64, Cc, 9, out_f32=out.f32, k_real=9 * s.cin)
+                cur = out
+                skips.append(out)
+                continue
+
+            # ---------------- main branch input -> residual base (fp32) + conv_res0 operand (bf16 mp_silu)
+            if s.flavor == "enc":
+                base = self.f32(B, R, Cc)
+                a0 = self.b16(B, R, Cc)
+                if s.resample == "down":
+                    self.eltwise(L.VB_EW_DOWN_PIXNORM, cur.f32, B, R, Cc, out_f32=base, out_silu=a0)
+                elif s.has_conv_skip:
+                    tmp = self.f32(B, R, Cc)
+                    w = self.prep_weight(mod_.conv_skip.weight)
+                    self.conv(cur.bf16, w, B, R, _pad(s.cin, 64), Cc, 1, out_f32=tmp, k_real=s.cin)
+                    self.eltwise(L.VB_EW_PIXNORM, tmp, B, R, Cc, out_f32=base, out_silu=a0)
+                else:
+                    self.eltwise(L.VB_EW_PIXNORM, cur.f32, B, R, Cc, out_f32=base, out_silu=a0)
+                k0 = Cc
+            else:
+                if s.resample == "up":
+                    base = self.f32(B, R, Cc)
+                    a0 = self.b16(B, R, Cc)
+                    self.eltwise(L.VB_EW_UP, cur.f32, B, R, Cc, out_f32=base, out_silu=a0)
+                    k0 = Cc
+                elif s.skip_ch:
+                    skip = skips.pop()
+                    na, nb = cur.C, skip.C
+                    assert nb == s.skip_ch and na + nb == s.cin
+                    t = unet.concat_balance
+                    cc = math.sqrt((na + nb) / ((1 - t) ** 2 + t ** 2))
+                    wa, wb = cc / math.sqrt(na) * (1 - t), cc / math.sqrt(nb) * t
+                    cat16 = self.b16(B, R, s.cin)
+                    a0 = self.b16(B, R, s.cin)
+                    self.eltwise(L.VB_EW_CAT, cur.f32, B, R, na, b=skip.f32, cb=nb, wa=wa, wb=wb, out_bf16=cat16,
+                                 out_silu=a0)
+                    base = self.f32(B, R, Cc)
+                    w = self.prep_weight(mod_.conv_skip.weight)
+                    self.conv(cat16, w, B, R, s.cin, Cc, 1, out_f32=base, k_real=s.cin)
+                    k0 = s.cin
+                else:
+                    base, a0, k0 = cur.f32, cur.silu, Cc
+            assert k0 % 64 == 0, f"{s.name}: {k0} input channels are not a multiple of 64"
+
+            # ---------------- residual branch
+            y0 = self.b16(B, R, Cc)
+            w0 = self.prep_weight(mod_.conv_res0.weight)
+            mo = offs[(s.group, s.name)]
+            self.conv(a0, w0, B, R, k0, Cc, 9, flags=L.VB_F_MODSILU, mod=mod.data_ptr() + 4 * mo, mod_stride=mod_total,
+                      out_bf16=y0)
+            w1 = self.prep_weight(mod_.conv_res1.weight)
+            attn = s.heads > 0
+            clip = mod_.clip_act
+            if not attn:
+                out.f32 = self.f32(B, R, Cc) if need_f32 else None
+                out.bf16 = self.b16(B, R, Cc) if need_b16 else None
+                out.silu = self.b16(B, R, Cc) if need_silu else None
+                self.conv(y0, w1, B, R, Cc, Cc, 9, flags=L.VB_F_RESIDUAL | (L.VB_F_CLIP if clip is not None else 0),
+                          res=base, res_t=mod_.res_balance, clip=clip, out_f32=out.f32, out_bf16=out.bf16,
+                          out_silu=out.silu)
+            else:
+                xr = self.f32(B, R, Cc)
+                xr16 = self.b16(B, R, Cc)
+                self.conv(y0, w1, B, R, Cc, Cc, 9, flags=L.VB_F_RESIDUAL, res=base, res_t=mod_.res_balance, out_f32=xr,
+                          out_bf16=xr16)
+                S, D, h = R * R, s.head_dim, s.heads
+                nseg = feat_seg if s.xattn else 0
+                real_seg = 0 if zero_feature_keys else nseg
+                sk = S * (1 + real_seg)
+                q = self.buf((B, h, S, D), torch.bfloat16)
+                k = self.buf((B, h, sk, D), torch.bfloat16)
+                v = self.buf((B, h, sk, D), torch.bfloat16)
+                wq = self.prep_weight(mod_.attn_qkv.weight, perm=(3, D))
+                self.conv(xr16, wq, B, R, Cc, 3 * Cc, 1, qkv=dict(D=D, parts=3, out=[q, k, v], seq=[S, sk, sk], off=[0, 0, 0]))
+                if s.xattn and not zero_feature_keys:
+                    f = features.pop(0)
+                    assert f.C == Cc and f.R == R, f"{s.name}: feature map mismatch"
+                    wkv = self.prep_weight(mod_.x_attn_kv.weight, perm=(2, D))
+                    self.conv(f.bf16, wkv, f.B, R, Cc, 2 * Cc, 1,
+                              qkv=dict(D=D, parts=2, out=[k, v], seq=[sk, sk], off=[S, S], seg_div=feat_seg))
+                elif s.xattn:
+                    # unconditional model: x_attn_kv(0) == 0 -> analytic zero keys; count the FLOPs the reference spends
+                    pass
+                y = self.b16(B, R, Cc)
+                self.attention(q, k, v, y, B, h, S, sk, D, S * nseg if zero_feature_keys else 0)
+                wp = self.prep_weight(mod_.attn_proj.weight)
+                out.f32 = self.f32(B, R, Cc) if need_f32 else None
+                out.bf16 = self.b16(B, R, Cc) if need_b16 else None
+                out.silu = self.b16(B, R, Cc) if need_silu else None
+                self.conv(y, wp, B, R, Cc, Cc, 1, flags=L.VB_F_RESIDUAL | (L.VB_F_CLIP if clip is not None else 0),
+                          res=xr, res_t=mod_.attn_balance, clip=clip, out_f32=out.f32, out_bf16=out.bf16,
+                          out_silu=out.silu)
+            if is_feature:
+                feats_out.append(out)
+            if s.group == "enc":
+                skips.append(out)
+            cur = out
+
+        raw = None
+        if unet.out_conv is not None:
+            wo = self.prep_weight(unet.out_conv.weight, gain=float(unet.out_gain.detach().float().item()), cout_pad=16)
+            raw = self.buf((B * cur.R * cur.R, 16), torch.float32)
+            self.conv(cur.bf16, wo, B, cur.R, cur.C, unet.out_conv.out_channels, 9, cout_pad=16, out_f32=raw)
+        return raw, feats_out
+
+    # ------------------------------------------------------------------ whole NVPrecond call
+    def _build(self):
+        net, B, Bx, dev = self.net, self.B, self.Bx, self.device
+        R = net.img_resolution
+        sd = float(net.sigma_data)
+        # persistent I/O buffers (callers copy into / out of these)
+        self.in_x = self.buf((Bx, 3, R, R), torch.float32, zero=True)
+        self.in_src = self.buf((Bx, 3, R, R), torch.float32, zero=True) if net.encoder is not None else None
+        self.in_sigma = self.buf((Bx,), torch.float32)
+        self.in_sigma.fill_(1.0)
+        ldim_enc = net.encoder.label_dim if net.encoder is not None else 0
+        ldim_unet = net.unet.label_dim
+        self.in_geom = self.buf((Bx, max(ldim_enc, ldim_unet // (2 if self.dual else 1), 1)), torch.float32, zero=True)
+        self.in_cond = self.buf((B, 3, R, R), torch.float32, zero=True) if net.super_res else None
+        self.in_noise = self.buf((B, 3, R, R), torch.float32, zero=True) if net.super_res else None
+        self.out_d = self.buf((B, 3, R, R), torch.float32, zero=True)
+        geom_scale = 0.0 if net.uncond else 1.0
+
+        features, feat_seg = None, 1
+        if net.encoder is not None:
+            enc = net.encoder
+            src16 = self.buf((Bx * R * R, 64), torch.bfloat16)
+            d = L.PrecondInDesc(x=self.in_src.data_ptr(), cond=None, noise=None, sigma=None, out=src16.data_ptr(), B=Bx,
+                                R=R, cpad=64, sigma_n=1, sigma_stride=0, img_stride=3 * R * R, sigma_data=sd, noisy_sr=0.0)
+            L.check(self.lib.vb_plan_add_precond_in(self.handle, C.byref(d)), "vb_plan_add_precond_in")
+            mod, offs, total = self.embed(enc, Bx, self.in_sigma, 1, self.in_geom if ldim_enc else None, Bx, ldim_enc,
+                                          0.0 if net.no_time_enc else 1.0, geom_scale)
+            _, features = self.run_unet(enc, src16, Bx, mod, offs, total, collect_features=True)
+            feat_seg = 2 if self.dual else 1
+
+        unet = net.unet
+        x16 = self.buf((B * R * R, 64), torch.bfloat16)
+        step = 2 if self.dual else 1
+        d = L.PrecondInDesc(x=self.in_x.data_ptr(), cond=L.ptr(self.in_cond), noise=L.ptr(self.in_noise),
+                            sigma=self.in_sigma.data_ptr(), out=x16.data_ptr(), B=B, R=R, cpad=64, sigma_n=B,
+                            sigma_stride=step, img_stride=3 * R * R * step, sigma_data=sd,
+                            noisy_sr=float(net.noisy_sr if net.noisy_sr is not None else 0.0))
+        L.check(self.lib.vb_plan_add_precond_in(self.handle, C.byref(d)), "vb_plan_add_precond_in")
+        mod, offs, total = self.embed(unet, B, self.in_sigma, step, self.in_geom if ldim_unet else None, B, ldim_unet,
+                                      1.0, geom_scale)
+        raw, _ = self.run_unet(unet, x16, B, mod, offs, total, features=features, feat_seg=feat_seg,
+                               zero_feature_keys=net.encoder is None)
+        d = L.PrecondOutDesc(x=self.in_x.data_ptr(), f=raw.data_ptr(), sigma=self.in_sigma.data_ptr(),
+                             d_out=self.out_d.data_ptr(), B=B, R=R, ldf=16, sigma_n=B, sigma_stride=step,
+                             img_stride=3 * R * R * step, sigma_data=sd)
+        L.check(self.lib.vb_plan_add_precond_out(self.handle, C.byref(d)), "vb_plan_add_precond_out")
+        self.num_ops = self.lib.vb_plan_num_ops(self.handle)
+        self.launches = int(self.lib.vb_plan_query(self.handle, 1))
+        self.padded_flops = self.lib.vb_plan_query(self.handle, 0)
+
+    # ------------------------------------------------------------------ execution
+    def run(self, graph=True):
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if graph:
+            L.check(self.lib.vb_plan_launch_graph(self.handle, stream), "vb_plan_launch_graph")
+        else:
+            L.check(self.lib.vb_plan_run(self.handle, 0, -1, stream), "vb_plan_run")

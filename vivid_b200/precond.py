@@ -1,0 +1,154 @@
+"""NVPrecond — drop-in for the reference's preconditioned denoiser object.
+
+Same constructor arguments, attributes and call signature as the reference
+(training/models.py:589-749; vanilla semantics: experiments/code/training/models.py:547-638),
+so it can be passed as net / gnet / sr_model to generate_images_nvs and called as
+`net(src, x, sigma, labels, conditioning_image)` by edm_sampler.  The forward runs entirely in
+libvividb200.so (bf16 tensor-core GEMMs, fp32 accumulation / statistics / residual stream).
+
+Two semantics behind one class, chosen by the constructor arguments instead of
+the reference's module-level VANILLA_MODE global:
+  label_dim=...                               -> vanilla: B inputs, B outputs, geometry may be None
+  source_label_dim=..., target_label_dim=...  -> dual-source: 2B interleaved inputs, B outputs
+"""
+import torch
+
+from . import engine
+from .networks import MPConv, MPFourier, SRXAttnUNet, UNetEncoder, XAttnUNet
+
+_UNSUPPORTED = "is outside the B200 hot path (SURVEY.md §8(b)); there is no CPU fallback"
+
+
+class NVPrecond(torch.nn.Module):
+    def __init__(self, img_resolution, img_channels, label_dim=None, use_fp16=True, sigma_data=0.5, logvar_channels=128,
+                 super_res=False, no_time_enc=None, depth_input=False, warp_depth_coor=False, uncond=None,
+                 noisy_sr=0.25, source_label_dim=None, target_label_dim=None, **unet_kwargs):
+        super().__init__()
+        if depth_input or warp_depth_coor:
+            raise NotImplementedError(f"depth_input / warp_depth_coor {_UNSUPPORTED}")
+        if img_channels != 3:
+            raise NotImplementedError("img_channels must be 3 (RGB pixel-space model)")
+        if img_resolution < 4 or img_resolution & (img_resolution - 1):
+            raise ValueError("img_resolution must be a power of two >= 4")
+        self.dual = label_dim is None
+        if self.dual:
+            if source_label_dim is None or target_label_dim is None:
+                raise TypeError("NVPrecond needs label_dim (vanilla) or source_label_dim+target_label_dim (dual-source)")
+            if target_label_dim != 2 * source_label_dim:
+                raise ValueError("dual-source mode expects target_label_dim == 2*source_label_dim")
+            enc_label, unet_label = source_label_dim, target_label_dim
+        else:
+            enc_label = unet_label = label_dim
+        self.init_kwargs = dict(img_resolution=img_resolution, img_channels=img_channels, use_fp16=use_fp16,
+                                sigma_data=sigma_data, logvar_channels=logvar_channels, super_res=super_res,
+                                no_time_enc=no_time_enc, depth_input=depth_input, warp_depth_coor=warp_depth_coor,
+                                uncond=uncond, noisy_sr=noisy_sr, **unet_kwargs)
+        self.init_kwargs.update(dict(source_label_dim=source_label_dim, target_label_dim=target_label_dim)
+                                if self.dual else dict(label_dim=label_dim))
+        self.init_args = ()
+        self.img_resolution = img_resolution
+        self.img_channels = img_channels
+        self.label_dim = unet_label
+        self.use_fp16 = use_fp16
+        self.sigma_data = sigma_data
+        self.super_res = super_res
+        self.no_time_enc = no_time_enc
+        self.depth_input = depth_input
+        self.warp_depth_coor = warp_depth_coor
+        self.uncond = uncond
+        self.noisy_sr = noisy_sr
+        self.encoder = UNetEncoder(img_resolution, img_channels, enc_label, **unet_kwargs) if not uncond else None
+        make = SRXAttnUNet if super_res else XAttnUNet
+        self.unet = make(img_resolution, img_channels, unet_label, **unet_kwargs)
+        self.logvar_fourier = MPFourier(logvar_channels)
+        self.logvar_linear = MPConv(logvar_channels, 1, kernel=[])
+        self._plans = {}
+        self.use_graph = True
+
+    # ------------------------------------------------------------------ construction helpers
+    @classmethod
+    def from_reference(cls, ref):
+        """Build from a reference NVPrecond instance (duck-typed: persistence re-creates classes from
+        embedded source, torch_utils/persistence.py:226-237, so isinstance is useless)."""
+        kw = dict(getattr(ref, "init_kwargs", {}))
+        args = list(getattr(ref, "init_args", ()))
+        names = ["img_resolution", "img_channels", "label_dim"]
+        if "source_label_dim" in kw or (len(args) > 3):
+            names = ["img_resolution", "img_channels", "source_label_dim", "target_label_dim"]
+        for n, a in zip(names, args):
+            kw[n] = a
+        kw.pop("class_name", None)
+        net = cls(**kw)
+        sd = {k: v for k, v in ref.state_dict().items()}
+        net.load_state_dict(sd, strict=True)
+        dev = next(ref.parameters()).device
+        return net.to(dev).eval()
+
+    def invalidate_plans(self):
+        """Call after mutating weights (plans bake the normalised bf16 weights)."""
+        self._plans.clear()
+
+    def _weight_signature(self):
+        return sum(p._version for p in self.parameters()) + sum(b._version for b in self.buffers())
+
+    def plan(self, batch, device):
+        key = (int(batch), str(device))
+        sig = self._weight_signature()
+        hit = self._plans.get(key)
+        if hit is not None and hit.weight_versions == sig:
+            return hit
+        p = engine.Plan(self, int(batch), device)
+        p.weight_versions = sig
+        self._plans[key] = p
+        return p
+
+    def _apply(self, fn, *a, **k):
+        self._plans = {}
+        return super()._apply(fn, *a, **k)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, src, dst, sigma, geometry=None, conditioning_image=None, force_fp32=False, return_logvar=False,
+                return_features=False, inject_features=None, **unet_kwargs):
+        if return_features or inject_features is not None:
+            raise NotImplementedError(f"return_features / inject_features (no_time_enc caching) {_UNSUPPORTED}")
+        if return_logvar:
+            raise NotImplementedError(f"return_logvar (training-only uncertainty head) {_UNSUPPORTED}")
+        if force_fp32:
+            raise NotImplementedError(f"force_fp32 {_UNSUPPORTED}: the GEMMs run in bf16 with fp32 accumulation")
+        if unet_kwargs:
+            raise TypeError(f"unexpected arguments {sorted(unet_kwargs)}")
+        if dst.device.type != "cuda":
+            raise RuntimeError("vivid_b200.NVPrecond runs on CUDA (sm_100a) only; there is no CPU fallback")
+        R = self.img_resolution
+        if dst.ndim != 4 or dst.shape[1:] != (3, R, R):
+            raise ValueError(f"dst must be [N,3,{R},{R}], got {tuple(dst.shape)}")
+        n_in = dst.shape[0]
+        if self.dual:
+            if n_in % 2:
+                raise ValueError("dual-source mode expects 2B interleaved inputs")
+            if geometry is None:
+                raise TypeError("dual-source mode requires geometry")   # reference: NoneType * int (models.py:631)
+        B = n_in // 2 if self.dual else n_in
+        with torch.no_grad():
+            p = self.plan(B, dst.device)
+            p.in_x.copy_(dst)
+            if p.in_src is not None:
+                if src.shape != p.in_src.shape:
+                    raise ValueError(f"src must be {tuple(p.in_src.shape)}, got {tuple(src.shape)}")
+                p.in_src.copy_(src)
+            sig = torch.as_tensor(sigma, dtype=torch.float32, device=dst.device).reshape(-1)
+            p.in_sigma.copy_(sig.expand(n_in) if sig.numel() == 1 else sig)
+            if geometry is None:
+                p.in_geom.zero_()
+            else:
+                g = geometry.to(torch.float32).reshape(-1, p.in_geom.shape[1])
+                p.in_geom.copy_(g.expand(n_in, -1) if g.shape[0] == 1 else g)
+            if self.super_res:
+                if conditioning_image is None:
+                    raise AssertionError("super_res model requires conditioning_image")
+                p.in_cond.copy_(conditioning_image)
+                # the reference draws this from the GLOBAL torch RNG on every call;
+                # same call, same device/dtype/shape, so identical noise for identical generator state
+                p.in_noise.copy_(torch.randn_like(conditioning_image))
+            p.run(graph=self.use_graph)
+            return p.out_d.clone()
