@@ -42,6 +42,9 @@ const char* vb_last_error(void);
 int vb_abi_version(void);
 /* 0 when the current CUDA device is compute capability 10.x, VB_ERR_NO_DEVICE otherwise. */
 int vb_device_check(void);
+/* sizeof() of the descriptor structs below, in declaration order (0 = vb_weight_prep_desc ... 7 = vb_heun_desc);
+ * lets a foreign-language binding verify its mirror of the layout.  -1 for an unknown index. */
+int vb_struct_size(int which);
 
 /* ------------------------------------------------------------------------
  * Weight preparation — replaces the per-call prologue of MPConv.forward

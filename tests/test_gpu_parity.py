@@ -1,0 +1,443 @@
+"""GPU parity tests (pytest -m gpu, B200): every kernel and the whole path, called through the C ABI
+(libvividb200.so via ctypes), against the oracle / the reference's golden outputs.
+
+Tolerances (BASELINE.json north_star): per-call denoiser output rel-L2 <= 1e-2 in bf16 mode, final
+image PSNR >= 40 dB.  Single kernels are compared on identical bf16-rounded operands, so only the
+accumulation order differs and the bound is much tighter.
+"""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (vivid_b200 has no CPU fallback)")
+    from vivid_b200 import _lib as L
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    lib = L.lib()
+    L.check(lib.vb_device_check(), "vb_device_check")
+    return L, lib, torch.device("cuda")
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def psnr_u8(a, b):
+    mse = ((a.double() - b.double()) ** 2).mean().item()
+    return 10 * math.log10(255.0 ** 2 / max(mse, 1e-12))
+
+
+def pad_to(v, m):
+    return (v + m - 1) // m * m
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def prep_weight(L, lib, w, gain=1.0, cout_pad=None, perm=(0, 0)):
+    cout, cin = w.shape[:2]
+    taps = w[0, 0].numel() if w.ndim == 4 else 1
+    cout_pad = cout_pad or pad_to(cout, 16)
+    dst = torch.empty(cout_pad, taps, pad_to(cin, 64), dtype=torch.bfloat16, device=w.device)
+    d = L.WeightPrepDesc(src=w.data_ptr(), dst=dst.data_ptr(), src_dtype={torch.float32: 0, torch.float16: 1}[w.dtype],
+                         dst_dtype=L.VB_BF16, cout=cout, cin=cin, taps=taps, cout_pad=cout_pad, split=cin,
+                         seg_a_pad=pad_to(cin, 64), seg_b_pad=0, perm_parts=perm[0], perm_dim=perm[1], gain=gain,
+                         scale_a=1.0, scale_b=1.0)
+    L.check(lib.vb_weight_prep(C.byref(d), stream()), "vb_weight_prep")
+    return dst
+
+
+def ref_weight(w, gain=1.0):
+    w32 = w.float()
+    n = w32.flatten(1).norm(dim=1).reshape(-1, *([1] * (w.ndim - 1)))
+    return gain * w32 / (1e-4 * math.sqrt(w32[0].numel()) + n)
+
+
+# ------------------------------------------------------------------------------- single kernels
+CONV_CASES = [
+    # B, R, cin, cout, taps, block_n, flags, gain
+    (1, 16, 64, 64, 1, 64, 0, 1.0),
+    (2, 16, 128, 128, 9, 128, 0, 1.0),
+    (2, 32, 64, 128, 9, 128, 1, 1.0),
+    (2, 64, 128, 128, 9, 128, 2, 1.0),
+    (3, 8, 192, 256, 9, 256, 7, 1.0),        # odd batch, 2 images per tile
+    (5, 4, 64, 64, 9, 64, 6, 1.0),           # 8 images per tile, ragged
+    (2, 16, 320, 192, 1, 192, 0, 1.0),       # N = 192, five K chunks
+    (2, 64, 4, 128, 9, 128, 0, 1.0),         # first conv: 4 -> 64 padded input channels
+    (2, 64, 128, 3, 9, 16, 0, 0.7),          # out_conv: 3 -> 16 padded output channels, gain
+    (1, 256, 64, 64, 9, 64, 7, 1.0),         # SR resolution
+    (40, 16, 384, 384, 9, 128, 7, 1.0),      # persistent loop, several tiles per CTA
+]
+
+
+@pytest.mark.parametrize("B,R,cin,cout,taps,bn,flags,gain", CONV_CASES)
+def test_conv_gemm_vs_conv2d(env, B, R, cin, cout, taps, bn, flags, gain):
+    """vb_conv (+vb_weight_prep) vs MPConv semantics (models.py:115-126) with the fused epilogues."""
+    L, lib, dev = env
+    g = torch.Generator().manual_seed(B * 1000 + R + cin + cout)
+    cin_pad, cout_pad, k = pad_to(cin, 64), pad_to(cout, bn), 3 if taps == 9 else 1
+    x = torch.randn(B, cin, R, R, generator=g).to(dev)
+    w = torch.randn(cout, cin, k, k, generator=g).to(dev)
+    x_nhwc = torch.zeros(B, R, R, cin_pad, dtype=torch.bfloat16, device=dev)
+    x_nhwc[..., :cin] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+    wp = prep_weight(L, lib, w, gain=gain, cout_pad=cout_pad)
+    wr = ref_weight(w, gain)
+    assert (wp[:cout].float().reshape(cout, taps, cin_pad)[..., :cin].permute(0, 2, 1).reshape(wr.shape)
+            - wr.to(torch.bfloat16).float()).abs().max() <= 4e-3 * wr.abs().max()
+    xr = x_nhwc[..., :cin].float().permute(0, 3, 1, 2)
+    wq = wp[:cout].float().reshape(cout, taps, cin_pad)[..., :cin].permute(0, 2, 1).reshape(cout, cin, k, k)
+    y = torch.nn.functional.conv2d(xr, wq, padding=k // 2)
+    mod = res = None
+    if flags & L.VB_F_MODSILU:
+        mod = (torch.randn(B, cout_pad, generator=g) * 0.3 + 1).to(dev)
+        y = torch.nn.functional.silu(y * mod[:, :cout, None, None]) / 0.596
+    if flags & L.VB_F_RESIDUAL:
+        res = torch.randn(B, R, R, cout_pad, generator=g).to(dev)
+        y = (res[..., :cout].permute(0, 3, 1, 2) * 0.7 + y * 0.3) / math.sqrt(0.7 ** 2 + 0.3 ** 2)
+    if flags & L.VB_F_CLIP:
+        y = y.clamp(-1.5, 1.5)
+    o32 = torch.full((B, R, R, cout_pad), float("nan"), device=dev)
+    o16 = torch.zeros(B, R, R, cout_pad, dtype=torch.bfloat16, device=dev)
+    osl = torch.zeros(B, R, R, cout_pad, dtype=torch.bfloat16, device=dev)
+    d = L.ConvDesc(x=x_nhwc.data_ptr(), w=wp.data_ptr(), mod=L.ptr(mod), res=L.ptr(res), out_f32=o32.data_ptr(),
+                   out_bf16=o16.data_ptr(), out_silu=osl.data_ptr(), B=B, H=R, W=R, cin_pad=cin_pad, cin2_pad=0,
+                   cout_pad=cout_pad, taps=taps, block_n=bn, epi_mode=L.VB_EPI_PLAIN, flags=flags, mod_stride=cout_pad,
+                   ld_res=cout_pad, ld_f32=cout_pad, ld_bf16=cout_pad, ld_silu=cout_pad, res_t=0.3, clip=1.5)
+    L.check(lib.vb_conv(C.byref(d), stream()), "vb_conv")
+    torch.cuda.synchronize()
+    assert rel(o32[..., :cout].permute(0, 3, 1, 2), y) < 2e-5
+    assert rel(o16[..., :cout].permute(0, 3, 1, 2).float(), y) < 4e-3
+    assert rel(osl[..., :cout].permute(0, 3, 1, 2).float(), torch.nn.functional.silu(y) / 0.596) < 5e-3
+    if cout_pad > cout:
+        assert o32[..., cout:].abs().max().item() == 0.0
+    # linearity of the GEMM (size-independent property): conv(2x) == 2 conv(x) exactly in bf16/fp32
+    if flags == 0:
+        x2 = (x_nhwc.float() * 2).to(torch.bfloat16)
+        o2 = torch.empty_like(o32)
+        d.x, d.out_f32, d.out_bf16, d.out_silu = x2.data_ptr(), o2.data_ptr(), None, None
+        L.check(lib.vb_conv(C.byref(d), stream()), "vb_conv")
+        torch.cuda.synchronize()
+        assert torch.equal(o2, o32 * 2)
+
+
+@pytest.mark.parametrize("B,R,ch,heads,D,parts,seg_div,bn", [(2, 16, 128, 2, 64, 3, 1, 128), (2, 8, 256, 4, 64, 2, 1, 128),
+                                                           (4, 8, 256, 4, 64, 2, 2, 64), (2, 32, 256, 8, 32, 3, 1, 64)])
+def test_qkv_epilogue(env, B, R, ch, heads, D, parts, seg_div, bn):
+    """1x1 GEMM + per-(token, head, q|k|v) normalise + scatter (models.py:192-193, 283-297)."""
+    L, lib, dev = env
+    g = torch.Generator().manual_seed(1)
+    cout = heads * parts * D
+    x = torch.randn(B, ch, R, R, generator=g).to(dev)
+    w = torch.randn(cout, ch, 1, 1, generator=g).to(dev)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    wp = prep_weight(L, lib, w, cout_pad=cout, perm=(parts, D))
+    S, Bo = R * R, B // seg_div
+    seq = [S if (j == 0 and parts == 3) else S * (1 + seg_div) for j in range(parts)]
+    off = [0 if parts == 3 else S] * parts
+    outs = [torch.zeros(Bo, heads, seq[j], D, dtype=torch.bfloat16, device=dev) for j in range(parts)]
+    d = L.ConvDesc(x=x_nhwc.data_ptr(), w=wp.data_ptr(), part_out=(C.c_void_p * 3)(*[o.data_ptr() for o in outs] + [None] * (3 - parts)),
+                   B=B, H=R, W=R, cin_pad=ch, cin2_pad=0, cout_pad=cout, taps=1, block_n=bn, epi_mode=L.VB_EPI_QKVNORM,
+                   head_dim=D, parts=parts, seg_div=seg_div, part_seq=(C.c_int32 * 3)(*(seq + [0] * (3 - parts))),
+                   part_off=(C.c_int32 * 3)(*(off + [0] * (3 - parts))))
+    L.check(lib.vb_conv(C.byref(d), stream()), "vb_conv qkv")
+    torch.cuda.synchronize()
+    y = torch.nn.functional.conv2d(x_nhwc.float().permute(0, 3, 1, 2), ref_weight(w).to(torch.bfloat16).float())
+    y = y.reshape(B, heads, D, parts, S)
+    y = y / (1e-4 + y.norm(dim=2, keepdim=True) / math.sqrt(D))
+    for j in range(parts):
+        ref = y[:, :, :, j, :].permute(0, 1, 3, 2)
+        for sg in range(seg_div):
+            got = outs[j][:, :, off[j] + sg * S: off[j] + (sg + 1) * S].float()
+            assert rel(got, ref[sg::seg_div]) < 5e-3
+
+
+@pytest.mark.parametrize("B,h,sq,sk,D,zk", [(2, 4, 1024, 2048, 64, 0), (3, 8, 64, 128, 64, 0), (2, 8, 64, 64, 64, 64),
+                                           (2, 2, 16, 48, 64, 0), (1, 8, 1024, 2048, 32, 0), (2, 6, 256, 768, 64, 0),
+                                           (1, 4, 16, 16, 32, 16)])
+def test_fused_attention(env, B, h, sq, sk, D, zk):
+    """vb_attn vs softmax(q k^T / sqrt(D)) v on normalised q,k,v, incl. analytic zero keys and ragged lengths."""
+    L, lib, dev = env
+    g = torch.Generator().manual_seed(sq + sk)
+
+    def nrm(t):
+        return (t / (1e-4 + t.norm(dim=-1, keepdim=True) / math.sqrt(D))).to(torch.bfloat16)
+    q = nrm(torch.randn(B, h, sq, D, generator=g)).to(dev)
+    k = nrm(torch.randn(B, h, sk, D, generator=g)).to(dev)
+    v = nrm(torch.randn(B, h, sk, D, generator=g)).to(dev)
+    y = torch.zeros(B, sq, h * D, dtype=torch.bfloat16, device=dev)
+    d = L.AttnDesc(q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), y=y.data_ptr(), B=B, heads=h, sq=sq, sk=sk, head_dim=D,
+                   zero_keys=zk)
+    L.check(lib.vb_attn(C.byref(d), stream()), "vb_attn")
+    torch.cuda.synchronize()
+    kz = torch.cat([k.float(), torch.zeros(B, h, zk, D, device=dev)], 2)
+    vz = torch.cat([v.float(), torch.zeros(B, h, zk, D, device=dev)], 2)
+    w = (q.float() @ kz.transpose(-1, -2) / math.sqrt(D)).softmax(-1)
+    ref = (w @ vz).permute(0, 2, 1, 3).reshape(B, sq, h * D)
+    assert rel(y.float(), ref) < 6e-3
+
+
+def test_elementwise_passes(env):
+    L, lib, dev = env
+    from oracle import vivid_oracle as O
+    g = torch.Generator().manual_seed(3)
+    B, R = 3, 8
+    for ch in (64, 192, 512):
+        a = torch.randn(B, R, R, ch, generator=g).to(dev)
+        nchw = a.permute(0, 3, 1, 2)
+        o32 = torch.empty_like(a)
+        osl = torch.empty(B, R, R, ch, dtype=torch.bfloat16, device=dev)
+        d = L.EwDesc(a=a.data_ptr(), out_f32=o32.data_ptr(), out_silu=osl.data_ptr(), kind=L.VB_EW_PIXNORM, B=B, H=R, W=R, ca=ch)
+        L.check(lib.vb_eltwise(C.byref(d), stream()), "pixnorm")
+        ref = O.normalize(nchw, dim=1)
+        assert rel(o32.permute(0, 3, 1, 2), ref) < 1e-6
+        assert rel(osl.float().permute(0, 3, 1, 2), O.mp_silu(ref)) < 4e-3
+        # idempotence (size-independent property): normalising a normalised tensor changes nothing beyond eps
+        d2 = L.EwDesc(a=o32.data_ptr(), out_f32=a.data_ptr(), kind=L.VB_EW_PIXNORM, B=B, H=R, W=R, ca=ch)
+        L.check(lib.vb_eltwise(C.byref(d2), stream()), "pixnorm")
+        assert rel(a, o32) < 2e-4
+        a = nchw.permute(0, 2, 3, 1).contiguous()
+        # 2x2 mean pool + pixnorm
+        o32 = torch.empty(B, R // 2, R // 2, ch, device=dev)
+        d = L.EwDesc(a=a.data_ptr(), out_f32=o32.data_ptr(), kind=L.VB_EW_DOWN_PIXNORM, B=B, H=R // 2, W=R // 2, ca=ch)
+        L.check(lib.vb_eltwise(C.byref(d), stream()), "down")
+        assert rel(o32.permute(0, 3, 1, 2), O.normalize(O.resample(nchw, "down"), dim=1)) < 1e-6
+        # nearest x2
+        u32 = torch.empty(B, 2 * R, 2 * R, ch, device=dev)
+        usl = torch.empty(B, 2 * R, 2 * R, ch, dtype=torch.bfloat16, device=dev)
+        d = L.EwDesc(a=a.data_ptr(), out_f32=u32.data_ptr(), out_silu=usl.data_ptr(), kind=L.VB_EW_UP, B=B, H=2 * R, W=2 * R, ca=ch)
+        L.check(lib.vb_eltwise(C.byref(d), stream()), "up")
+        assert torch.equal(u32.permute(0, 3, 1, 2), O.resample(nchw, "up"))
+        assert rel(usl.float().permute(0, 3, 1, 2), O.mp_silu(O.resample(nchw, "up"))) < 4e-3
+        # mp_cat
+        b = torch.randn(B, R, R, 128, generator=g).to(dev)
+        t = 0.5
+        cc = math.sqrt((ch + 128) / ((1 - t) ** 2 + t ** 2))
+        wa, wb = cc / math.sqrt(ch) * (1 - t), cc / math.sqrt(128) * t
+        c16 = torch.empty(B, R, R, ch + 128, dtype=torch.bfloat16, device=dev)
+        csl = torch.empty_like(c16)
+        d = L.EwDesc(a=a.data_ptr(), b=b.data_ptr(), out_bf16=c16.data_ptr(), out_silu=csl.data_ptr(), kind=L.VB_EW_CAT, B=B,
+                     H=R, W=R, ca=ch, cb=128, wa=wa, wb=wb)
+        L.check(lib.vb_eltwise(C.byref(d), stream()), "cat")
+        ref = O.mp_cat(nchw, b.permute(0, 3, 1, 2), t=t)
+        assert rel(c16.float().permute(0, 3, 1, 2), ref) < 4e-3
+        assert rel(csl.float().permute(0, 3, 1, 2), O.mp_silu(ref)) < 4e-3
+    torch.cuda.synchronize()
+
+
+def test_heun_guidance_and_codec(env, golden):
+    L, lib, dev = env
+    g = torch.Generator().manual_seed(5)
+    shp = (3, 3, 16, 16)
+    dn, dg, xh = (torch.randn(shp, generator=g).to(dev) for _ in range(3))
+    dc, xn = torch.empty(shp, device=dev), torch.empty(shp, device=dev)
+    th, tn, w = 5.0, 3.0, 1.5
+    d = L.HeunDesc(d_net=dn.data_ptr(), d_gnet=dg.data_ptr(), x_hat=xh.data_ptr(), d_cur=dc.data_ptr(), x_next=xn.data_ptr(),
+                   n=xh.numel(), phase=0, guidance=w, t_hat=th, t_next=tn)
+    L.check(lib.vb_heun(C.byref(d), stream()), "heun0")
+    D = dg.lerp(dn, w)
+    dcur = (xh - D) / th
+    x1 = xh + (tn - th) * dcur
+    assert torch.allclose(dc, dcur, rtol=1e-6, atol=1e-6) and torch.allclose(xn, x1, rtol=1e-6, atol=1e-6)
+    dn2, dg2 = (torch.randn(shp, generator=g).to(dev) for _ in range(2))
+    d = L.HeunDesc(d_net=dn2.data_ptr(), d_gnet=dg2.data_ptr(), x_hat=xh.data_ptr(), d_cur=dc.data_ptr(), x_next=xn.data_ptr(),
+                   n=xh.numel(), phase=1, guidance=w, t_hat=th, t_next=tn)
+    L.check(lib.vb_heun(C.byref(d), stream()), "heun1")
+    dpr = (x1 - dg2.lerp(dn2, w)) / tn
+    assert torch.allclose(xn, xh + (tn - th) * (0.5 * dcur + 0.5 * dpr), rtol=1e-5, atol=1e-5)
+    # codec: bit-exact against the reference's own vectors (training/encoders.py:58-62)
+    from vivid_b200 import StandardRGBEncoder
+    ops = golden["vanilla"]["ops"]
+    enc = StandardRGBEncoder()
+    assert torch.equal(enc.encode_latents(ops["u8"].to(dev)).cpu(), ops["encode_latents"])
+    assert torch.equal(enc.decode(ops["lat"].to(dev)).cpu(), ops["decode"])
+    ramp = torch.linspace(-1.2, 1.2, 100001, device=dev)
+    assert torch.equal(enc.decode(ramp), (ramp * 127.5 + 128).clip(0, 255).to(torch.uint8))
+
+
+# ------------------------------------------------------------------------------- whole denoiser
+def _product(case, dev):
+    import vivid_b200
+    net = vivid_b200.NVPrecond(**cases.CASES[case]["cfg"])
+    shapes = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+    net.load_state_dict(cases.synth_state_dict(shapes))
+    return net.to(dev).eval()
+
+
+@pytest.mark.parametrize("case", ["v_cond", "v_uncond", "v_sr", "d_cond", "v_tiny"])
+def test_denoiser_vs_reference_golden(env, golden, case):
+    """CUDA path vs outputs of the UNMODIFIED reference (fp32 CPU) on identical weights/inputs."""
+    L, lib, dev = env
+    mode = cases.CASES[case]["mode"]
+    rec = golden[mode]["nets"][case]
+    net = _product(case, dev)
+    inp = {k: v.to(dev) for k, v in cases.synth_inputs(case, rec["B"]).items()}
+    n_in = inp["src"].shape[0]
+    for graph in (False, True):
+        net.use_graph = graph
+        for sg, ref in rec["D"].items():
+            x = inp["tgt"] + sg * inp["noise"]
+            kw = {}
+            if rec["cfg"].get("super_res"):
+                # the SR forward draws torch.randn_like from the global RNG; the golden used the CPU stream of
+                # seed 123, so feed that exact draw through the same torch call by seeding identically on CPU
+                torch.manual_seed(123)
+                cpu_noise = torch.randn_like(inp["tgt"].cpu())
+                kw["conditioning_image"] = inp["tgt"]
+                net_noise = cpu_noise.to(dev)
+                orig = torch.randn_like
+                torch.randn_like = lambda t, *a, **k: net_noise if t.shape == net_noise.shape else orig(t, *a, **k)
+                try:
+                    d = net(inp["src"], x, torch.full((n_in,), sg, device=dev), inp["geometry"], **kw)
+                finally:
+                    torch.randn_like = orig
+            else:
+                d = net(inp["src"], x, torch.full((n_in,), sg, device=dev), inp["geometry"])
+            assert d.dtype == torch.float32 and d.shape == ref.shape
+            c_skip = 0.25 / (sg ** 2 + 0.25)
+            xs = (x[::2] if mode == "dual" else x).cpu()
+            assert rel(d.cpu(), ref) <= 1e-2, (case, sg, graph)                       # north-star tolerance
+            assert rel(d.cpu() - c_skip * xs, ref - c_skip * xs) <= 1.5e-2, (case, sg)  # network part alone
+    if "D_nogeom" in rec:
+        x = inp["tgt"] + 5.0 * inp["noise"]
+        d = net(inp["src"], x, torch.full((n_in,), 5.0, device=dev))                   # gnet-style call, geometry=None
+        assert rel(d.cpu(), rec["D_nogeom"]) <= 1e-2
+        d0 = net(inp["src"], x, torch.tensor(5.0, device=dev))                         # 0-dim sigma (snapshot sampler)
+        assert torch.equal(d0, d)
+
+
+def test_guided_sampler_vs_reference_golden(env, golden):
+    """edm_sampler(net + uncond gnet, w=1.5): final image PSNR >= 40 dB against the reference's sample."""
+    L, lib, dev = env
+    import vivid_b200
+    nets = golden["vanilla"]["nets"]
+    net, gnet = _product("v_cond", dev), _product("v_uncond", dev)
+    inp = {k: v.to(dev) for k, v in cases.synth_inputs("v_cond", 2).items()}
+    ref = nets["sampler_guided"]
+    lat = vivid_b200.edm_sampler(net, inp["src"], inp["noise"], labels=inp["geometry"], gnet=gnet,
+                                 num_steps=ref["num_steps"], guidance=ref["guidance"])
+    img = vivid_b200.StandardRGBEncoder().decode(lat).cpu()
+    assert psnr_u8(img, ref["images"]) >= 40.0
+    assert rel(lat.cpu(), ref["latents"]) <= 1e-2
+    lat1 = vivid_b200.edm_sampler(net, inp["src"], inp["noise"], labels=inp["geometry"], num_steps=4)
+    assert rel(lat1.cpu(), nets["sampler_unguided"]["latents"]) <= 1e-2
+    # determinism: same inputs, same bits
+    lat2 = vivid_b200.edm_sampler(net, inp["src"], inp["noise"], labels=inp["geometry"], num_steps=4)
+    assert torch.equal(lat1, lat2)
+
+
+def test_dual_and_tiny_samplers_vs_reference_golden(env, golden):
+    L, lib, dev = env
+    import vivid_b200
+    net = _product("d_cond", dev)
+    inp = {k: v.to(dev) for k, v in cases.synth_inputs("d_cond", 2).items()}
+    lat = vivid_b200.edm_sampler(net, inp["src"], inp["noise"], labels=inp["geometry"], num_steps=3)
+    ref = golden["dual"]["nets"]["sampler_dual"]["latents"]
+    assert lat.shape == ref.shape and rel(lat.cpu(), ref) <= 1e-2
+    # BASELINE.json configs[0]: tiny net, Heun 8 steps, batch 2
+    net = _product("v_tiny", dev)
+    inp = {k: v.to(dev) for k, v in cases.synth_inputs("v_tiny", 2).items()}
+    lat = vivid_b200.edm_sampler(net, inp["src"], inp["noise"], labels=inp["geometry"], num_steps=8)
+    ref = golden["vanilla"]["nets"]["sampler_tiny"]["latents"]
+    dec = vivid_b200.StandardRGBEncoder().decode
+    assert psnr_u8(dec(lat).cpu(), dec(ref.to(dev)).cpu()) >= 40.0
+
+
+def _preset(name):
+    base = dict(img_resolution=64, img_channels=3, label_dim=20, model_channels=128, extra_attn=1)
+    return {"vivid-base": base, "vivid-uncond": dict(base, uncond=True),
+            "vivid-sr": dict(img_resolution=256, img_channels=3, label_dim=20, model_channels=64, super_res=True, noisy_sr=0.25)}[name]
+
+
+@pytest.mark.parametrize("preset,B", [("vivid-base", 3), ("vivid-uncond", 3), ("vivid-sr", 1)])
+def test_full_size_presets_vs_oracle(env, preset, B):
+    """BASELINE.json configs[1..2] architectures at full size vs the oracle on the GPU (fp32, TF32 off)."""
+    L, lib, dev = env
+    import vivid_b200
+    from oracle import vivid_oracle as O
+    from vivid_b200.synthetic import synth_batch
+    cfg = _preset(preset)
+    torch.manual_seed(0)
+    net = vivid_b200.NVPrecond(**cfg)
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.ndim == 0:
+                p.fill_(1.0)                                    # zero-init gains make parity vacuous
+    net = net.to(dev).eval()
+    onet = O.OracleNet({k: v.detach().clone() for k, v in net.state_dict().items()}, cfg)
+    R = cfg["img_resolution"]
+    batch = synth_batch(range(B), R)
+    src = (batch["src_image"] / 127.5 - 1).to(dev)
+    tgt = (batch["tgt_image"] / 127.5 - 1).to(dev)
+    geom = batch["geometry"].to(dev)
+    g = torch.Generator().manual_seed(11)
+    for sg in (40.0, 1.0):
+        x = tgt + sg * torch.randn(tgt.shape, generator=g).to(dev)
+        sigma = torch.full((B,), sg, device=dev)
+        kw = dict(conditioning_image=tgt) if cfg.get("super_res") else {}
+        torch.manual_seed(77)
+        d = net(src, x, sigma, geom, **kw)
+        torch.manual_seed(77)
+        with torch.no_grad():
+            ref = onet(src, x, sigma, geom, **kw)
+        assert rel(d, ref) <= 1e-2, (preset, sg)
+    # size-independent properties at the bench batch size: batch-composition independence + graph == eager
+    Bb = 8 if preset != "vivid-sr" else 2
+    batch = synth_batch(range(Bb), R)
+    src = (batch["src_image"] / 127.5 - 1).to(dev)
+    tgt = (batch["tgt_image"] / 127.5 - 1).to(dev)
+    geom = batch["geometry"].to(dev)
+    x = tgt + 2.0 * torch.randn(tgt.shape, generator=g).to(dev)
+    kw = dict(conditioning_image=tgt) if cfg.get("super_res") else {}
+    sigma = torch.full((Bb,), 2.0, device=dev)
+    net.use_graph = True
+    torch.manual_seed(5)
+    full = net(src, x, sigma, geom, **kw)
+    net.use_graph = False
+    torch.manual_seed(5)
+    eager = net(src, x, sigma, geom, **kw)
+    assert torch.equal(full, eager)
+    if not cfg.get("super_res"):
+        sub = net(src[:3], x[:3], sigma[:3], geom[:3])
+        assert rel(sub, full[:3]) < 1e-5
+
+
+def test_generate_images_nvs_pipeline(env):
+    """base -> resize -> SR pipeline through the public driver: uint8 images, seed-keyed (world-size invariant)."""
+    L, lib, dev = env
+    import vivid_b200
+    torch.manual_seed(0)
+    small = dict(img_channels=3, label_dim=20, model_channels=64, channel_mult=[1, 2], num_blocks=1)
+    net = vivid_b200.NVPrecond(img_resolution=16, attn_resolutions=[8], **small)
+    gnet = vivid_b200.NVPrecond(img_resolution=16, attn_resolutions=[8], uncond=True, **small)
+    sr = vivid_b200.NVPrecond(img_resolution=64, attn_resolutions=[], super_res=True, **small)
+    for m in (net, gnet, sr):
+        with torch.no_grad():
+            for p in m.parameters():
+                if p.ndim == 0:
+                    p.fill_(0.5)
+    from vivid_b200.generate import SyntheticDataset
+    ds = SyntheticDataset(imsize=16, sr_imsize=64)
+    kw = dict(gnet=gnet, device=dev, dataset=ds, num_steps=4, guidance=1.5, verbose=False)
+    # base stage only: noise, images and poses are keyed by seed, so the batch split must not matter
+    a = list(vivid_b200.generate_images_nvs(net, seeds=[3, 4, 5, 6, 7], max_batch_size=8, **kw))
+    b = list(vivid_b200.generate_images_nvs(net, seeds=[3, 4, 5, 6, 7], max_batch_size=2, **kw))
+    assert len(a) == 1 and a[0].images.shape == (5, 3, 16, 16) and a[0].images.dtype == torch.uint8
+    assert [len(r.seeds) for r in b] == [2, 2, 1]
+    assert (a[0].images.int() - torch.cat([r.images for r in b]).int()).abs().max() <= 1
+    # two-stage pipeline: base -> bilinear x4 -> SR model
+    c = list(vivid_b200.generate_images_nvs(net, seeds=[3, 4, 5], max_batch_size=8, sr_model=sr, **kw))
+    assert c[0].images.shape == (3, 3, 64, 64) and c[0].images.dtype == torch.uint8
+    assert c[0].tgt.shape == (3, 3, 64, 64) and c[0].noise.shape == (3, 3, 64, 64)
+    m = vivid_b200.get_metrics(iter(c), device=dev)
+    assert m["num_images"] == 3 and 3.0 < m["psnr"] < 60.0

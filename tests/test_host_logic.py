@@ -1,0 +1,200 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports what include/vivid_b200.h declares, the
+host-side mirror of the reference interface has the reference's parameter tree / error behaviour,
+and the seed sharding + metric reduction work at world_size 2 over gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from vivid_b200 import build, _lib
+    build.build()
+    return _lib.lib()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "vivid_b200.h")).read()
+    declared = set(re.findall(r"\b(vb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    raw = ctypes.CDLL(os.path.join(ROOT, "vivid_b200", "libvividb200.so"))
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} declared in include/vivid_b200.h but not exported"
+    from vivid_b200 import _lib
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_abi_version_and_struct_mirror(lib):
+    from vivid_b200 import _lib
+    assert lib.vb_abi_version() == 1
+    for i, st in enumerate(_lib.STRUCTS):
+        assert lib.vb_struct_size(i) == ctypes.sizeof(st)
+    assert lib.vb_struct_size(99) == -1
+
+
+def test_fails_loudly_without_gpu(lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert lib.vb_device_check() != 0
+    assert b"no CPU fallback" in lib.vb_last_error()
+    import vivid_b200
+    net = vivid_b200.NVPrecond(**cases.CASES["v_cond"]["cfg"])
+    x = torch.zeros(1, 3, 16, 16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(x, x, torch.ones(1), torch.zeros(1, 20))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        vivid_b200.edm_sampler(net, x, x)
+
+
+def test_argument_validation_returns_error_codes(lib):
+    from vivid_b200 import _lib as L
+    d = L.ConvDesc(B=1, H=12, W=12, cin_pad=64, cout_pad=64, taps=9, block_n=64)
+    assert lib.vb_conv(ctypes.byref(d), None) == -1
+    assert b"required" in lib.vb_last_error()
+    d = L.ConvDesc(x=1 << 20, w=1 << 20, B=1, H=12, W=12, cin_pad=64, cout_pad=64, taps=9, block_n=64)
+    assert lib.vb_conv(ctypes.byref(d), None) == -1 and b"power of two" in lib.vb_last_error()
+    d = L.ConvDesc(x=1 << 20, w=1 << 20, B=1, H=16, W=16, cin_pad=60, cout_pad=64, taps=9, block_n=64)
+    assert lib.vb_conv(ctypes.byref(d), None) == -1 and b"multiples of 64" in lib.vb_last_error()
+    a = L.AttnDesc(q=1, k=1, v=1, y=1, B=1, heads=1, sq=16, sk=16, head_dim=48)
+    assert lib.vb_attn(ctypes.byref(a), None) == -1 and b"head_dim" in lib.vb_last_error()
+    assert lib.vb_plan_run(None, 0, -1, None) == -1
+
+
+@pytest.mark.parametrize("case", list(cases.CASES))
+def test_parameter_tree_matches_reference(golden, case):
+    """state_dict keys, shapes AND order equal the reference's (shapes recorded by make_golden.py)."""
+    import vivid_b200
+    mode = cases.CASES[case]["mode"]
+    ref_shapes = [(k, tuple(s)) for k, s in golden[mode]["nets"][case]["shapes"]]
+    with torch.device("meta"):
+        net = vivid_b200.NVPrecond(**cases.CASES[case]["cfg"])
+    mine = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+    assert mine == ref_shapes
+    assert net.dual == (mode == "dual")
+
+
+def test_preset_parameter_counts():
+    """base 250.65 M (enc 119.39 + unet 131.26), uncond 131.26 M, sr 38.20 M, tiny 59.33 M."""
+    import vivid_b200
+
+    def count(**kw):
+        with torch.device("meta"):
+            return sum(p.numel() for p in vivid_b200.NVPrecond(img_channels=3, label_dim=20, **kw).parameters())
+    assert count(img_resolution=64, model_channels=128, extra_attn=1) == 250643011
+    assert count(img_resolution=64, model_channels=128, extra_attn=1, uncond=True) == 131254309
+    assert count(img_resolution=256, model_channels=64, super_res=True) == 38193205
+    assert count(img_resolution=32, model_channels=64) == 59326852
+    with torch.device("meta"):
+        base = vivid_b200.NVPrecond(64, 3, 20, model_channels=128, extra_attn=1)
+    feats = base.encoder.feature_specs()
+    assert len(feats) == 17                      # 32²x256 x2, 16²x384 x7, 8²x512 x8
+    assert sorted((f.res, f.cout) for f in feats).count((8, 512)) == 8
+    assert [f.name for f in base.unet.feature_specs()] == [f.name for f in feats]
+
+
+def test_interface_attributes_and_unsupported_flags():
+    import vivid_b200
+    with torch.device("meta"):
+        net = vivid_b200.NVPrecond(64, 3, 20, model_channels=128, extra_attn=1, noisy_sr=0.25)
+    for attr, val in dict(img_resolution=64, img_channels=3, no_time_enc=None, depth_input=False, super_res=False,
+                          uncond=None, use_fp16=True, sigma_data=0.5, noisy_sr=0.25, label_dim=20).items():
+        assert getattr(net, attr) == val
+    assert net.init_kwargs["model_channels"] == 128
+    with pytest.raises(NotImplementedError):
+        vivid_b200.NVPrecond(64, 3, 20, depth_input=True)
+    with pytest.raises(NotImplementedError):
+        vivid_b200.NVPrecond(64, 3, 20, warp_depth_coor=True)
+    with pytest.raises(NotImplementedError):
+        vivid_b200.NVPrecond(64, 3, 20, model_channels=64, epipolar_attention_bias=True)
+    with pytest.raises(TypeError):
+        vivid_b200.NVPrecond(64, 3)
+    with pytest.raises(ValueError):
+        vivid_b200.NVPrecond(48, 3, 20)
+    x = torch.zeros(1, 3, 64, 64)
+    for kw in (dict(return_logvar=True), dict(force_fp32=True), dict(return_features=True), dict(inject_features=[x])):
+        with pytest.raises(NotImplementedError):
+            net(x, x, torch.ones(1), None, **kw)
+
+
+def test_seed_sharding_matches_reference_formula():
+    from vivid_b200.generate import split_seeds
+    for n, mb, w in [(8, 32, 1), (10000, 32, 8), (100, 32, 2), (33, 32, 4), (1, 32, 8)]:
+        got = [split_seeds(n, mb, r, w) for r in range(w)]
+        # reference: generate_images.py:199-200
+        num_batches = max((n - 1) // (mb * w) + 1, 1) * w
+        ref = np.array_split(np.arange(n), num_batches)
+        flat = sorted(int(i) for part in got for b in part for i in b)
+        assert flat == list(range(n))
+        assert all(len(b) <= mb for part in got for b in part)
+        assert len({len(p) for p in got}) == 1            # every rank sees the same number of batches
+        for r in range(w):
+            assert all(np.array_equal(a, b) for a, b in zip(got[r], ref[r::w]))
+    assert {len(b) for b in split_seeds(10000, 32, 0, 8)} == {31, 32}
+
+
+def test_synthetic_inputs_are_seed_keyed_and_contract_shaped():
+    from vivid_b200 import synthetic
+    a = synthetic.synth_batch([5, 9], 64)
+    b = synthetic.synth_batch([9], 64)
+    assert a["src_image"].shape == (2, 3, 64, 64) and a["geometry"].shape == (2, 20)
+    assert torch.equal(a["src_image"][1], b["src_image"][0]) and torch.equal(a["geometry"][1], b["geometry"][0])
+    assert a["src_image"].min() >= 0 and a["src_image"].max() <= 255
+    assert (a["geometry"][:, [14, 15, 18, 19]] == 0).all()           # std == 0 entries (cx, cy) are zeroed
+    d = synthetic.synth_batch([1, 2], 32, dual=True)
+    assert d["src_image"].shape[0] == 4 and torch.equal(d["tgt_image"][0], d["tgt_image"][1])
+
+
+def test_compose_geometry_and_schedule_match_reference(golden):
+    from vivid_b200 import synthetic
+    from vivid_b200.sampler import sigma_steps
+    g = golden["dual"]["ops"]
+    assert torch.allclose(synthetic.compose_geometry(g["ext"], g["k_src"], g["k_tgt"], 64), g["compose_geometry_64"], atol=1e-6)
+    assert torch.allclose(synthetic.compose_geometry(g["ext"], g["k_src"] * 4, g["k_tgt"] * 4, 256),
+                          g["compose_geometry_256"], atol=1e-6)
+    t = sigma_steps(32, 0.002, 80, 7, "cpu")
+    assert torch.equal(t[:-1], golden["vanilla"]["nets"]["t_steps_32"]) and t[-1] == 0
+    from vivid_b200 import StackedRandomGenerator
+    assert torch.equal(StackedRandomGenerator("cpu", [3, 4, (1 << 32) + 3]).randn([3, 2, 4]), g["stacked_randn"])
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from vivid_b200.generate import split_seeds, get_metrics, EasyDict
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+batches = split_seeds(10, 3, rank, 2)
+def it():
+    for b in batches:
+        img = torch.stack([torch.full((3, 4, 4), float(10 * i), dtype=torch.uint8) for i in b])
+        tgt = torch.stack([torch.full((3, 4, 4), float(10 * i + 2)) for i in b])
+        yield EasyDict(images=img, tgt=tgt)
+m = get_metrics(it(), device=torch.device("cpu"))
+assert m["num_images"] == 10, m
+import math
+assert abs(m["psnr"] - 10 * math.log10(255 ** 2 / 4.0)) < 1e-9, m
+print("rank", rank, "ok")
+"""
+
+
+def test_world_size_2_sharding_and_metric_reduction(tmp_path):
+    """N>1 host path on CPU: gloo, two ranks, disjoint seed shards, all_reduced PSNR statistics."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"rank {r} ok" in o

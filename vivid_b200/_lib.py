@@ -71,6 +71,7 @@ SIGNATURES = {
     "vb_last_error": (C.c_char_p, []),
     "vb_abi_version": (C.c_int, []),
     "vb_device_check": (C.c_int, []),
+    "vb_struct_size": (C.c_int, [C.c_int]),
     "vb_weight_prep": (C.c_int, [C.POINTER(WeightPrepDesc), vp]),
     "vb_conv": (C.c_int, [C.POINTER(ConvDesc), vp]),
     "vb_attn": (C.c_int, [C.POINTER(AttnDesc), vp]),
@@ -96,6 +97,8 @@ SIGNATURES = {
     "vb_plan_query": (C.c_double, [vp, C.c_int]),
 }
 
+STRUCTS = [WeightPrepDesc, ConvDesc, AttnDesc, EwDesc, EmbDesc, PrecondInDesc, PrecondOutDesc, HeunDesc]
+
 _lib = None
 
 
@@ -117,6 +120,10 @@ def lib():
         fn = getattr(h, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    for i, st in enumerate(STRUCTS):
+        if h.vb_struct_size(i) != C.sizeof(st):
+            raise VividB200Error(f"ABI mismatch: {st.__name__} is {C.sizeof(st)} bytes here, "
+                                 f"{h.vb_struct_size(i)} in {LIB_PATH}; rebuild with `python -m vivid_b200.build`")
     _lib = h
     return h
 

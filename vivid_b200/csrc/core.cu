@@ -94,3 +94,18 @@ extern "C" int vb_device_check(void) {
   }
   return VB_OK;
 }
+
+// sizeof of every descriptor struct, so bindings can verify their mirror of the layout.
+extern "C" int vb_struct_size(int which) {
+  switch (which) {
+    case 0: return static_cast<int>(sizeof(vb_weight_prep_desc));
+    case 1: return static_cast<int>(sizeof(vb_conv_desc));
+    case 2: return static_cast<int>(sizeof(vb_attn_desc));
+    case 3: return static_cast<int>(sizeof(vb_ew_desc));
+    case 4: return static_cast<int>(sizeof(vb_emb_desc));
+    case 5: return static_cast<int>(sizeof(vb_precond_in_desc));
+    case 6: return static_cast<int>(sizeof(vb_precond_out_desc));
+    case 7: return static_cast<int>(sizeof(vb_heun_desc));
+    default: return -1;
+  }
+}

@@ -31,6 +31,8 @@ class Act:
         self.f32 = None    # fp32 residual stream
         self.bf16 = None   # bf16 GEMM operand
         self.silu = None   # bf16 mp_silu(x) GEMM operand
+        self.is_skip = False
+        self.is_feature = False
 
 
 _DT = {torch.float32: L.VB_F32, torch.float16: L.VB_F16, torch.bfloat16: L.VB_BF16}
@@ -48,6 +50,8 @@ class Plan:
         self.dual = net.dual
         self.Bx = 2 * B if net.dual else B
         self.keep = []                  # every buffer the plan touches (keeps them alive)
+        self.pool = {}                  # (numel, dtype) -> free activation buffers
+        self.op_info = []               # per recorded op: (kind, label, algorithmic flops, algorithmic bytes)
         self.handle = C.c_void_p()
         L.check(self.lib.vb_plan_create(C.byref(self.handle)), "vb_plan_create")
         self.stream = torch.cuda.current_stream(device).cuda_stream
@@ -70,11 +74,24 @@ class Plan:
         self.keep.append(t)
         return t
 
+    # Activations come from a size-keyed pool: ops replay in order on one stream, so a buffer whose last
+    # consumer has been recorded can back a later activation (keeps the working set near L2 / HBM-friendly).
+    def act(self, rows, ch, dtype):
+        key = (rows * ch, dtype)
+        free = self.pool.get(key)
+        t = free.pop() if free else self.buf((rows * ch,), dtype)
+        return t.view(rows, ch)
+
+    def release(self, *tensors):
+        for t in tensors:
+            if t is not None:
+                self.pool.setdefault((t.numel(), t.dtype), []).append(t.view(-1))
+
     def f32(self, B, R, ch):
-        return self.buf((B * R * R, ch), torch.float32)
+        return self.act(B * R * R, ch, torch.float32)
 
     def b16(self, B, R, ch):
-        return self.buf((B * R * R, ch), torch.bfloat16)
+        return self.act(B * R * R, ch, torch.bfloat16)
 
     # ------------------------------------------------------------------ weights
     def prep_weight(self, w, gain=1.0, cout_pad=None, perm=(0, 0), split=None, scales=(1.0, 1.0), fp32=False):
@@ -134,18 +151,31 @@ class Plan:
                 d.part_seq[j] = qkv["seq"][j]
                 d.part_off[j] = qkv["off"][j]
         L.check(self.lib.vb_plan_add_conv(self.handle, C.byref(d)), "vb_plan_add_conv")
-        self.alg_flops += 2.0 * B * R * R * cout * (k_real if k_real is not None else taps * (cin_pad + cin2_pad))
+        fl = 2.0 * B * R * R * cout * (k_real if k_real is not None else taps * (cin_pad + cin2_pad))
+        self.alg_flops += fl
+        P = B * R * R
+        by = 2.0 * P * (cin_pad + cin2_pad) + 2.0 * cout_pad * taps * (cin_pad + cin2_pad)
+        by += P * cout_pad * (4.0 * (res is not None) + 4.0 * (out_f32 is not None) + 2.0 * (out_bf16 is not None)
+                              + 2.0 * (out_silu is not None) + (2.0 if qkv else 0.0))
+        self.op_info.append(("conv%d" % (3 if taps == 9 else 1), f"{R}x{R} k{taps * (cin_pad + cin2_pad)} n{cout_pad} bn{bn}", fl, by))
 
     def eltwise(self, kind, a, B, R, ca, *, b=None, cb=0, wa=1.0, wb=1.0, out_f32=None, out_bf16=None, out_silu=None):
         d = L.EwDesc(a=a.data_ptr(), b=L.ptr(b), out_f32=L.ptr(out_f32), out_bf16=L.ptr(out_bf16),
                      out_silu=L.ptr(out_silu), kind=kind, B=B, H=R, W=R, ca=ca, cb=cb, wa=wa, wb=wb)
         L.check(self.lib.vb_plan_add_eltwise(self.handle, C.byref(d)), "vb_plan_add_eltwise")
+        P = B * R * R
+        cin_tot, cout_tot = ca + cb, ca + cb
+        rd = 4.0 * P * cin_tot * (1.0 if kind != L.VB_EW_UP else 0.25) * (4.0 if kind == L.VB_EW_DOWN_PIXNORM else 1.0)
+        wr = P * cout_tot * (4.0 * (out_f32 is not None) + 2.0 * (out_bf16 is not None) + 2.0 * (out_silu is not None))
+        self.op_info.append(("eltwise", f"kind{kind} {R}x{R} c{cin_tot}", 0.0, rd + wr))
 
     def attention(self, q, k, v, y, B, heads, sq, sk, D, zero_keys):
         d = L.AttnDesc(q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), y=y.data_ptr(), B=B, heads=heads, sq=sq, sk=sk,
                        head_dim=D, zero_keys=zero_keys)
         L.check(self.lib.vb_plan_add_attn(self.handle, C.byref(d)), "vb_plan_add_attn")
         self.alg_flops += 4.0 * B * heads * sq * sk * D
+        self.op_info.append(("attn", f"h{heads} sq{sq} sk{sk} d{D}", 4.0 * B * heads * sq * sk * D,
+                             2.0 * B * heads * D * (2 * sq + 2 * sk)))
 
     # ------------------------------------------------------------------ embedding of one UNet
     def embed(self, unet, B, sigma, sigma_stride, geom, geom_rows, label_dim, noise_scale, geom_scale):
@@ -174,6 +204,7 @@ class Plan:
                       label_dim=label_dim, mod_total=total, geom_rows=geom_rows, label_balance=unet.label_balance,
                       noise_scale=noise_scale, geom_scale=geom_scale)
         L.check(self.lib.vb_plan_add_embed(self.handle, C.byref(d)), "vb_plan_add_embed")
+        self.op_info.append(("embed", f"cemb{unet.cemb} mod{total}", 0.0, 4.0 * total * unet.cemb))
         return mod, offs, total
 
     # ------------------------------------------------------------------ one UNet / encoder
@@ -210,11 +241,14 @@ class Plan:
                 need_b16 = True                                # x_attn_kv GEMM operand in the denoising UNet
             out = Act(B, s.res, s.cout)
             R, Cc = s.res, s.cout
+            temps = []                                         # buffers that die with this block
+            popped_skip = None
 
             if s.kind == "conv":
                 w = self.prep_weight(mod_.weight)
                 out.f32 = self.f32(B, R, Cc)
                 self.conv(x_in, w, B, R, 64, Cc, 9, out_f32=out.f32, k_real=9 * s.cin)
+                out.is_skip = True
                 cur = out
                 skips.append(out)
                 continue
@@ -223,10 +257,12 @@ class Plan:
             if s.flavor == "enc":
                 base = self.f32(B, R, Cc)
                 a0 = self.b16(B, R, Cc)
+                temps += [base, a0]
                 if s.resample == "down":
                     self.eltwise(L.VB_EW_DOWN_PIXNORM, cur.f32, B, R, Cc, out_f32=base, out_silu=a0)
                 elif s.has_conv_skip:
                     tmp = self.f32(B, R, Cc)
+                    temps.append(tmp)
                     w = self.prep_weight(mod_.conv_skip.weight)
                     self.conv(cur.bf16, w, B, R, _pad(s.cin, 64), Cc, 1, out_f32=tmp, k_real=s.cin)
                     self.eltwise(L.VB_EW_PIXNORM, tmp, B, R, Cc, out_f32=base, out_silu=a0)
@@ -237,10 +273,12 @@ class Plan:
                 if s.resample == "up":
                     base = self.f32(B, R, Cc)
                     a0 = self.b16(B, R, Cc)
+                    temps += [base, a0]
                     self.eltwise(L.VB_EW_UP, cur.f32, B, R, Cc, out_f32=base, out_silu=a0)
                     k0 = Cc
                 elif s.skip_ch:
                     skip = skips.pop()
+                    popped_skip = skip
                     na, nb = cur.C, skip.C
                     assert nb == s.skip_ch and na + nb == s.cin
                     t = unet.concat_balance
@@ -248,9 +286,11 @@ class Plan:
                     wa, wb = cc / math.sqrt(na) * (1 - t), cc / math.sqrt(nb) * t
                     cat16 = self.b16(B, R, s.cin)
                     a0 = self.b16(B, R, s.cin)
+                    temps += [cat16, a0]
                     self.eltwise(L.VB_EW_CAT, cur.f32, B, R, na, b=skip.f32, cb=nb, wa=wa, wb=wb, out_bf16=cat16,
                                  out_silu=a0)
                     base = self.f32(B, R, Cc)
+                    temps.append(base)
                     w = self.prep_weight(mod_.conv_skip.weight)
                     self.conv(cat16, w, B, R, s.cin, Cc, 1, out_f32=base, k_real=s.cin)
                     k0 = s.cin
@@ -260,6 +300,7 @@ class Plan:
 
             # ---------------- residual branch
             y0 = self.b16(B, R, Cc)
+            temps.append(y0)
             w0 = self.prep_weight(mod_.conv_res0.weight)
             mo = offs[(s.group, s.name)]
             self.conv(a0, w0, B, R, k0, Cc, 9, flags=L.VB_F_MODSILU, mod=mod.data_ptr() + 4 * mo, mod_stride=mod_total,
@@ -277,15 +318,16 @@ class Plan:
             else:
                 xr = self.f32(B, R, Cc)
                 xr16 = self.b16(B, R, Cc)
+                temps += [xr, xr16]
                 self.conv(y0, w1, B, R, Cc, Cc, 9, flags=L.VB_F_RESIDUAL, res=base, res_t=mod_.res_balance, out_f32=xr,
                           out_bf16=xr16)
                 S, D, h = R * R, s.head_dim, s.heads
                 nseg = feat_seg if s.xattn else 0
                 real_seg = 0 if zero_feature_keys else nseg
                 sk = S * (1 + real_seg)
-                q = self.buf((B, h, S, D), torch.bfloat16)
-                k = self.buf((B, h, sk, D), torch.bfloat16)
-                v = self.buf((B, h, sk, D), torch.bfloat16)
+                q = self.act(B * h * S, D, torch.bfloat16)
+                k = self.act(B * h * sk, D, torch.bfloat16)
+                v = self.act(B * h * sk, D, torch.bfloat16)
                 wq = self.prep_weight(mod_.attn_qkv.weight, perm=(3, D))
                 self.conv(xr16, wq, B, R, Cc, 3 * Cc, 1, qkv=dict(D=D, parts=3, out=[q, k, v], seq=[S, sk, sk], off=[0, 0, 0]))
                 if s.xattn and not zero_feature_keys:
@@ -294,10 +336,12 @@ class Plan:
                     wkv = self.prep_weight(mod_.x_attn_kv.weight, perm=(2, D))
                     self.conv(f.bf16, wkv, f.B, R, Cc, 2 * Cc, 1,
                               qkv=dict(D=D, parts=2, out=[k, v], seq=[sk, sk], off=[S, S], seg_div=feat_seg))
+                    temps.append(f.bf16)                       # each feature map feeds exactly one block
                 elif s.xattn:
                     # unconditional model: x_attn_kv(0) == 0 -> analytic zero keys; count the FLOPs the reference spends
                     pass
                 y = self.b16(B, R, Cc)
+                temps += [q, k, v, y]
                 self.attention(q, k, v, y, B, h, S, sk, D, S * nseg if zero_feature_keys else 0)
                 wp = self.prep_weight(mod_.attn_proj.weight)
                 out.f32 = self.f32(B, R, Cc) if need_f32 else None
@@ -310,6 +354,15 @@ class Plan:
                 feats_out.append(out)
             if s.group == "enc":
                 skips.append(out)
+            # recycle: this block's temporaries, the consumed skip, and the previous block's output unless it
+            # lives on as a skip connection (encoder outputs) or as a source-view feature
+            self.release(*temps)
+            if popped_skip is not None:
+                self.release(popped_skip.f32, None if popped_skip.is_feature else popped_skip.bf16, popped_skip.silu)
+            if cur is not None and not cur.is_skip:
+                self.release(cur.f32, None if cur.is_feature else cur.bf16, cur.silu)
+            out.is_skip = s.group == "enc"
+            out.is_feature = is_feature
             cur = out
 
         raw = None
@@ -344,6 +397,7 @@ class Plan:
             d = L.PrecondInDesc(x=self.in_src.data_ptr(), cond=None, noise=None, sigma=None, out=src16.data_ptr(), B=Bx,
                                 R=R, cpad=64, sigma_n=1, sigma_stride=0, img_stride=3 * R * R, sigma_data=sd, noisy_sr=0.0)
             L.check(self.lib.vb_plan_add_precond_in(self.handle, C.byref(d)), "vb_plan_add_precond_in")
+            self.op_info.append(("precond", "in", 0.0, d.B * R * R * (12.0 + 128.0)))
             mod, offs, total = self.embed(enc, Bx, self.in_sigma, 1, self.in_geom if ldim_enc else None, Bx, ldim_enc,
                                           0.0 if net.no_time_enc else 1.0, geom_scale)
             _, features = self.run_unet(enc, src16, Bx, mod, offs, total, collect_features=True)
@@ -357,6 +411,7 @@ class Plan:
                             sigma_stride=step, img_stride=3 * R * R * step, sigma_data=sd,
                             noisy_sr=float(net.noisy_sr if net.noisy_sr is not None else 0.0))
         L.check(self.lib.vb_plan_add_precond_in(self.handle, C.byref(d)), "vb_plan_add_precond_in")
+        self.op_info.append(("precond", "in", 0.0, d.B * R * R * (12.0 + 128.0)))
         mod, offs, total = self.embed(unet, B, self.in_sigma, step, self.in_geom if ldim_unet else None, B, ldim_unet,
                                       1.0, geom_scale)
         raw, _ = self.run_unet(unet, x16, B, mod, offs, total, features=features, feat_seg=feat_seg,
@@ -365,11 +420,29 @@ class Plan:
                              d_out=self.out_d.data_ptr(), B=B, R=R, ldf=16, sigma_n=B, sigma_stride=step,
                              img_stride=3 * R * R * step, sigma_data=sd)
         L.check(self.lib.vb_plan_add_precond_out(self.handle, C.byref(d)), "vb_plan_add_precond_out")
+        self.op_info.append(("precond", "out", 0.0, B * R * R * (12.0 + 64.0 + 12.0)))
         self.num_ops = self.lib.vb_plan_num_ops(self.handle)
         self.launches = int(self.lib.vb_plan_query(self.handle, 1))
         self.padded_flops = self.lib.vb_plan_query(self.handle, 0)
 
     # ------------------------------------------------------------------ execution
+    def profile(self, repeats=3):
+        """Time every recorded op on its own with CUDA events (eager replay, launching stream = current stream).
+        Returns [(kind, label, flops, bytes, milliseconds)] — the source of the roofline numbers in bench.py."""
+        assert len(self.op_info) == self.num_ops, (len(self.op_info), self.num_ops)
+        stream = torch.cuda.current_stream(self.device)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(self.num_ops + 1)]
+        best = [float("inf")] * self.num_ops
+        for _ in range(repeats):
+            ev[0].record(stream)
+            for i in range(self.num_ops):
+                L.check(self.lib.vb_plan_run(self.handle, i, i + 1, stream.cuda_stream), "vb_plan_run")
+                ev[i + 1].record(stream)
+            stream.synchronize()
+            for i in range(self.num_ops):
+                best[i] = min(best[i], ev[i].elapsed_time(ev[i + 1]))
+        return [(k, lab, fl, by, ms) for (k, lab, fl, by), ms in zip(self.op_info, best)]
+
     def run(self, graph=True):
         stream = torch.cuda.current_stream(self.device).cuda_stream
         if graph:

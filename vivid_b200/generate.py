@@ -1,0 +1,199 @@
+"""Generation driver — drop-in for the reference's `generate_images_nvs`
+(generate_images.py:139-343; snapshot experiments/code/generate_images.py:116-260) and the `gen`
+call shape of calculate_metrics.py:406-430.
+
+Differences that are deliberate:
+  * runs without litdata / RealEstate files: the default dataset is the seed-keyed synthetic one
+    (vivid_b200.synthetic), any object with `batch(seeds) -> dict` honouring the reference's batch
+    contract (src_image, tgt_image, geometry, sr_src_image, sr_tgt_image, sr_geometry) can be passed;
+  * works with or without an initialised process group (the reference calls barrier() unconditionally);
+  * per-sample inputs are keyed by seed, so outputs do not depend on the world size;
+  * the SR stage's global-RNG noise is seeded per batch from the batch's first seed.
+"""
+import os
+import pickle
+
+import numpy as np
+import torch
+
+from .encoders import StandardRGBEncoder
+from .precond import NVPrecond
+from .sampler import StackedRandomGenerator, edm_sampler
+from . import synthetic
+
+
+class EasyDict(dict):
+    """Attribute-style dict (the reference uses dnnlib.EasyDict for the per-batch record)."""
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        self[name] = value
+
+
+def _rank_world():
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_rank(), torch.distributed.get_world_size()
+    return 0, 1
+
+
+def _barrier():
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.barrier()
+
+
+def resolve_model(model, device, name="model"):
+    """Path / reference module / vivid_b200 module / None -> vivid_b200.NVPrecond on `device`
+    (reference training/utils.py:219-229 + generate_images.py:164-174)."""
+    if model is None:
+        return None
+    if isinstance(model, str):
+        with open(model, "rb") as f:
+            data = pickle.load(f)        # needs the reference's torch_utils.persistence importable, as in the reference
+        model = data["ema" if "ema" in data else "net"]
+    if isinstance(model, NVPrecond):
+        return model.to(device).eval()
+    if hasattr(model, "unet") and hasattr(model, "state_dict"):      # duck-typed reference NVPrecond
+        return NVPrecond.from_reference(model).to(device).eval()
+    raise TypeError(f"cannot interpret {name} of type {type(model).__name__}")
+
+
+class SyntheticDataset:
+    """Seed-keyed stand-in for datautils.RealEstate10K / CustomLitDataset (batch-dict contract, datautils.py:99)."""
+
+    def __init__(self, imsize=64, sr_imsize=256, dual=False):
+        self.imsize, self.sr_imsize, self.dual = imsize, sr_imsize, dual
+
+    def batch(self, seeds):
+        lo = synthetic.synth_batch(seeds, self.imsize, dual=self.dual)
+        hi = synthetic.synth_batch(seeds, self.sr_imsize, dual=self.dual)
+        return dict(src_image=lo["src_image"], tgt_image=lo["tgt_image"], geometry=lo["geometry"],
+                    sr_src_image=hi["src_image"], sr_tgt_image=hi["tgt_image"], sr_geometry=hi["geometry"])
+
+
+def split_seeds(num_seeds, max_batch_size, rank, world_size):
+    """Seed -> batch -> rank partition, identical to generate_images.py:199-200."""
+    num_batches = max((num_seeds - 1) // (max_batch_size * world_size) + 1, 1) * world_size
+    return np.array_split(np.arange(num_seeds), num_batches)[rank::world_size]
+
+
+def generate_images_nvs(
+    net, gnet=None, encoder=None, outdir=None, subdirs=False, seeds=range(16, 24), class_idx=None, max_batch_size=32,
+    encoder_batch_size=None, verbose=True, device=torch.device("cuda"), sampler_fn=edm_sampler, datakwargs=None,
+    range_selection=None, sr_model=None, depth_model=None, dataset=None, **sampler_kwargs,
+):
+    if depth_model is not None:
+        raise NotImplementedError("depth models are outside the B200 hot path (all presets: depth_input=False)")
+    device = torch.device(device)
+    rank, world = _rank_world()
+    if rank != 0:
+        _barrier()                      # rank 0 goes first (model files)
+    net = resolve_model(net, device, "net")
+    assert net is not None
+    gnet = resolve_model(gnet, device, "gnet")
+    if gnet is None:
+        gnet = net
+    if encoder is None:
+        encoder = StandardRGBEncoder()
+    encoder.init(device)
+    sr_model = resolve_model(sr_model, device, "sr_model")
+    if rank == 0:
+        _barrier()
+
+    seeds = list(seeds)
+    rank_batches = split_seeds(len(seeds), max_batch_size, rank, world)
+    super_res = net.img_resolution == 256
+    dual = bool(getattr(net, "dual", False))
+    if dataset is None:
+        dataset = SyntheticDataset(imsize=64 if super_res else net.img_resolution,
+                                   sr_imsize=sr_model.img_resolution if sr_model is not None else 256, dual=dual,
+                                   **(datakwargs or {}))
+    sr_sampler_kwargs = {k: v for k, v in sampler_kwargs.items() if k != "guidance"}     # no guidance in the SR stage
+
+    class ImageIterable:
+        def __len__(self):
+            return len(rank_batches)
+
+        def __iter__(self):
+            for batch_idx, indices in enumerate(rank_batches):
+                r = EasyDict(images=None, src=None, tgt=None, labels=None, noise=None, batch_idx=batch_idx,
+                             num_batches=len(rank_batches), indices=indices)
+                r.seeds = [seeds[idx] for idx in indices]
+                if len(r.seeds) > 0:
+                    data = dataset.batch(r.seeds)
+                    pre = "sr_" if super_res else ""
+                    r.src, r.tgt, geometry = data[pre + "src_image"], data[pre + "tgt_image"], data[pre + "geometry"]
+                    src = encoder.encode_latents(r.src.to(device, non_blocking=True))
+                    rnd = StackedRandomGenerator(device, r.seeds)
+                    r.noise = rnd.randn([len(r.seeds), net.img_channels, net.img_resolution, net.img_resolution], device=device)
+                    if dual:
+                        r.noise = r.noise.repeat_interleave(2, dim=0)
+                    r.labels = geometry.to(device, non_blocking=True)
+                    kwargs = dict(sampler_kwargs)
+                    if super_res:
+                        tgt = encoder.encode_latents(r.tgt.to(device))
+                        small = torch.nn.functional.interpolate(tgt, size=tgt.shape[-1] // 4, mode="bilinear", antialias=True)
+                        kwargs["conditioning_image"] = torch.nn.functional.interpolate(small, size=tgt.shape[-1], mode="bilinear")
+                        torch.manual_seed(int(r.seeds[0]) % (1 << 32))
+                    with torch.no_grad():
+                        latents = sampler_fn(net=net, src=src, noise=r.noise, labels=r.labels, gnet=gnet,
+                                             randn_like=rnd.randn_like, **kwargs)
+                        r.images = encoder.decode(latents)
+                    if sr_model is not None:
+                        r.src, r.tgt, sr_geometry = data["sr_src_image"], data["sr_tgt_image"], data["sr_geometry"]
+                        sr_src = encoder.encode_latents(r.src.to(device, non_blocking=True))
+                        rnd = StackedRandomGenerator(device, r.seeds)
+                        r.noise = rnd.randn([len(r.seeds), sr_model.img_channels, sr_model.img_resolution,
+                                             sr_model.img_resolution], device=device)
+                        r.labels = sr_geometry.to(device, non_blocking=True)
+                        # inter-stage bilinear upscale (generate_images.py:322; torch library op, once per batch)
+                        low_res = torch.nn.functional.interpolate(latents, size=sr_src.shape[-1], mode="bilinear")
+                        torch.manual_seed(int(r.seeds[0]) % (1 << 32))
+                        with torch.no_grad():
+                            sr_latents = sampler_fn(net=sr_model, src=sr_src, noise=r.noise, labels=r.labels, gnet=sr_model,
+                                                    randn_like=rnd.randn_like, conditioning_image=low_res,
+                                                    **sr_sampler_kwargs)
+                            r.images = encoder.decode(sr_latents)
+                    if outdir is not None:
+                        import PIL.Image
+                        tiles = zip(r.seeds, r.src.clip(0, 255).to(torch.uint8).permute(0, 2, 3, 1).cpu().numpy(),
+                                    r.tgt.clip(0, 255).to(torch.uint8).permute(0, 2, 3, 1).cpu().numpy(),
+                                    r.images.permute(0, 2, 3, 1).cpu().numpy())
+                        for seed, _src, _tgt, image in tiles:
+                            image_dir = os.path.join(outdir, f"{seed // 1000 * 1000:06d}") if subdirs else outdir
+                            os.makedirs(image_dir, exist_ok=True)
+                            PIL.Image.fromarray(_src, "RGB").save(os.path.join(image_dir, f"src_{seed:06d}.png"))
+                            PIL.Image.fromarray(_tgt, "RGB").save(os.path.join(image_dir, f"tgt_{seed:06d}.png"))
+                            PIL.Image.fromarray(image, "RGB").save(os.path.join(image_dir, f"sample_{seed:06d}.png"))
+                _barrier()              # keep the ranks in step (per-batch metric all_reduce)
+                yield r
+
+    return ImageIterable()
+
+
+def get_metrics(image_iter, device=torch.device("cuda")):
+    """PSNR leg of calculate_metrics.get_metrics / calculate_stats_for_iterable_nvs
+    (calculate_metrics.py:148,221-236): per-image PSNR of uint8 images against tgt, fp64 sum,
+    two int64 counters and one fp64 scalar all_reduced.  The Inception/DINOv2 detectors need
+    network downloads and are out of scope."""
+    psnr_sum = torch.zeros([], dtype=torch.float64, device=device)
+    count = torch.zeros([], dtype=torch.int64, device=device)
+    for r in image_iter:
+        if r.images is None:
+            continue
+        img = r.images.to(device).to(torch.float64)
+        tgt = r.tgt.to(device).clip(0, 255).to(torch.uint8).to(torch.float64)
+        if tgt.shape[0] != img.shape[0]:        # dual-source: targets are duplicated per source
+            tgt = tgt[::2]
+        mse = ((img - tgt) ** 2).mean(dim=(1, 2, 3))
+        psnr_sum += (10 * torch.log10(255.0 ** 2 / mse.clamp_min(1e-12))).sum()
+        count += img.shape[0]
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.all_reduce(psnr_sum)
+        torch.distributed.all_reduce(count)
+    n = int(count.item())
+    return dict(psnr=float(psnr_sum.item() / max(n, 1)), num_images=n)
