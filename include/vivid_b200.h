@@ -14,9 +14,12 @@
  *     void*), no implicit synchronisation, no allocation on the hot path;
  *   - the library is GPU-only: there is no CPU fallback.
  *
- * Activation layout inside the library is NHWC ("pixels x channels"), bf16 for
- * GEMM operands and fp32 for the residual stream.  Channel counts of GEMM
- * operands are padded to multiples of 64 (inputs) / 16 (outputs).
+ * Activation layout inside the library is NHWC ("pixels x channels") in ONE
+ * 16-bit format for GEMM operands and the residual stream alike: IEEE fp16, the
+ * reference's own reduced precision (training/models.py:632) — a build with
+ * -DVB_OP_BF16 switches it to bf16.  Accumulation (TMEM), normalisation
+ * statistics and the sampler state are fp32.  Channel counts of GEMM operands
+ * are padded to multiples of 64 (inputs) / 16 (outputs).
  */
 #ifndef VIVID_B200_H_
 #define VIVID_B200_H_
@@ -45,12 +48,14 @@ int vb_device_check(void);
 /* sizeof() of the descriptor structs below, in declaration order (0 = vb_weight_prep_desc ... 7 = vb_heun_desc);
  * lets a foreign-language binding verify its mirror of the layout.  -1 for an unknown index. */
 int vb_struct_size(int which);
+/* vb_dtype of GEMM operands / stream in this build (VB_F16 unless built with -DVB_OP_BF16). */
+int vb_operand_dtype(void);
 
 /* ------------------------------------------------------------------------
  * Weight preparation — replaces the per-call prologue of MPConv.forward
  * (reference training/models.py:115-121 + normalize :37-42):
  *   w_eff = gain * w / (eps*sqrt(K) + ||w||_2 per out-channel),  K = cin*taps, eps = 1e-4
- * computed in fp32 from fp32/fp16 parameters, rounded once to bf16 and
+ * computed in fp32 from fp32/fp16 parameters, rounded once to 16 bits and
  * repacked OIHW -> [cout_pad][tap][cin_pad] (K-major GEMM B operand).
  * Optional: fold the two mp_cat scale factors (models.py:78-84) into the
  * input-channel segments [0,split) and [split,cin); de-interleave the qkv /
@@ -63,7 +68,7 @@ typedef struct vb_weight_prep_desc {
   const void* src; /* [cout][cin][taps] contiguous */
   void* dst;
   int32_t src_dtype; /* vb_dtype */
-  int32_t dst_dtype; /* VB_BF16 (padded, repacked) or VB_F32 (plain) */
+  int32_t dst_dtype; /* VB_F16 / VB_BF16 = the library's operand format (padded, repacked) or VB_F32 (plain) */
   int32_t cout, cin, taps;
   int32_t cout_pad; /* rows of dst (>= cout, extra rows zero) */
   int32_t split;    /* = cin when there is a single input segment */
@@ -79,35 +84,43 @@ int vb_weight_prep(const vb_weight_prep_desc* d, void* stream);
  * replaces F.conv2d in MPConv.forward (models.py:126) together with the
  * pointwise ops the reference runs around it (Block.forward, models.py:165-206):
  *   flags VB_F_MODSILU : v = mp_silu(v * mod[b][c])                 (:175-176)
- *   flags VB_F_RESIDUAL: v = mp_sum(res, v, res_t)                  (:184,202)
+ *   res_mode           : v = mp_sum(res, v, res_t)                  (:184,202)
  *   flags VB_F_CLIP    : v = clamp(v, -clip, clip)                  (:204-205)
  *   epi  VB_EPI_QKVNORM: per-(token, head, q|k|v) normalize over D and scatter
- *                        to [B][heads][seq][D] bf16 tensors         (:192-193,283-297)
+ *                        to [B][heads][seq][D] 16-bit tensors       (:192-193,283-297)
  * GEMM view: M = B*H*W pixels, N = cout, K = taps*(cin_pad+cin2_pad).
  * ------------------------------------------------------------------------ */
 enum { VB_EPI_PLAIN = 0, VB_EPI_QKVNORM = 1 };
-enum { VB_F_MODSILU = 1, VB_F_RESIDUAL = 2, VB_F_CLIP = 4 };
+enum { VB_F_MODSILU = 1, VB_F_CLIP = 4 };
+/* residual input: none | mp_sum(res, v) | mp_sum(pixel_norm(res), v)  (the enc-flavour block normalises its input
+ * before using it as the residual base, models.py:171,184; recomputed in the epilogue instead of stored) */
+enum { VB_RES_NONE = 0, VB_RES_PLAIN = 1, VB_RES_PIXNORM = 2 };
+/* output slots: v | mp_silu(v*scale) | pixel_norm(v) | mp_silu(pixel_norm(v)).  The NORM kinds need the whole
+ * channel extent in one tile (cout_pad == block_n <= 256): this is the next block's pixel-norm fused here. */
+enum { VB_OUT_NONE = 0, VB_OUT_RAW = 1, VB_OUT_SILU = 2, VB_OUT_NORM = 3, VB_OUT_NORM_SILU = 4 };
 
 typedef struct vb_conv_desc {
-  const void* x;  /* bf16 NHWC [B][H][W][cin_pad] */
-  const void* x2; /* optional second channel segment (mp_cat folded into K), bf16 NHWC [B][H][W][cin2_pad] */
-  const void* w;  /* bf16 [cout_pad][taps*(cin_pad+cin2_pad)] from vb_weight_prep */
+  const void* x;  /* 16-bit NHWC [B][H][W][cin_pad] */
+  const void* x2; /* optional second channel segment (mp_cat folded into K), 16-bit NHWC [B][H][W][cin2_pad] */
+  const void* w;  /* 16-bit [cout_pad][taps*(cin_pad+cin2_pad)] from vb_weight_prep */
   const float* mod; /* fp32 [B][mod_stride], pre-offset to this layer's first channel */
-  const float* res; /* fp32 [B*H*W][ld_res] */
-  float* out_f32;   /* optional fp32 [B*H*W][ld_f32] */
-  void* out_bf16;   /* optional bf16 [B*H*W][ld_bf16] */
-  void* out_silu;   /* optional bf16 [B*H*W][ld_silu] = mp_silu(result) */
-  void* part_out[3]; /* QKVNORM: q,k,v (or k,v) bf16 [B/seg_div][heads][part_seq[j]][head_dim] */
+  const void* res;  /* 16-bit NHWC [B*H*W][cout_pad] residual stream (TMA-staged through shared memory) */
+  void* out[3];     /* 16-bit NHWC [B*H*W][cout_pad] outputs (shared-memory staged, TMA stores) */
+  float* out_f32;   /* optional fp32 [B*H*W][ld_f32] copy of v, direct stores (the 3-channel out_conv) */
+  void* part_out[3]; /* QKVNORM: q,k,v (or k,v) 16-bit [B/seg_div][heads][part_seq[j]][head_dim] */
   int32_t B, H, W;
   int32_t cin_pad, cin2_pad;
   int32_t cout_pad; /* multiple of block_n */
   int32_t taps;     /* 1 or 9 */
-  int32_t block_n;  /* 16..256, multiple of 16 */
+  int32_t block_n;  /* 16..256, multiple of 16 (multiple of 64 when res/out[] are used) */
   int32_t epi_mode, flags;
-  int32_t mod_stride, ld_res, ld_f32, ld_bf16, ld_silu;
+  int32_t mod_stride, ld_f32;
+  int32_t res_mode;
+  int32_t out_kind[3];
   int32_t head_dim, parts, seg_div;
   int32_t part_seq[3]; /* total sequence length of each destination */
   int32_t part_off[3]; /* first sequence slot written by image segment 0 */
+  float out_scale[3];  /* VB_OUT_SILU: mp_silu(v * scale) (mp_cat weight folded in) */
   float res_t, clip;
 } vb_conv_desc;
 int vb_conv(const vb_conv_desc* d, void* stream);
@@ -121,31 +134,33 @@ int vb_conv(const vb_conv_desc* d, void* stream);
  * unconditional gnet's all-zero source features, snapshot models.py:616-625).
  * ------------------------------------------------------------------------ */
 typedef struct vb_attn_desc {
-  const void* q; /* bf16 [B][heads][sq][D] */
-  const void* k; /* bf16 [B][heads][sk][D] */
-  const void* v; /* bf16 [B][heads][sk][D] */
-  void* y;       /* bf16 [B][sq][heads*D] (NHWC) */
+  const void* q; /* 16-bit [B][heads][sq][D] */
+  const void* k; /* 16-bit [B][heads][sk][D] */
+  const void* v; /* 16-bit [B][heads][sk][D] */
+  void* y;       /* 16-bit [B][sq][heads*D] (NHWC) */
   int32_t B, heads, sq, sk, head_dim;
   int32_t zero_keys;
 } vb_attn_desc;
 int vb_attn(const vb_attn_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------
- * Fused elementwise passes (vectorised, coalesced; warp-shuffle reductions).
- * kind selects the pass; unused fields are ignored.  N = pixels, C = channels.
- *   VB_EW_PIXNORM   out_f32 = x/(eps+||x||_C/sqrt(C)); out_silu = mp_silu(out)   (models.py:171, :37-42)
- *   VB_EW_DOWN_PIXNORM  2x2 mean pool (resample 'down', :48-61) then PIXNORM
- *   VB_EW_UP        nearest x2 (resample 'up'); out_f32 = up(x); out_silu = mp_silu(up(x))
- *   VB_EW_CAT       mp_cat(a,b,t) (:78-84): out_bf16 = cat; out_silu = mp_silu(cat)
- *   VB_EW_SILU      out_silu = mp_silu(x) (+ optional bf16 copy)
+ * Fused elementwise passes over the 16-bit NHWC stream (vectorised, coalesced;
+ * warp-shuffle reductions; fp32 math).  Only the passes that cannot ride in a
+ * GEMM epilogue remain:
+ *   VB_EW_PIXNORM      out = x/(eps+||x||_C/sqrt(C)); out_silu = mp_silu(out)    (models.py:171, :37-42)
+ *                      (levels whose channel count exceeds one GEMM tile: C > 256)
+ *   VB_EW_DOWN_PIXNORM 2x2 mean pool (resample 'down', :48-61) then PIXNORM
+ *   VB_EW_UP           nearest x2 (resample 'up'): out = up(x); out_silu = mp_silu(up(x))
+ *   VB_EW_CAT          mp_cat(a,b,t) (:78-84): out = cat; out_silu = mp_silu(cat)  (kept for odd channel counts;
+ *                      the plans fold mp_cat into the consumer GEMM's K loop instead)
+ *   VB_EW_SILU         out = x*wa (optional), out_silu = mp_silu(x*wa)
  * ------------------------------------------------------------------------ */
 enum { VB_EW_PIXNORM = 0, VB_EW_DOWN_PIXNORM = 1, VB_EW_UP = 2, VB_EW_CAT = 3, VB_EW_SILU = 4 };
 typedef struct vb_ew_desc {
-  const float* a; /* fp32 [pixels_in][ca] */
-  const float* b; /* fp32 [pixels][cb] (CAT) */
-  float* out_f32;
-  void* out_bf16;
-  void* out_silu;
+  const void* a; /* 16-bit [pixels_in][ca] */
+  const void* b; /* 16-bit [pixels][cb] (CAT) */
+  void* out;      /* optional 16-bit result */
+  void* out_silu; /* optional 16-bit mp_silu(result) */
   int32_t kind;
   int32_t B, H, W; /* OUTPUT spatial extent */
   int32_t ca, cb;
@@ -180,7 +195,7 @@ int vb_embed(const vb_emb_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------
  * EDM preconditioning (NVPrecond.forward, snapshot models.py:588-595,608-611,632)
- *   vb_precond_in : x_in = c_in(sigma)*x  -> NHWC bf16, + ones channel, + SR
+ *   vb_precond_in : x_in = c_in(sigma)*x  -> NHWC 16-bit, + ones channel, + SR
  *                   conditioning channels (cond + noisy_sr*noise), zero padded to cpad
  *   vb_precond_out: D = c_skip*x + c_out*F   (fp32 NCHW)
  * ------------------------------------------------------------------------ */
@@ -189,7 +204,7 @@ typedef struct vb_precond_in_desc {
   const float* cond;  /* optional fp32 NCHW [B][3][R][R] */
   const float* noise; /* optional fp32 NCHW [B][3][R][R], added as noisy_sr*noise */
   const float* sigma; /* [B] or [1]; NULL => no c_in scaling (encoder input) */
-  void* out;          /* bf16 NHWC [B][R][R][cpad] */
+  void* out;          /* 16-bit NHWC [B][R][R][cpad] */
   int32_t B, R, cpad, sigma_n, sigma_stride;
   int64_t img_stride; /* elements between consecutive images of x (allows x[::2]) */
   float sigma_data, noisy_sr;

@@ -45,15 +45,17 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def prep_weight(L, lib, w, gain=1.0, cout_pad=None, perm=(0, 0)):
+def prep_weight(L, lib, w, gain=1.0, cout_pad=None, perm=(0, 0), split=None, scales=(1.0, 1.0)):
     cout, cin = w.shape[:2]
     taps = w[0, 0].numel() if w.ndim == 4 else 1
     cout_pad = cout_pad or pad_to(cout, 16)
-    dst = torch.empty(cout_pad, taps, pad_to(cin, 64), dtype=torch.bfloat16, device=w.device)
+    split = cin if split is None else split
+    sa, sb = pad_to(split, 64), (pad_to(cin - split, 64) if cin > split else 0)
+    dst = torch.empty(cout_pad, taps, sa + sb, dtype=L.operand_torch_dtype(), device=w.device)
     d = L.WeightPrepDesc(src=w.data_ptr(), dst=dst.data_ptr(), src_dtype={torch.float32: 0, torch.float16: 1}[w.dtype],
-                         dst_dtype=L.VB_BF16, cout=cout, cin=cin, taps=taps, cout_pad=cout_pad, split=cin,
-                         seg_a_pad=pad_to(cin, 64), seg_b_pad=0, perm_parts=perm[0], perm_dim=perm[1], gain=gain,
-                         scale_a=1.0, scale_b=1.0)
+                         dst_dtype=lib.vb_operand_dtype(), cout=cout, cin=cin, taps=taps, cout_pad=cout_pad, split=split,
+                         seg_a_pad=sa, seg_b_pad=sb, perm_parts=perm[0], perm_dim=perm[1], gain=gain,
+                         scale_a=scales[0], scale_b=scales[1])
     L.check(lib.vb_weight_prep(C.byref(d), stream()), "vb_weight_prep")
     return dst
 
@@ -64,71 +66,119 @@ def ref_weight(w, gain=1.0):
     return gain * w32 / (1e-4 * math.sqrt(w32[0].numel()) + n)
 
 
+def pixnorm(x):          # NCHW, reference normalize(x, dim=1)
+    n = x.norm(dim=1, keepdim=True)
+    return x / (1e-4 + n / math.sqrt(x.shape[1]))
+
+
+def mp_silu(x):
+    return torch.nn.functional.silu(x) / 0.596
+
+
 # ------------------------------------------------------------------------------- single kernels
 CONV_CASES = [
-    # B, R, cin, cout, taps, block_n, flags, gain
-    (1, 16, 64, 64, 1, 64, 0, 1.0),
-    (2, 16, 128, 128, 9, 128, 0, 1.0),
-    (2, 32, 64, 128, 9, 128, 1, 1.0),
-    (2, 64, 128, 128, 9, 128, 2, 1.0),
-    (3, 8, 192, 256, 9, 256, 7, 1.0),        # odd batch, 2 images per tile
-    (5, 4, 64, 64, 9, 64, 6, 1.0),           # 8 images per tile, ragged
-    (2, 16, 320, 192, 1, 192, 0, 1.0),       # N = 192, five K chunks
-    (2, 64, 4, 128, 9, 128, 0, 1.0),         # first conv: 4 -> 64 padded input channels
-    (2, 64, 128, 3, 9, 16, 0, 0.7),          # out_conv: 3 -> 16 padded output channels, gain
-    (1, 256, 64, 64, 9, 64, 7, 1.0),         # SR resolution
-    (40, 16, 384, 384, 9, 128, 7, 1.0),      # persistent loop, several tiles per CTA
+    # B, R, cin, cout, taps, block_n, modsilu, res_mode, clip, out kinds
+    (1, 16, 64, 64, 1, 64, 0, 0, 0, (1,)),
+    (2, 16, 128, 128, 9, 128, 0, 0, 0, (1, 2)),
+    (2, 32, 64, 128, 9, 128, 1, 0, 0, (1,)),
+    (2, 64, 128, 128, 9, 128, 0, 1, 1, (1, 4, 2)),      # residual + fused next-block pixel-norm + skip silu
+    (2, 64, 128, 128, 9, 128, 0, 2, 1, (1, 4)),         # residual pixel-norm recomputed in the epilogue
+    (3, 8, 192, 256, 9, 256, 1, 2, 1, (1, 3, 4)),       # odd batch, 4 chunks (streamed residual ring), 3 slots
+    (5, 4, 64, 64, 9, 64, 0, 1, 1, (1,)),               # 8 images per tile, ragged
+    (2, 16, 320, 192, 1, 192, 0, 1, 0, (3, 4)),         # N = 192 (3 chunks), five K chunks, NORM outputs only
+    (2, 64, 4, 128, 9, 128, 0, 0, 0, (1, 4)),           # first conv: 4 -> 64 padded input channels
+    (1, 256, 64, 64, 9, 64, 0, 2, 1, (1, 4, 2)),        # SR resolution
+    (40, 16, 384, 384, 9, 128, 0, 1, 1, (1, 2)),        # persistent loop, several tiles per CTA, 3 N tiles
+    (40, 16, 384, 384, 9, 192, 1, 0, 0, (1,)),
 ]
 
 
-@pytest.mark.parametrize("B,R,cin,cout,taps,bn,flags,gain", CONV_CASES)
-def test_conv_gemm_vs_conv2d(env, B, R, cin, cout, taps, bn, flags, gain):
+@pytest.mark.parametrize("B,R,cin,cout,taps,bn,modsilu,res_mode,clip,kinds", CONV_CASES)
+def test_conv_gemm_vs_conv2d(env, B, R, cin, cout, taps, bn, modsilu, res_mode, clip, kinds):
     """vb_conv (+vb_weight_prep) vs MPConv semantics (models.py:115-126) with the fused epilogues."""
     L, lib, dev = env
+    dt = L.operand_torch_dtype()
     g = torch.Generator().manual_seed(B * 1000 + R + cin + cout)
-    cin_pad, cout_pad, k = pad_to(cin, 64), pad_to(cout, bn), 3 if taps == 9 else 1
+    cin_pad, k = pad_to(cin, 64), 3 if taps == 9 else 1
     x = torch.randn(B, cin, R, R, generator=g).to(dev)
     w = torch.randn(cout, cin, k, k, generator=g).to(dev)
-    x_nhwc = torch.zeros(B, R, R, cin_pad, dtype=torch.bfloat16, device=dev)
-    x_nhwc[..., :cin] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
-    wp = prep_weight(L, lib, w, gain=gain, cout_pad=cout_pad)
-    wr = ref_weight(w, gain)
-    assert (wp[:cout].float().reshape(cout, taps, cin_pad)[..., :cin].permute(0, 2, 1).reshape(wr.shape)
-            - wr.to(torch.bfloat16).float()).abs().max() <= 4e-3 * wr.abs().max()
-    xr = x_nhwc[..., :cin].float().permute(0, 3, 1, 2)
-    wq = wp[:cout].float().reshape(cout, taps, cin_pad)[..., :cin].permute(0, 2, 1).reshape(cout, cin, k, k)
-    y = torch.nn.functional.conv2d(xr, wq, padding=k // 2)
+    x_nhwc = torch.zeros(B, R, R, cin_pad, dtype=dt, device=dev)
+    x_nhwc[..., :cin] = x.permute(0, 2, 3, 1).to(dt)
+    wp = prep_weight(L, lib, w, cout_pad=cout)
+    wr = ref_weight(w)
+    wq = wp.float().reshape(cout, taps, cin_pad)[..., :cin].permute(0, 2, 1).reshape(cout, cin, k, k)
+    assert (wq - wr.to(dt).float()).abs().max() <= 2e-3 * wr.abs().max()
+    y = torch.nn.functional.conv2d(x_nhwc[..., :cin].float().permute(0, 3, 1, 2), wq, padding=k // 2)
     mod = res = None
-    if flags & L.VB_F_MODSILU:
-        mod = (torch.randn(B, cout_pad, generator=g) * 0.3 + 1).to(dev)
-        y = torch.nn.functional.silu(y * mod[:, :cout, None, None]) / 0.596
-    if flags & L.VB_F_RESIDUAL:
-        res = torch.randn(B, R, R, cout_pad, generator=g).to(dev)
-        y = (res[..., :cout].permute(0, 3, 1, 2) * 0.7 + y * 0.3) / math.sqrt(0.7 ** 2 + 0.3 ** 2)
-    if flags & L.VB_F_CLIP:
+    if modsilu:
+        mod = (torch.randn(B, cout, generator=g) * 0.3 + 1).to(dev)
+        y = mp_silu(y * mod[:, :, None, None])
+    if res_mode:
+        res = (torch.randn(B, R, R, cout, generator=g) * 1.7).to(dev).to(dt)
+        r = res.float().permute(0, 3, 1, 2)
+        if res_mode == 2:
+            r = pixnorm(r)
+        y = (r * 0.7 + y * 0.3) / math.sqrt(0.7 ** 2 + 0.3 ** 2)
+    if clip:
         y = y.clamp(-1.5, 1.5)
-    o32 = torch.full((B, R, R, cout_pad), float("nan"), device=dev)
-    o16 = torch.zeros(B, R, R, cout_pad, dtype=torch.bfloat16, device=dev)
-    osl = torch.zeros(B, R, R, cout_pad, dtype=torch.bfloat16, device=dev)
-    d = L.ConvDesc(x=x_nhwc.data_ptr(), w=wp.data_ptr(), mod=L.ptr(mod), res=L.ptr(res), out_f32=o32.data_ptr(),
-                   out_bf16=o16.data_ptr(), out_silu=osl.data_ptr(), B=B, H=R, W=R, cin_pad=cin_pad, cin2_pad=0,
-                   cout_pad=cout_pad, taps=taps, block_n=bn, epi_mode=L.VB_EPI_PLAIN, flags=flags, mod_stride=cout_pad,
-                   ld_res=cout_pad, ld_f32=cout_pad, ld_bf16=cout_pad, ld_silu=cout_pad, res_t=0.3, clip=1.5)
+    refs = {1: y, 2: mp_silu(y * 0.8), 3: pixnorm(y), 4: mp_silu(pixnorm(y))}
+    outs = [torch.full((B, R, R, cout), float("nan"), dtype=dt, device=dev) for _ in kinds]
+    o32 = torch.full((B, R, R, cout), float("nan"), device=dev)
+    d = L.ConvDesc(x=x_nhwc.data_ptr(), w=wp.data_ptr(), mod=L.ptr(mod), res=L.ptr(res), out_f32=o32.data_ptr(), B=B, H=R, W=R,
+                   cin_pad=cin_pad, cin2_pad=0, cout_pad=cout, taps=taps, block_n=bn, epi_mode=L.VB_EPI_PLAIN,
+                   flags=(L.VB_F_MODSILU if modsilu else 0) | (L.VB_F_CLIP if clip else 0), mod_stride=cout, ld_f32=cout,
+                   res_mode=res_mode, res_t=0.3, clip=1.5)
+    for i, kd in enumerate(kinds):
+        d.out[i], d.out_kind[i], d.out_scale[i] = outs[i].data_ptr(), kd, 0.8
+    if any(kd >= 3 for kd in kinds) or res_mode == 2:
+        assert bn == cout
     L.check(lib.vb_conv(C.byref(d), stream()), "vb_conv")
     torch.cuda.synchronize()
-    assert rel(o32[..., :cout].permute(0, 3, 1, 2), y) < 2e-5
-    assert rel(o16[..., :cout].permute(0, 3, 1, 2).float(), y) < 4e-3
-    assert rel(osl[..., :cout].permute(0, 3, 1, 2).float(), torch.nn.functional.silu(y) / 0.596) < 5e-3
-    if cout_pad > cout:
-        assert o32[..., cout:].abs().max().item() == 0.0
-    # linearity of the GEMM (size-independent property): conv(2x) == 2 conv(x) exactly in bf16/fp32
-    if flags == 0:
-        x2 = (x_nhwc.float() * 2).to(torch.bfloat16)
+    tol = 2e-3 if dt == torch.float16 else 8e-3
+    assert rel(o32.permute(0, 3, 1, 2), y) < (2e-3 if (modsilu or res_mode == 2) else 2e-5)   # tanh-based silu / rsqrt
+    for o, kd in zip(outs, kinds):
+        assert rel(o.float().permute(0, 3, 1, 2), refs[kd]) < tol, kd
+    # linearity of the GEMM (size-independent property): conv(2x) == 2 conv(x) exactly
+    if not (modsilu or res_mode or clip):
+        x2 = (x_nhwc.float() * 2).to(dt)
         o2 = torch.empty_like(o32)
-        d.x, d.out_f32, d.out_bf16, d.out_silu = x2.data_ptr(), o2.data_ptr(), None, None
+        d.x, d.out_f32 = x2.data_ptr(), o2.data_ptr()
         L.check(lib.vb_conv(C.byref(d), stream()), "vb_conv")
         torch.cuda.synchronize()
         assert torch.equal(o2, o32 * 2)
+
+
+def test_conv_two_source_and_narrow_output(env):
+    """mp_cat folded into the K loop (models.py:78-84,403): conv(cat(wa*a, wb*b)) with the weights split over two tensors;
+    and the 3-channel out_conv (padded to 16 columns, fp32 direct stores)."""
+    L, lib, dev = env
+    dt = L.operand_torch_dtype()
+    g = torch.Generator().manual_seed(9)
+    B, R, na, nb, cout = 2, 16, 128, 64, 128
+    a = torch.randn(B, R, R, na, generator=g).to(dev).to(dt)
+    b = torch.randn(B, R, R, nb, generator=g).to(dev).to(dt)
+    w = torch.randn(cout, na + nb, 3, 3, generator=g).to(dev)
+    wa, wb = 1.3, 0.6
+    wp = prep_weight(L, lib, w, cout_pad=cout, split=na, scales=(wa, wb))
+    out = torch.empty(B, R, R, cout, dtype=dt, device=dev)
+    d = L.ConvDesc(x=a.data_ptr(), x2=b.data_ptr(), w=wp.data_ptr(), B=B, H=R, W=R, cin_pad=na, cin2_pad=nb, cout_pad=cout,
+                   taps=9, block_n=128, epi_mode=L.VB_EPI_PLAIN)
+    d.out[0], d.out_kind[0] = out.data_ptr(), L.VB_OUT_RAW
+    L.check(lib.vb_conv(C.byref(d), stream()), "vb_conv 2src")
+    cat = torch.cat([a.float() * wa, b.float() * wb], dim=-1).permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(cat, ref_weight(w), padding=1)
+    assert rel(out.float().permute(0, 3, 1, 2), ref) < 3e-3
+    # out_conv
+    w3 = torch.randn(3, 128, 3, 3, generator=g).to(dev)
+    wp3 = prep_weight(L, lib, w3, gain=0.7, cout_pad=16)
+    o32 = torch.full((B, R, R, 16), float("nan"), device=dev)
+    d = L.ConvDesc(x=a.data_ptr(), w=wp3.data_ptr(), out_f32=o32.data_ptr(), B=B, H=R, W=R, cin_pad=na, cout_pad=16, taps=9,
+                   block_n=16, epi_mode=L.VB_EPI_PLAIN, ld_f32=16)
+    L.check(lib.vb_conv(C.byref(d), stream()), "vb_conv out")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(a.float().permute(0, 3, 1, 2), wp3[:3].float().reshape(3, 9, 128).permute(0, 2, 1).reshape(3, 128, 3, 3), padding=1)
+    assert rel(o32[..., :3].permute(0, 3, 1, 2), ref) < 2e-5
+    assert o32[..., 3:].abs().max().item() == 0.0
 
 
 @pytest.mark.parametrize("B,R,ch,heads,D,parts,seg_div,bn", [(2, 16, 128, 2, 64, 3, 1, 128), (2, 8, 256, 4, 64, 2, 1, 128),
@@ -136,23 +186,24 @@ def test_conv_gemm_vs_conv2d(env, B, R, cin, cout, taps, bn, flags, gain):
 def test_qkv_epilogue(env, B, R, ch, heads, D, parts, seg_div, bn):
     """1x1 GEMM + per-(token, head, q|k|v) normalise + scatter (models.py:192-193, 283-297)."""
     L, lib, dev = env
+    dt = L.operand_torch_dtype()
     g = torch.Generator().manual_seed(1)
     cout = heads * parts * D
     x = torch.randn(B, ch, R, R, generator=g).to(dev)
     w = torch.randn(cout, ch, 1, 1, generator=g).to(dev)
-    x_nhwc = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().to(dt)
     wp = prep_weight(L, lib, w, cout_pad=cout, perm=(parts, D))
     S, Bo = R * R, B // seg_div
     seq = [S if (j == 0 and parts == 3) else S * (1 + seg_div) for j in range(parts)]
     off = [0 if parts == 3 else S] * parts
-    outs = [torch.zeros(Bo, heads, seq[j], D, dtype=torch.bfloat16, device=dev) for j in range(parts)]
+    outs = [torch.zeros(Bo, heads, seq[j], D, dtype=dt, device=dev) for j in range(parts)]
     d = L.ConvDesc(x=x_nhwc.data_ptr(), w=wp.data_ptr(), part_out=(C.c_void_p * 3)(*[o.data_ptr() for o in outs] + [None] * (3 - parts)),
                    B=B, H=R, W=R, cin_pad=ch, cin2_pad=0, cout_pad=cout, taps=1, block_n=bn, epi_mode=L.VB_EPI_QKVNORM,
                    head_dim=D, parts=parts, seg_div=seg_div, part_seq=(C.c_int32 * 3)(*(seq + [0] * (3 - parts))),
                    part_off=(C.c_int32 * 3)(*(off + [0] * (3 - parts))))
     L.check(lib.vb_conv(C.byref(d), stream()), "vb_conv qkv")
     torch.cuda.synchronize()
-    y = torch.nn.functional.conv2d(x_nhwc.float().permute(0, 3, 1, 2), ref_weight(w).to(torch.bfloat16).float())
+    y = torch.nn.functional.conv2d(x_nhwc.float().permute(0, 3, 1, 2), ref_weight(w).to(dt).float())
     y = y.reshape(B, heads, D, parts, S)
     y = y / (1e-4 + y.norm(dim=2, keepdim=True) / math.sqrt(D))
     for j in range(parts):
@@ -168,14 +219,15 @@ def test_qkv_epilogue(env, B, R, ch, heads, D, parts, seg_div, bn):
 def test_fused_attention(env, B, h, sq, sk, D, zk):
     """vb_attn vs softmax(q k^T / sqrt(D)) v on normalised q,k,v, incl. analytic zero keys and ragged lengths."""
     L, lib, dev = env
+    dt = L.operand_torch_dtype()
     g = torch.Generator().manual_seed(sq + sk)
 
     def nrm(t):
-        return (t / (1e-4 + t.norm(dim=-1, keepdim=True) / math.sqrt(D))).to(torch.bfloat16)
+        return (t / (1e-4 + t.norm(dim=-1, keepdim=True) / math.sqrt(D))).to(dt)
     q = nrm(torch.randn(B, h, sq, D, generator=g)).to(dev)
     k = nrm(torch.randn(B, h, sk, D, generator=g)).to(dev)
     v = nrm(torch.randn(B, h, sk, D, generator=g)).to(dev)
-    y = torch.zeros(B, sq, h * D, dtype=torch.bfloat16, device=dev)
+    y = torch.zeros(B, sq, h * D, dtype=dt, device=dev)
     d = L.AttnDesc(q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), y=y.data_ptr(), B=B, heads=h, sq=sq, sk=sk, head_dim=D,
                    zero_keys=zk)
     L.check(lib.vb_attn(C.byref(d), stream()), "vb_attn")
@@ -184,54 +236,56 @@ def test_fused_attention(env, B, h, sq, sk, D, zk):
     vz = torch.cat([v.float(), torch.zeros(B, h, zk, D, device=dev)], 2)
     w = (q.float() @ kz.transpose(-1, -2) / math.sqrt(D)).softmax(-1)
     ref = (w @ vz).permute(0, 2, 1, 3).reshape(B, sq, h * D)
-    assert rel(y.float(), ref) < 6e-3
+    assert rel(y.float(), ref) < (2e-3 if dt == torch.float16 else 6e-3)
 
 
 def test_elementwise_passes(env):
     L, lib, dev = env
+    dt = L.operand_torch_dtype()
+    tol = 1.5e-3 if dt == torch.float16 else 6e-3
     from oracle import vivid_oracle as O
     g = torch.Generator().manual_seed(3)
     B, R = 3, 8
-    for ch in (64, 192, 512):
-        a = torch.randn(B, R, R, ch, generator=g).to(dev)
-        nchw = a.permute(0, 3, 1, 2)
-        o32 = torch.empty_like(a)
-        osl = torch.empty(B, R, R, ch, dtype=torch.bfloat16, device=dev)
-        d = L.EwDesc(a=a.data_ptr(), out_f32=o32.data_ptr(), out_silu=osl.data_ptr(), kind=L.VB_EW_PIXNORM, B=B, H=R, W=R, ca=ch)
+    for ch in (64, 128, 192, 384, 512):
+        a = torch.randn(B, R, R, ch, generator=g).to(dev).to(dt)
+        nchw = a.float().permute(0, 3, 1, 2)
+        o = torch.empty_like(a)
+        osl = torch.empty_like(a)
+        d = L.EwDesc(a=a.data_ptr(), out=o.data_ptr(), out_silu=osl.data_ptr(), kind=L.VB_EW_PIXNORM, B=B, H=R, W=R, ca=ch)
         L.check(lib.vb_eltwise(C.byref(d), stream()), "pixnorm")
         ref = O.normalize(nchw, dim=1)
-        assert rel(o32.permute(0, 3, 1, 2), ref) < 1e-6
-        assert rel(osl.float().permute(0, 3, 1, 2), O.mp_silu(ref)) < 4e-3
-        # idempotence (size-independent property): normalising a normalised tensor changes nothing beyond eps
-        d2 = L.EwDesc(a=o32.data_ptr(), out_f32=a.data_ptr(), kind=L.VB_EW_PIXNORM, B=B, H=R, W=R, ca=ch)
+        assert rel(o.float().permute(0, 3, 1, 2), ref) < tol
+        assert rel(osl.float().permute(0, 3, 1, 2), O.mp_silu(ref)) < tol
+        # idempotence (size-independent property): normalising a normalised tensor changes nothing beyond rounding
+        o2 = torch.empty_like(a)
+        d2 = L.EwDesc(a=o.data_ptr(), out=o2.data_ptr(), kind=L.VB_EW_PIXNORM, B=B, H=R, W=R, ca=ch)
         L.check(lib.vb_eltwise(C.byref(d2), stream()), "pixnorm")
-        assert rel(a, o32) < 2e-4
-        a = nchw.permute(0, 2, 3, 1).contiguous()
+        assert rel(o2.float(), o.float()) < tol
         # 2x2 mean pool + pixnorm
-        o32 = torch.empty(B, R // 2, R // 2, ch, device=dev)
-        d = L.EwDesc(a=a.data_ptr(), out_f32=o32.data_ptr(), kind=L.VB_EW_DOWN_PIXNORM, B=B, H=R // 2, W=R // 2, ca=ch)
+        od = torch.empty(B, R // 2, R // 2, ch, dtype=dt, device=dev)
+        d = L.EwDesc(a=a.data_ptr(), out=od.data_ptr(), kind=L.VB_EW_DOWN_PIXNORM, B=B, H=R // 2, W=R // 2, ca=ch)
         L.check(lib.vb_eltwise(C.byref(d), stream()), "down")
-        assert rel(o32.permute(0, 3, 1, 2), O.normalize(O.resample(nchw, "down"), dim=1)) < 1e-6
+        assert rel(od.float().permute(0, 3, 1, 2), O.normalize(O.resample(nchw, "down"), dim=1)) < tol
         # nearest x2
-        u32 = torch.empty(B, 2 * R, 2 * R, ch, device=dev)
-        usl = torch.empty(B, 2 * R, 2 * R, ch, dtype=torch.bfloat16, device=dev)
-        d = L.EwDesc(a=a.data_ptr(), out_f32=u32.data_ptr(), out_silu=usl.data_ptr(), kind=L.VB_EW_UP, B=B, H=2 * R, W=2 * R, ca=ch)
+        u = torch.empty(B, 2 * R, 2 * R, ch, dtype=dt, device=dev)
+        usl = torch.empty_like(u)
+        d = L.EwDesc(a=a.data_ptr(), out=u.data_ptr(), out_silu=usl.data_ptr(), kind=L.VB_EW_UP, B=B, H=2 * R, W=2 * R, ca=ch)
         L.check(lib.vb_eltwise(C.byref(d), stream()), "up")
-        assert torch.equal(u32.permute(0, 3, 1, 2), O.resample(nchw, "up"))
-        assert rel(usl.float().permute(0, 3, 1, 2), O.mp_silu(O.resample(nchw, "up"))) < 4e-3
+        assert torch.equal(u.float().permute(0, 3, 1, 2), O.resample(nchw, "up"))
+        assert rel(usl.float().permute(0, 3, 1, 2), O.mp_silu(O.resample(nchw, "up"))) < tol
         # mp_cat
-        b = torch.randn(B, R, R, 128, generator=g).to(dev)
+        b = torch.randn(B, R, R, 128, generator=g).to(dev).to(dt)
         t = 0.5
         cc = math.sqrt((ch + 128) / ((1 - t) ** 2 + t ** 2))
         wa, wb = cc / math.sqrt(ch) * (1 - t), cc / math.sqrt(128) * t
-        c16 = torch.empty(B, R, R, ch + 128, dtype=torch.bfloat16, device=dev)
+        c16 = torch.empty(B, R, R, ch + 128, dtype=dt, device=dev)
         csl = torch.empty_like(c16)
-        d = L.EwDesc(a=a.data_ptr(), b=b.data_ptr(), out_bf16=c16.data_ptr(), out_silu=csl.data_ptr(), kind=L.VB_EW_CAT, B=B,
+        d = L.EwDesc(a=a.data_ptr(), b=b.data_ptr(), out=c16.data_ptr(), out_silu=csl.data_ptr(), kind=L.VB_EW_CAT, B=B,
                      H=R, W=R, ca=ch, cb=128, wa=wa, wb=wb)
         L.check(lib.vb_eltwise(C.byref(d), stream()), "cat")
-        ref = O.mp_cat(nchw, b.permute(0, 3, 1, 2), t=t)
-        assert rel(c16.float().permute(0, 3, 1, 2), ref) < 4e-3
-        assert rel(csl.float().permute(0, 3, 1, 2), O.mp_silu(ref)) < 4e-3
+        ref = O.mp_cat(nchw, b.float().permute(0, 3, 1, 2), t=t)
+        assert rel(c16.float().permute(0, 3, 1, 2), ref) < tol
+        assert rel(csl.float().permute(0, 3, 1, 2), O.mp_silu(ref)) < tol
     torch.cuda.synchronize()
 
 

@@ -22,14 +22,19 @@ only = os.environ.get("VB_ONLY")
 for idx, (R, cin, cout, taps, bn) in enumerate(SHAPES):
     if only is not None and str(idx) not in only.split(","):
         continue
-    x = torch.randn(B, R, R, cin, device=dev).to(torch.bfloat16)
-    w = torch.randn(cout, taps * cin, device=dev).to(torch.bfloat16) * 0.03
-    res = torch.randn(B * R * R, cout, device=dev)
-    o32 = torch.empty(B * R * R, cout, device=dev)
-    o16 = torch.empty(B * R * R, cout, dtype=torch.bfloat16, device=dev)
-    d = L.ConvDesc(x=x.data_ptr(), w=w.data_ptr(), res=res.data_ptr(), out_f32=o32.data_ptr(), out_bf16=o16.data_ptr(),
-                   B=B, H=R, W=R, cin_pad=cin, cin2_pad=0, cout_pad=cout, taps=taps, block_n=bn, epi_mode=0,
-                   flags=L.VB_F_RESIDUAL | L.VB_F_CLIP, ld_res=cout, ld_f32=cout, ld_bf16=cout, res_t=0.3, clip=256.0)
+    dt = L.operand_torch_dtype()
+    x = torch.randn(B, R, R, cin, device=dev).to(dt)
+    w = (torch.randn(cout, taps * cin, device=dev) * 0.03).to(dt)
+    res = torch.randn(B * R * R, cout, device=dev).to(dt)
+    o0 = torch.empty(B * R * R, cout, dtype=dt, device=dev)
+    o1 = torch.empty(B * R * R, cout, dtype=dt, device=dev)
+    fullrow = cout == bn and cout <= 256
+    d = L.ConvDesc(x=x.data_ptr(), w=w.data_ptr(), res=res.data_ptr(), B=B, H=R, W=R, cin_pad=cin, cin2_pad=0,
+                   cout_pad=cout, taps=taps, block_n=bn, epi_mode=0, flags=L.VB_F_CLIP,
+                   res_mode=L.VB_RES_PIXNORM if fullrow else L.VB_RES_PLAIN, res_t=0.3, clip=256.0)
+    d.out[0], d.out_kind[0] = o0.data_ptr(), L.VB_OUT_RAW
+    d.out[1], d.out_kind[1] = o1.data_ptr(), (L.VB_OUT_NORM_SILU if fullrow else L.VB_OUT_SILU)
+    d.out_scale[1] = 1.0
     plan = C.c_void_p()
     L.check(lib.vb_plan_create(C.byref(plan)), "create")
     L.check(lib.vb_plan_add_conv(plan, C.byref(d)), "add")

@@ -12,7 +12,9 @@ LIB_PATH = os.path.join(_HERE, "libvividb200.so")
 
 VB_F32, VB_F16, VB_BF16 = 0, 1, 2
 VB_EPI_PLAIN, VB_EPI_QKVNORM = 0, 1
-VB_F_MODSILU, VB_F_RESIDUAL, VB_F_CLIP = 1, 2, 4
+VB_F_MODSILU, VB_F_CLIP = 1, 4
+VB_RES_NONE, VB_RES_PLAIN, VB_RES_PIXNORM = 0, 1, 2
+VB_OUT_NONE, VB_OUT_RAW, VB_OUT_SILU, VB_OUT_NORM, VB_OUT_NORM_SILU = 0, 1, 2, 3, 4
 VB_EW_PIXNORM, VB_EW_DOWN_PIXNORM, VB_EW_UP, VB_EW_CAT, VB_EW_SILU = 0, 1, 2, 3, 4
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -25,12 +27,12 @@ class WeightPrepDesc(C.Structure):
 
 
 class ConvDesc(C.Structure):
-    _fields_ = [("x", vp), ("x2", vp), ("w", vp), ("mod", vp), ("res", vp), ("out_f32", vp), ("out_bf16", vp),
-                ("out_silu", vp), ("part_out", vp * 3), ("B", i32), ("H", i32), ("W", i32), ("cin_pad", i32),
-                ("cin2_pad", i32), ("cout_pad", i32), ("taps", i32), ("block_n", i32), ("epi_mode", i32),
-                ("flags", i32), ("mod_stride", i32), ("ld_res", i32), ("ld_f32", i32), ("ld_bf16", i32),
-                ("ld_silu", i32), ("head_dim", i32), ("parts", i32), ("seg_div", i32), ("part_seq", i32 * 3),
-                ("part_off", i32 * 3), ("res_t", f32), ("clip", f32)]
+    _fields_ = [("x", vp), ("x2", vp), ("w", vp), ("mod", vp), ("res", vp), ("out", vp * 3), ("out_f32", vp),
+                ("part_out", vp * 3), ("B", i32), ("H", i32), ("W", i32), ("cin_pad", i32), ("cin2_pad", i32),
+                ("cout_pad", i32), ("taps", i32), ("block_n", i32), ("epi_mode", i32), ("flags", i32),
+                ("mod_stride", i32), ("ld_f32", i32), ("res_mode", i32), ("out_kind", i32 * 3), ("head_dim", i32),
+                ("parts", i32), ("seg_div", i32), ("part_seq", i32 * 3), ("part_off", i32 * 3),
+                ("out_scale", f32 * 3), ("res_t", f32), ("clip", f32)]
 
 
 class AttnDesc(C.Structure):
@@ -39,7 +41,7 @@ class AttnDesc(C.Structure):
 
 
 class EwDesc(C.Structure):
-    _fields_ = [("a", vp), ("b", vp), ("out_f32", vp), ("out_bf16", vp), ("out_silu", vp), ("kind", i32),
+    _fields_ = [("a", vp), ("b", vp), ("out", vp), ("out_silu", vp), ("kind", i32),
                 ("B", i32), ("H", i32), ("W", i32), ("ca", i32), ("cb", i32), ("wa", f32), ("wb", f32)]
 
 
@@ -72,6 +74,7 @@ SIGNATURES = {
     "vb_abi_version": (C.c_int, []),
     "vb_device_check": (C.c_int, []),
     "vb_struct_size": (C.c_int, [C.c_int]),
+    "vb_operand_dtype": (C.c_int, []),
     "vb_weight_prep": (C.c_int, [C.POINTER(WeightPrepDesc), vp]),
     "vb_conv": (C.c_int, [C.POINTER(ConvDesc), vp]),
     "vb_attn": (C.c_int, [C.POINTER(AttnDesc), vp]),
@@ -126,6 +129,12 @@ def lib():
                                  f"{h.vb_struct_size(i)} in {LIB_PATH}; rebuild with `python -m vivid_b200.build`")
     _lib = h
     return h
+
+
+def operand_torch_dtype():
+    """torch dtype of GEMM operands / the residual stream in the loaded build (fp16 unless built with -DVB_OP_BF16)."""
+    import torch
+    return {VB_F16: torch.float16, VB_BF16: torch.bfloat16}[lib().vb_operand_dtype()]
 
 
 def check(rc, what="vivid_b200 call"):

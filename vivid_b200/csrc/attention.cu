@@ -4,14 +4,13 @@
 // (experiments/code/training/models.py:190-191, 274-280) and F.scaled_dot_product_attention of
 // the current tree (training/models.py:198, 305).  q, k, v arrive already pixel-normalised
 // (the qkv GEMM epilogue does it), so |q.k|/sqrt(D) <= sqrt(D): the softmax needs no running
-// max — p = exp(q.k/sqrt(D) - sqrt(D)) is in (e^-2sqrt(D), ~1] — and no rescaling pass.
+// max — p = exp(q.k/sqrt(D)) stays within [e^-8, e^8], all normal 16-bit values — and no rescaling pass.
 // Keys/values of the self segment and of the 1-2 cross (source-view) segments already sit
 // back to back in one [B][heads][Sk][D] buffer, so the concat of the reference is free.
-// `zero_keys` extra all-zero keys (unconditional gnet) only add exp(0 - sqrt(D)) each to the
-// denominator.
+// `zero_keys` extra all-zero keys (unconditional gnet) only add exp(0) = 1 each to the denominator.
 //
 // v1 data path: cp.async double-buffered K/V tiles in XOR-swizzled shared memory, ldmatrix,
-// mma.sync.m16n8k16 bf16 with fp32 accumulation; 4 warps x 16 query rows per CTA.
+// mma.sync.m16n8k16 (16-bit operands) with fp32 accumulation; 4 warps x 16 query rows per CTA.
 #include "common.h"
 #include "ptx.cuh"
 
@@ -44,8 +43,13 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, u
 }
 __device__ __forceinline__ void mma_bf16(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                          uint32_t b1) {
+#ifdef VB_OP_BF16
+#define VB_MMA_OP "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32"
+#else
+#define VB_MMA_OP "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32"
+#endif
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      VB_MMA_OP " {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
@@ -59,35 +63,35 @@ __device__ __forceinline__ int swz(int row, int chunk) {
 }
 
 template <int D>
-__device__ __forceinline__ void load_tile_async(__nv_bfloat16* smem, const __nv_bfloat16* gmem, int row0, int rows_total,
+__device__ __forceinline__ void load_tile_async(op_t* smem, const op_t* gmem, int row0, int rows_total,
                                                 int tile_rows) {
   constexpr int kChunks = D / 8;
   for (int i = threadIdx.x; i < tile_rows * kChunks; i += kAttnThreads) {
     const int r = i / kChunks, c = i - r * kChunks;
     const bool ok = row0 + r < rows_total;
-    const __nv_bfloat16* src = gmem + static_cast<size_t>(ok ? row0 + r : 0) * D + c * 8;
+    const op_t* src = gmem + static_cast<size_t>(ok ? row0 + r : 0) * D + c * 8;
     cp_async16(smem + swz<D>(r, c) * 8, src, ok);
   }
 }
 
 template <int D>
-__global__ void __launch_bounds__(kAttnThreads) attn_kernel(const __nv_bfloat16* __restrict__ q,
-                                                            const __nv_bfloat16* __restrict__ k,
-                                                            const __nv_bfloat16* __restrict__ v,
-                                                            __nv_bfloat16* __restrict__ y, int heads, int sq, int sk,
+__global__ void __launch_bounds__(kAttnThreads) attn_kernel(const op_t* __restrict__ q,
+                                                            const op_t* __restrict__ k,
+                                                            const op_t* __restrict__ v,
+                                                            op_t* __restrict__ y, int heads, int sq, int sk,
                                                             int zero_keys) {
   constexpr int kKSteps = D / 16;    // k-steps of the QK^T product
   constexpr int kDTiles = D / 8;     // n-tiles of the PV product
-  __shared__ __align__(128) __nv_bfloat16 s_q[kBlockQ * D];
-  __shared__ __align__(128) __nv_bfloat16 s_k[2][kBlockKV * D];
-  __shared__ __align__(128) __nv_bfloat16 s_v[2][kBlockKV * D];
+  __shared__ __align__(128) op_t s_q[kBlockQ * D];
+  __shared__ __align__(128) op_t s_k[2][kBlockKV * D];
+  __shared__ __align__(128) op_t s_v[2][kBlockKV * D];
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kBlockQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t bh = static_cast<size_t>(b) * heads + h;
-  const __nv_bfloat16* qp = q + bh * sq * D;
-  const __nv_bfloat16* kp = k + bh * sk * D;
-  const __nv_bfloat16* vp = v + bh * sk * D;
+  const op_t* qp = q + bh * sq * D;
+  const op_t* kp = k + bh * sk * D;
+  const op_t* vp = v + bh * sk * D;
 
   load_tile_async<D>(s_q, qp, q0, sq, kBlockQ);
   load_tile_async<D>(s_k[0], kp, 0, sk, kBlockKV);
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const __nv_bfloat16*
 
   const float sqrt_d = sqrtf(static_cast<float>(D));
   const float c1 = 1.4426950408889634f / sqrt_d;    // log2(e)/sqrt(D)
-  const float c2 = 1.4426950408889634f * sqrt_d;    // log2(e)*sqrt(D)
+  const float c2 = 0.f;   // no offset: |logit| <= sqrt(D) <= 8, so exp(logit) in [3e-4, 3e3] is exact enough in fp16/bf16 and cannot overflow
 
   uint32_t qf[kKSteps][4];
   float o[kDTiles][4];
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const __nv_bfloat16*
         mma_bf16(s[2 * jp + 1], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b2, b3);
       }
     }
-    // P = exp(S/sqrt(D) - sqrt(D)); mask keys past the end of the sequence
+    // P = exp(S/sqrt(D)); mask keys past the end of the sequence
     const int key0 = t * kBlockKV + 2 * (lane & 3);
     uint32_t pf[kBlockKV / 16][4];
 #pragma unroll
@@ -154,8 +158,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const __nv_bfloat16*
       if (kk + 1 >= sk) p1 = p3 = 0.f;
       l0 += p0 + p1;
       l1 += p2 + p3;
-      pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
-      pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      pf[j >> 1][(j & 1) * 2 + 0] = pack_op2(p0, p1);
+      pf[j >> 1][(j & 1) * 2 + 1] = pack_op2(p2, p3);
     }
     // O += P V
 #pragma unroll
@@ -188,8 +192,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const __nv_bfloat16*
   for (int j = 0; j < kDTiles; ++j) {
     const int r0 = warp * 16 + g, r1 = r0 + 8;
     const int col = j * 8 + 2 * tq;
-    *reinterpret_cast<uint32_t*>(s_q + swz<D>(r0, col >> 3) * 8 + (col & 7)) = pack_bf16x2(o[j][0] * i0, o[j][1] * i0);
-    *reinterpret_cast<uint32_t*>(s_q + swz<D>(r1, col >> 3) * 8 + (col & 7)) = pack_bf16x2(o[j][2] * i1, o[j][3] * i1);
+    *reinterpret_cast<uint32_t*>(s_q + swz<D>(r0, col >> 3) * 8 + (col & 7)) = pack_op2(o[j][0] * i0, o[j][1] * i0);
+    *reinterpret_cast<uint32_t*>(s_q + swz<D>(r1, col >> 3) * 8 + (col & 7)) = pack_op2(o[j][2] * i1, o[j][3] * i1);
   }
   __syncthreads();
   constexpr int kChunks = D / 8;
@@ -211,10 +215,10 @@ int attn_launch(const vb_attn_desc* d, cudaStream_t s) {
   VB_REQUIRE(d->head_dim == 64 || d->head_dim == 32, "vb_attn: head_dim must be 32 or 64 (got %d)", d->head_dim);
   VB_REQUIRE(d->zero_keys >= 0, "vb_attn: zero_keys < 0");
   const dim3 grid((d->sq + kBlockQ - 1) / kBlockQ, d->heads, d->B);
-  const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(d->q);
-  const __nv_bfloat16* k = static_cast<const __nv_bfloat16*>(d->k);
-  const __nv_bfloat16* v = static_cast<const __nv_bfloat16*>(d->v);
-  __nv_bfloat16* y = static_cast<__nv_bfloat16*>(d->y);
+  const op_t* q = static_cast<const op_t*>(d->q);
+  const op_t* k = static_cast<const op_t*>(d->k);
+  const op_t* v = static_cast<const op_t*>(d->v);
+  op_t* y = static_cast<op_t*>(d->y);
   if (d->head_dim == 64)
     attn_kernel<64><<<grid, kAttnThreads, 0, s>>>(q, k, v, y, d->heads, d->sq, d->sk, d->zero_keys);
   else

@@ -31,9 +31,9 @@ void set_error(const char* fmt, ...);
 
 int num_sms();
 
-// Encode a tiled bf16 tensor map with SWIZZLE_128B (inner box = 64 elements = 128 B).
+// Encode a tiled 16-bit (operand format) tensor map with SWIZZLE_128B (inner box = 64 elements = 128 B).
 // dims/strides innermost first; strides in BYTES for dims 1..rank-1.
-int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+int encode_tmap_16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box);
 
 // ---- prepared launches (tensor maps encoded once, replayable) ----

@@ -31,6 +31,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+#ifdef VB_OP_BF16
+static const CUtensorMapDataType kTmapDtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+#else
+static const CUtensorMapDataType kTmapDtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+#endif
+
 static EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static std::once_flag once;
@@ -44,7 +50,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+int encode_tmap_16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
@@ -65,7 +71,7 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
     estr[i] = 1;
     if (i + 1 < rank) gstrides[i] = strides_bytes[i];
   }
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdims,
+  CUresult r = fn(map, kTmapDtype, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdims,
                   gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -80,6 +86,11 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
 
 extern "C" const char* vb_last_error(void) { return vb::g_err; }
 extern "C" int vb_abi_version(void) { return VB_ABI_VERSION; }
+#ifdef VB_OP_BF16
+extern "C" int vb_operand_dtype(void) { return VB_BF16; }
+#else
+extern "C" int vb_operand_dtype(void) { return VB_F16; }
+#endif
 extern "C" int vb_device_check(void) {
   int dev = 0;
   cudaDeviceProp prop;

@@ -1,5 +1,5 @@
-// Fused elementwise passes over the NHWC residual stream (fp32) — HBM-bound, 16-byte
-// vector accesses, one warp per pixel so the per-pixel channel reductions are warp shuffles.
+// Fused elementwise passes over the 16-bit NHWC residual stream (fp32 math) — HBM-bound, 16-byte
+// vector accesses, a power-of-two lane group per pixel so the per-pixel channel reductions are warp shuffles.
 // Reference ops: normalize(dim=1) pixel-norm (training/models.py:171, 37-42), resample up/down
 // (:48-61), mp_silu (:66-67), mp_cat (:78-84), MPFourier + embedding linears (:96-101, 388-391,
 // 175), EDM preconditioning (NVPrecond.forward), Heun/guidance update (generate_images.py:62,
@@ -11,130 +11,154 @@ namespace vb {
 namespace {
 
 constexpr int kEwThreads = 256;
-constexpr int kMaxVec = 8;   // float4 per lane -> up to 1024 channels per pixel
+constexpr int kMaxVpl = 4;   // 16-byte vectors per lane -> up to 32*4*8 = 1024 channels per pixel
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ uint2 pack4(float a, float b, float c, float d) {
-  return make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+// Sum over the `lpp` (power of two) consecutive lanes that share a pixel.
+__device__ __forceinline__ float group_sum(float v, int lpp) {
+  for (int o = lpp >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+struct Vec8 {
+  float v[8];
+};
+__device__ __forceinline__ Vec8 ld8(const op_t* p) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  Vec8 r;
+  const float2 a = unpack_op2(q.x), b = unpack_op2(q.y), c = unpack_op2(q.z), d = unpack_op2(q.w);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
+  return r;
+}
+__device__ __forceinline__ void st8(op_t* p, const Vec8& r) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_op2(r.v[0], r.v[1]), pack_op2(r.v[2], r.v[3]), pack_op2(r.v[4], r.v[5]),
+                                            pack_op2(r.v[6], r.v[7]));
+}
+__device__ __forceinline__ uint4 pack8_silu(const Vec8& r, float scale) {
+  return make_uint4(pack_op2(mp_silu_f(r.v[0] * scale), mp_silu_f(r.v[1] * scale)), pack_op2(mp_silu_f(r.v[2] * scale), mp_silu_f(r.v[3] * scale)),
+                 pack_op2(mp_silu_f(r.v[4] * scale), mp_silu_f(r.v[5] * scale)), pack_op2(mp_silu_f(r.v[6] * scale), mp_silu_f(r.v[7] * scale)));
+}
+__device__ __forceinline__ void st8_silu(op_t* p, const Vec8& r, float scale) {
+  *reinterpret_cast<uint4*>(p) = pack8_silu(r, scale);
 }
 
-// ---- PIXNORM / DOWN_PIXNORM: one warp per output pixel --------------------------------
+// ---- PIXNORM / DOWN_PIXNORM: `lpp` lanes per output pixel (32/lpp pixels per warp) ------------------
 template <bool DOWN>
-__global__ void __launch_bounds__(kEwThreads) pixnorm_kernel(const float* __restrict__ a, float* __restrict__ out_f32,
-                                                             __nv_bfloat16* __restrict__ out_bf16,
-                                                             __nv_bfloat16* __restrict__ out_silu, long long pixels,
-                                                             int H, int W, int C) {
-  const long long pix = (static_cast<long long>(blockIdx.x) * kEwThreads + threadIdx.x) >> 5;
-  if (pix >= pixels) return;
+__global__ void __launch_bounds__(kEwThreads) pixnorm_kernel(const op_t* __restrict__ a, op_t* __restrict__ out,
+                                                             op_t* __restrict__ out_silu, long long pixels, int H, int W,
+                                                             int C, int lpp) {
   const int lane = threadIdx.x & 31;
-  const int nvec = C >> 2;
-  float4 v[kMaxVec];
+  const int ppw = 32 / lpp;                         // pixels per warp
+  const long long warp_id = (static_cast<long long>(blockIdx.x) * kEwThreads + threadIdx.x) >> 5;
+  const long long pix = warp_id * ppw + lane / lpp;
+  const int gl = lane % lpp;                        // lane within the pixel group
+  const int nvec = C >> 3;
+  const bool live = pix < pixels;
+  Vec8 v[kMaxVpl];
   float ss = 0.f;
-  if (!DOWN) {
-    const float4* src = reinterpret_cast<const float4*>(a + pix * C);
+  if (live) {
+    if (!DOWN) {
+      const op_t* src = a + pix * C;
 #pragma unroll
-    for (int j = 0; j < kMaxVec; ++j) {
-      const int i = lane + j * 32;
-      if (i < nvec) {
-        v[j] = __ldg(src + i);
-        ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+      for (int j = 0; j < kMaxVpl; ++j) {
+        const int i = gl + j * lpp;
+        if (i < nvec) {
+          v[j] = ld8(src + i * 8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ss += v[j].v[e] * v[j].v[e];
+        }
       }
-    }
-  } else {
-    // output pixel (n, y, x) <- mean of the 2x2 input patch at (2y, 2x) of a [2H][2W] image
-    const int x = static_cast<int>(pix % W);
-    const long long t = pix / W;
-    const int y = static_cast<int>(t % H);
-    const long long n = t / H;
-    const long long p00 = (n * 2 * H + 2 * y) * (2 * W) + 2 * x;
-    const float4* s0 = reinterpret_cast<const float4*>(a + p00 * C);
-    const float4* s1 = reinterpret_cast<const float4*>(a + (p00 + 1) * C);
-    const float4* s2 = reinterpret_cast<const float4*>(a + (p00 + 2 * W) * C);
-    const float4* s3 = reinterpret_cast<const float4*>(a + (p00 + 2 * W + 1) * C);
+    } else {
+      // output pixel (n, y, x) <- mean of the 2x2 input patch at (2y, 2x) of a [2H][2W] image
+      const int x = static_cast<int>(pix % W);
+      const long long t = pix / W;
+      const int y = static_cast<int>(t % H);
+      const long long n = t / H;
+      const long long p00 = (n * 2 * H + 2 * y) * (2 * W) + 2 * x;
+      const op_t* s0 = a + p00 * C;
+      const op_t* s1 = a + (p00 + 1) * C;
+      const op_t* s2 = a + (p00 + 2 * W) * C;
+      const op_t* s3 = a + (p00 + 2 * W + 1) * C;
 #pragma unroll
-    for (int j = 0; j < kMaxVec; ++j) {
-      const int i = lane + j * 32;
-      if (i < nvec) {
-        const float4 p = __ldg(s0 + i), q = __ldg(s1 + i), r = __ldg(s2 + i), s = __ldg(s3 + i);
-        v[j] = make_float4(0.25f * (p.x + q.x + r.x + s.x), 0.25f * (p.y + q.y + r.y + s.y),
-                           0.25f * (p.z + q.z + r.z + s.z), 0.25f * (p.w + q.w + r.w + s.w));
-        ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+      for (int j = 0; j < kMaxVpl; ++j) {
+        const int i = gl + j * lpp;
+        if (i < nvec) {
+          const Vec8 p = ld8(s0 + i * 8), q = ld8(s1 + i * 8), r = ld8(s2 + i * 8), s = ld8(s3 + i * 8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            v[j].v[e] = 0.25f * (p.v[e] + q.v[e] + r.v[e] + s.v[e]);
+            ss += v[j].v[e] * v[j].v[e];
+          }
+        }
       }
     }
   }
-  ss = warp_sum(ss);
+  ss = group_sum(ss, lpp);
+  if (!live) return;
   const float inv = 1.0f / (1e-4f + sqrtf(ss) * rsqrtf(static_cast<float>(C)));
 #pragma unroll
-  for (int j = 0; j < kMaxVec; ++j) {
-    const int i = lane + j * 32;
+  for (int j = 0; j < kMaxVpl; ++j) {
+    const int i = gl + j * lpp;
     if (i < nvec) {
-      const float4 o = make_float4(v[j].x * inv, v[j].y * inv, v[j].z * inv, v[j].w * inv);
-      if (out_f32) reinterpret_cast<float4*>(out_f32 + pix * C)[i] = o;
-      if (out_bf16) reinterpret_cast<uint2*>(out_bf16 + pix * C)[i] = pack4(o.x, o.y, o.z, o.w);
-      if (out_silu)
-        reinterpret_cast<uint2*>(out_silu + pix * C)[i] = pack4(mp_silu_f(o.x), mp_silu_f(o.y), mp_silu_f(o.z), mp_silu_f(o.w));
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[j].v[e] *= inv;
+      if (out) st8(out + pix * C + i * 8, v[j]);
+      if (out_silu) st8_silu(out_silu + pix * C + i * 8, v[j], 1.0f);
     }
   }
 }
 
-// ---- UP: one warp per INPUT pixel, writes the 2x2 output patch ------------------------
-__global__ void __launch_bounds__(kEwThreads) up_kernel(const float* __restrict__ a, float* __restrict__ out_f32,
-                                                        __nv_bfloat16* __restrict__ out_bf16,
-                                                        __nv_bfloat16* __restrict__ out_silu, long long in_pixels, int Hi,
-                                                        int Wi, int C) {
-  const long long pix = (static_cast<long long>(blockIdx.x) * kEwThreads + threadIdx.x) >> 5;
-  if (pix >= in_pixels) return;
+// ---- UP: `lpp` lanes per INPUT pixel, each writes the 2x2 output patch -------------------------------
+__global__ void __launch_bounds__(kEwThreads) up_kernel(const op_t* __restrict__ a, op_t* __restrict__ out,
+                                                        op_t* __restrict__ out_silu, long long in_pixels, int Hi, int Wi,
+                                                        int C, int lpp) {
   const int lane = threadIdx.x & 31;
-  const int nvec = C >> 2;
+  const int ppw = 32 / lpp;
+  const long long warp_id = (static_cast<long long>(blockIdx.x) * kEwThreads + threadIdx.x) >> 5;
+  const long long pix = warp_id * ppw + lane / lpp;
+  if (pix >= in_pixels) return;
+  const int gl = lane % lpp;
+  const int nvec = C >> 3;
   const int x = static_cast<int>(pix % Wi);
   const long long t = pix / Wi;
   const int y = static_cast<int>(t % Hi);
   const long long n = t / Hi;
   const long long o00 = (n * 2 * Hi + 2 * y) * (2 * Wi) + 2 * x;
   const long long offs[4] = {o00, o00 + 1, o00 + 2 * Wi, o00 + 2 * Wi + 1};
-  const float4* src = reinterpret_cast<const float4*>(a + pix * C);
-  for (int i = lane; i < nvec; i += 32) {
-    const float4 o = __ldg(src + i);
-    const uint2 b = pack4(o.x, o.y, o.z, o.w);
-    const uint2 s = pack4(mp_silu_f(o.x), mp_silu_f(o.y), mp_silu_f(o.z), mp_silu_f(o.w));
+  for (int i = gl; i < nvec; i += lpp) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(a + pix * C + i * 8));
+    const Vec8 v = ld8(a + pix * C + i * 8);
+    const uint4 sl = pack8_silu(v, 1.0f);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (out_f32) reinterpret_cast<float4*>(out_f32 + offs[k] * C)[i] = o;
-      if (out_bf16) reinterpret_cast<uint2*>(out_bf16 + offs[k] * C)[i] = b;
-      if (out_silu) reinterpret_cast<uint2*>(out_silu + offs[k] * C)[i] = s;
+      if (out) *reinterpret_cast<uint4*>(out + offs[k] * C + i * 8) = raw;
+      if (out_silu) *reinterpret_cast<uint4*>(out_silu + offs[k] * C + i * 8) = sl;
     }
   }
 }
 
-// ---- CAT / SILU: one warp per pixel ---------------------------------------------------
-__global__ void __launch_bounds__(kEwThreads) cat_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                                         float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
-                                                         __nv_bfloat16* __restrict__ out_silu, long long pixels, int ca,
-                                                         int cb, float wa, float wb) {
-  const long long pix = (static_cast<long long>(blockIdx.x) * kEwThreads + threadIdx.x) >> 5;
-  if (pix >= pixels) return;
+// ---- CAT / SILU: `lpp` lanes per pixel ------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads) cat_kernel(const op_t* __restrict__ a, const op_t* __restrict__ b,
+                                                         op_t* __restrict__ out, op_t* __restrict__ out_silu,
+                                                         long long pixels, int ca, int cb, float wa, float wb, int lpp) {
   const int lane = threadIdx.x & 31;
-  const int na = ca >> 2, nb = cb >> 2;
+  const int ppw = 32 / lpp;
+  const long long warp_id = (static_cast<long long>(blockIdx.x) * kEwThreads + threadIdx.x) >> 5;
+  const long long pix = warp_id * ppw + lane / lpp;
+  if (pix >= pixels) return;
+  const int gl = lane % lpp;
+  const int na = ca >> 3, nb = cb >> 3;
   const int C = ca + cb;
-  const float4* sa = reinterpret_cast<const float4*>(a + pix * ca);
-  const float4* sb = b ? reinterpret_cast<const float4*>(b + pix * cb) : nullptr;
-  for (int i = lane; i < na + nb; i += 32) {
-    float4 o;
-    if (i < na) {
-      o = __ldg(sa + i);
-      o = make_float4(o.x * wa, o.y * wa, o.z * wa, o.w * wa);
-    } else {
-      o = __ldg(sb + (i - na));
-      o = make_float4(o.x * wb, o.y * wb, o.z * wb, o.w * wb);
-    }
-    if (out_f32) reinterpret_cast<float4*>(out_f32 + pix * C)[i] = o;
-    if (out_bf16) reinterpret_cast<uint2*>(out_bf16 + pix * C)[i] = pack4(o.x, o.y, o.z, o.w);
-    if (out_silu)
-      reinterpret_cast<uint2*>(out_silu + pix * C)[i] = pack4(mp_silu_f(o.x), mp_silu_f(o.y), mp_silu_f(o.z), mp_silu_f(o.w));
+  for (int i = gl; i < na + nb; i += lpp) {
+    Vec8 v = i < na ? ld8(a + pix * ca + i * 8) : ld8(b + pix * cb + (i - na) * 8);
+    const float w = i < na ? wa : wb;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v.v[e] *= w;
+    if (out) st8(out + pix * C + i * 8, v);
+    if (out_silu) st8_silu(out_silu + pix * C + i * 8, v, 1.0f);
   }
 }
 
@@ -211,8 +235,8 @@ __global__ void __launch_bounds__(256) precond_in_kernel(const vb_precond_in_des
     k = 6;
   }
   ch[k] = 1.0f;   // bias-as-channel (training/models.py:394)
-  uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(d.out) + pix * d.cpad);
-  o[0] = make_uint4(pack_bf16x2(ch[0], ch[1]), pack_bf16x2(ch[2], ch[3]), pack_bf16x2(ch[4], ch[5]), pack_bf16x2(ch[6], ch[7]));
+  uint4* o = reinterpret_cast<uint4*>(static_cast<op_t*>(d.out) + pix * d.cpad);
+  o[0] = make_uint4(pack_op2(ch[0], ch[1]), pack_op2(ch[2], ch[3]), pack_op2(ch[4], ch[5]), pack_op2(ch[6], ch[7]));
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
   for (int i = 1; i < d.cpad / 8; ++i) o[i] = z;
 }
@@ -287,38 +311,55 @@ __global__ void decode_u8_kernel(const float* __restrict__ src, uint8_t* __restr
 }
 
 inline unsigned warp_grid(long long warps) { return static_cast<unsigned>((warps * 32 + kEwThreads - 1) / kEwThreads); }
+inline int lanes_per_pixel(int channels) {
+  const int nvec = channels / 8;
+  int lpp = 1;
+  while (lpp < nvec && lpp < 32) lpp <<= 1;
+  return lpp;
+}
 
 }  // namespace
 
 int eltwise_launch(const vb_ew_desc* d, cudaStream_t s) {
   VB_REQUIRE(d != nullptr && d->a != nullptr, "vb_eltwise: null input");
   VB_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0, "vb_eltwise: empty extent");
-  VB_REQUIRE(d->ca > 0 && d->ca % 4 == 0 && d->ca <= kMaxVec * 128, "vb_eltwise: channels %d must be a multiple of 4, <= %d",
-             d->ca, kMaxVec * 128);
-  VB_REQUIRE(d->out_f32 || d->out_bf16 || d->out_silu, "vb_eltwise: no output");
+  VB_REQUIRE(d->ca > 0 && d->ca % 8 == 0 && d->ca <= kMaxVpl * 256, "vb_eltwise: channels %d must be a multiple of 8, <= %d",
+             d->ca, kMaxVpl * 256);
+  VB_REQUIRE(d->out || d->out_silu, "vb_eltwise: no output");
   const long long pixels = static_cast<long long>(d->B) * d->H * d->W;
-  __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(d->out_bf16);
-  __nv_bfloat16* os = static_cast<__nv_bfloat16*>(d->out_silu);
+  const op_t* a = static_cast<const op_t*>(d->a);
+  op_t* o = static_cast<op_t*>(d->out);
+  op_t* os = static_cast<op_t*>(d->out_silu);
   switch (d->kind) {
     case VB_EW_PIXNORM:
-      pixnorm_kernel<false><<<warp_grid(pixels), kEwThreads, 0, s>>>(d->a, d->out_f32, ob, os, pixels, d->H, d->W, d->ca);
+    case VB_EW_DOWN_PIXNORM: {
+      const int lpp = lanes_per_pixel(d->ca);
+      const long long warps = (pixels + 32 / lpp - 1) / (32 / lpp);
+      if (d->kind == VB_EW_PIXNORM)
+        pixnorm_kernel<false><<<warp_grid(warps), kEwThreads, 0, s>>>(a, o, os, pixels, d->H, d->W, d->ca, lpp);
+      else
+        pixnorm_kernel<true><<<warp_grid(warps), kEwThreads, 0, s>>>(a, o, os, pixels, d->H, d->W, d->ca, lpp);
       break;
-    case VB_EW_DOWN_PIXNORM:
-      pixnorm_kernel<true><<<warp_grid(pixels), kEwThreads, 0, s>>>(d->a, d->out_f32, ob, os, pixels, d->H, d->W, d->ca);
-      break;
+    }
     case VB_EW_UP: {
       VB_REQUIRE(d->H % 2 == 0 && d->W % 2 == 0, "vb_eltwise: UP needs even output extent");
       const long long in_pixels = pixels / 4;
-      up_kernel<<<warp_grid(in_pixels), kEwThreads, 0, s>>>(d->a, d->out_f32, ob, os, in_pixels, d->H / 2, d->W / 2, d->ca);
+      const int lpp = lanes_per_pixel(d->ca);
+      const long long warps = (in_pixels + 32 / lpp - 1) / (32 / lpp);
+      up_kernel<<<warp_grid(warps), kEwThreads, 0, s>>>(a, o, os, in_pixels, d->H / 2, d->W / 2, d->ca, lpp);
       break;
     }
     case VB_EW_CAT:
-      VB_REQUIRE(d->b != nullptr && d->cb > 0 && d->cb % 4 == 0, "vb_eltwise: CAT needs b with cb %% 4 == 0");
-      cat_kernel<<<warp_grid(pixels), kEwThreads, 0, s>>>(d->a, d->b, d->out_f32, ob, os, pixels, d->ca, d->cb, d->wa, d->wb);
+    case VB_EW_SILU: {
+      const bool cat = d->kind == VB_EW_CAT;
+      if (cat) VB_REQUIRE(d->b != nullptr && d->cb > 0 && d->cb % 8 == 0, "vb_eltwise: CAT needs b with cb %% 8 == 0");
+      const int lpp = lanes_per_pixel(d->ca + (cat ? d->cb : 0));
+      const long long warps = (pixels + 32 / lpp - 1) / (32 / lpp);
+      cat_kernel<<<warp_grid(warps), kEwThreads, 0, s>>>(a, cat ? static_cast<const op_t*>(d->b) : nullptr, o, os, pixels,
+                                                         d->ca, cat ? d->cb : 0, cat ? d->wa : (d->wa != 0.f ? d->wa : 1.0f),
+                                                         cat ? d->wb : 1.0f, lpp);
       break;
-    case VB_EW_SILU:
-      cat_kernel<<<warp_grid(pixels), kEwThreads, 0, s>>>(d->a, nullptr, d->out_f32, ob, os, pixels, d->ca, 0, 1.0f, 1.0f);
-      break;
+    }
     default:
       VB_REQUIRE(false, "vb_eltwise: unknown kind %d", d->kind);
   }

@@ -1,5 +1,5 @@
 // Weight preparation: forced weight normalisation + magnitude-preserving scaling + gain,
-// fp32 statistics, one rounding to bf16, repack for the implicit-GEMM B operand.
+// fp32 statistics, one rounding to the 16-bit operand format, repack for the implicit-GEMM B operand.
 // Reference: MPConv.forward prologue, training/models.py:115-121 and normalize :37-42:
 //   w = normalize(w.float()) * (gain / sqrt(K))  ==  gain * w / (eps*sqrt(K) + ||w||),  K = cin*taps.
 // Runs once per weight version (weights are constant while sampling), not per denoiser call.
@@ -30,9 +30,9 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const vb_weight_prep_d
     row = h * pd + j * d.perm_dim + dd;
   }
   if (co >= d.cout) {
-    // zero padding rows (bf16 destination only)
-    __nv_bfloat16* drow = static_cast<__nv_bfloat16*>(d.dst) + static_cast<size_t>(co) * d.taps * cin_pad;
-    for (int i = threadIdx.x; i < d.taps * cin_pad; i += blockDim.x) drow[i] = __float2bfloat16(0.f);
+    // zero padding rows (16-bit destination only)
+    op_t* drow = static_cast<op_t*>(d.dst) + static_cast<size_t>(co) * d.taps * cin_pad;
+    for (int i = threadIdx.x; i < d.taps * cin_pad; i += blockDim.x) drow[i] = to_op(0.f);
     return;
   }
   const size_t src0 = static_cast<size_t>(co) * K;
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const vb_weight_prep_d
     for (int i = threadIdx.x; i < K; i += blockDim.x) drow[i] = load_w(d.src, d.src_dtype, src0 + i) * scale;
     return;
   }
-  __nv_bfloat16* drow = static_cast<__nv_bfloat16*>(d.dst) + static_cast<size_t>(row) * d.taps * cin_pad;
+  op_t* drow = static_cast<op_t*>(d.dst) + static_cast<size_t>(row) * d.taps * cin_pad;
   for (int i = threadIdx.x; i < d.taps * cin_pad; i += blockDim.x) {
     const int tap = i / cin_pad;
     const int c = i - tap * cin_pad;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const vb_weight_prep_d
     }
     float v = 0.f;
     if (ci >= 0) v = load_w(d.src, d.src_dtype, src0 + static_cast<size_t>(ci) * d.taps + tap) * scale * sc;
-    drow[i] = __float2bfloat16(v);
+    drow[i] = to_op(v);
   }
 }
 
@@ -87,17 +87,17 @@ extern "C" int vb_weight_prep(const vb_weight_prep_desc* d, void* stream) {
   VB_REQUIRE(d->cout > 0 && d->cin > 0 && d->taps > 0, "vb_weight_prep: empty weight");
   VB_REQUIRE(d->src_dtype >= VB_F32 && d->src_dtype <= VB_BF16, "vb_weight_prep: bad src dtype");
   VB_REQUIRE(d->split >= 0 && d->split <= d->cin, "vb_weight_prep: split out of range");
-  if (d->dst_dtype == VB_BF16) {
+  if (d->dst_dtype == VB_OP_DTYPE) {
     VB_REQUIRE(d->cout_pad >= d->cout, "vb_weight_prep: cout_pad < cout");
     VB_REQUIRE(d->seg_a_pad >= d->split && d->seg_b_pad >= d->cin - d->split, "vb_weight_prep: padded segments too small");
     VB_REQUIRE((d->seg_a_pad + d->seg_b_pad) % 64 == 0, "vb_weight_prep: padded cin must be a multiple of 64");
   } else {
-    VB_REQUIRE(d->dst_dtype == VB_F32, "vb_weight_prep: dst dtype must be bf16 or f32");
+    VB_REQUIRE(d->dst_dtype == VB_F32, "vb_weight_prep: dst dtype must be the operand format (%d) or f32", VB_OP_DTYPE);
     VB_REQUIRE(d->split == d->cin, "vb_weight_prep: fp32 destination has no segments");
   }
   if (d->perm_parts > 0)
     VB_REQUIRE(d->perm_dim > 0 && d->cout % (d->perm_parts * d->perm_dim) == 0, "vb_weight_prep: bad permutation");
-  const int rows = d->dst_dtype == VB_BF16 ? d->cout_pad : d->cout;
+  const int rows = d->dst_dtype == VB_OP_DTYPE ? d->cout_pad : d->cout;
   vb::weight_prep_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(*d);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;

@@ -1,15 +1,21 @@
 """Plan builder: turns one NVPrecond parameter tree + batch size into a recorded sequence of
 libvividb200 ops (include/vivid_b200.h) over fixed device buffers.
 
-Dataflow per block (reference Block.forward, training/models.py:165-206; NHWC inside):
-  enc:  [2x2 pool] -> [1x1 skip GEMM] -> PIXNORM pass (fp32 stream + bf16 mp_silu copy)
-        -> 3x3 GEMM (epilogue: *(emb+1), mp_silu) -> 3x3 GEMM (epilogue: mp_sum with stream, clip)
-  dec:  [nearest up | mp_cat pass] -> 3x3 GEMM -> [1x1 skip GEMM] -> 3x3 GEMM (mp_sum, clip)
-  attn: 1x1 qkv GEMM (epilogue: per-head normalise, scatter to [B,h,S,D]) [+ 1x1 kv GEMM on the
-        source-view features, written behind the self keys] -> fused attention -> 1x1 proj GEMM
-        (epilogue: mp_sum, clip)
-The residual stream is fp32; every GEMM operand is a bf16 copy written by the producing
-kernel, so no standalone cast / silu / lerp / clamp kernels exist.
+Everything in HBM is NHWC in ONE 16-bit format (fp16 by default — the reference's own reduced
+precision); accumulation, normalisation statistics and the sampler state are fp32.
+
+Dataflow per block (reference Block.forward, training/models.py:165-206).  `raw` = block output
+(the residual stream), `nsilu` = mp_silu(pixel_norm(raw)), `silu(w)` = mp_silu(w*raw):
+  enc : conv_res0 reads the PREVIOUS block's nsilu (its pixel-norm + mp_silu were fused into that block's
+        last GEMM epilogue); conv_res1's epilogue re-derives pixel_norm(raw_prev) from the TMA-staged
+        residual tile, applies mp_sum + clip and emits raw [+ nsilu for the next block] [+ silu(wb) for
+        the decoder block that will concatenate this skip].  Levels with C > 256 (one GEMM tile cannot hold
+        a whole pixel) use the PIXNORM pass instead; 'down' blocks use the fused pool+norm pass.
+  dec : mp_cat is folded into the consumers: conv_res0 and the 1x1 conv_skip run a two-source K loop over
+        [silu(wa*x) | silu(wb*skip)] and [x | skip] (mp_cat weights inside mp_silu, resp. folded into the
+        conv_skip weights), so no concatenated tensor exists.
+  attn: 1x1 qkv GEMM (epilogue: per-head normalise, scatter to [B,h,S,D]) [+ 1x1 kv GEMM on the source-view
+        features, written behind the self keys] -> fused attention -> 1x1 proj GEMM (mp_sum, clip).
 """
 import ctypes as C
 import math
@@ -24,18 +30,24 @@ def _pad(v, m):
 
 
 class Act:
-    """One activation in up to three physical forms (all NHWC [B*R*R, C])."""
+    """Block output and the derived forms later consumers read (all 16-bit NHWC [B*R*R, C])."""
 
     def __init__(self, B, R, ch):
         self.B, self.R, self.C = B, R, ch
-        self.f32 = None    # fp32 residual stream
-        self.bf16 = None   # bf16 GEMM operand
-        self.silu = None   # bf16 mp_silu(x) GEMM operand
+        self.raw = None       # block output (residual stream / GEMM operand)
+        self.norm = None      # pixel_norm(raw)
+        self.nsilu = None     # mp_silu(pixel_norm(raw))
+        self.silu = {}        # scale -> mp_silu(scale * raw)
         self.is_skip = False
         self.is_feature = False
 
+    def tensors(self, keep_raw=False):
+        out = [] if keep_raw else [self.raw]
+        return out + [self.norm, self.nsilu] + list(self.silu.values())
+
 
 _DT = {torch.float32: L.VB_F32, torch.float16: L.VB_F16, torch.bfloat16: L.VB_BF16}
+FULLROW_MAX = 256          # widest channel count one GEMM tile (and TMEM accumulator buffer) can hold
 
 
 class Plan:
@@ -44,13 +56,15 @@ class Plan:
     def __init__(self, net, B, device):
         self.lib = L.lib()
         L.check(self.lib.vb_device_check(), "vb_device_check")
+        self.op_dtype = L.operand_torch_dtype()
+        self.op_code = self.lib.vb_operand_dtype()
         self.net = net
         self.device = device
         self.B = B                      # number of target images (outputs)
         self.dual = net.dual
         self.Bx = 2 * B if net.dual else B
         self.keep = []                  # every buffer the plan touches (keeps them alive)
-        self.pool = {}                  # (numel, dtype) -> free activation buffers
+        self.pool = {}                  # numel -> free activation buffers
         self.op_info = []               # per recorded op: (kind, label, algorithmic flops, algorithmic bytes)
         self.handle = C.c_void_p()
         L.check(self.lib.vb_plan_create(C.byref(self.handle)), "vb_plan_create")
@@ -76,22 +90,18 @@ class Plan:
 
     # Activations come from a size-keyed pool: ops replay in order on one stream, so a buffer whose last
     # consumer has been recorded can back a later activation (keeps the working set near L2 / HBM-friendly).
-    def act(self, rows, ch, dtype):
-        key = (rows * ch, dtype)
-        free = self.pool.get(key)
-        t = free.pop() if free else self.buf((rows * ch,), dtype)
+    def act(self, rows, ch):
+        free = self.pool.get(rows * ch)
+        t = free.pop() if free else self.buf((rows * ch,), self.op_dtype)
         return t.view(rows, ch)
 
     def release(self, *tensors):
         for t in tensors:
             if t is not None:
-                self.pool.setdefault((t.numel(), t.dtype), []).append(t.view(-1))
+                self.pool.setdefault(t.numel(), []).append(t.view(-1))
 
-    def f32(self, B, R, ch):
-        return self.act(B * R * R, ch, torch.float32)
-
-    def b16(self, B, R, ch):
-        return self.act(B * R * R, ch, torch.bfloat16)
+    def a16(self, B, R, ch):
+        return self.act(B * R * R, ch)
 
     # ------------------------------------------------------------------ weights
     def prep_weight(self, w, gain=1.0, cout_pad=None, perm=(0, 0), split=None, scales=(1.0, 1.0), fp32=False):
@@ -111,8 +121,8 @@ class Plan:
             sa = _pad(split, 64)
             sb = _pad(cin - split, 64) if cin > split else 0
             cout_pad = cout_pad or _pad(cout, 16)
-            dst = self.buf((cout_pad, taps * (sa + sb)), torch.bfloat16)
-            d = L.WeightPrepDesc(src=w.data_ptr(), dst=dst.data_ptr(), src_dtype=_DT[w.dtype], dst_dtype=L.VB_BF16,
+            dst = self.buf((cout_pad, taps * (sa + sb)), self.op_dtype)
+            d = L.WeightPrepDesc(src=w.data_ptr(), dst=dst.data_ptr(), src_dtype=_DT[w.dtype], dst_dtype=self.op_code,
                                  cout=cout, cin=cin, taps=taps, cout_pad=cout_pad, split=split, seg_a_pad=sa,
                                  seg_b_pad=sb, perm_parts=perm[0], perm_dim=perm[1], gain=float(gain),
                                  scale_a=float(scales[0]), scale_b=float(scales[1]))
@@ -121,28 +131,46 @@ class Plan:
         return dst
 
     # ------------------------------------------------------------------ op emitters
-    def pick_block_n(self, cout_pad, m_pixels, multiple=16):
-        """Largest N tile that still yields at least one tile per SM (falls back to the smallest)."""
+    def pick_block_n(self, cout_pad, m_pixels, k_blocks, multiple=16, fullrow=False):
+        """N tile minimising an estimated makespan: waves x (main loop + epilogue) per tile."""
+        if fullrow:
+            return cout_pad
         m_tiles = (m_pixels + 127) // 128
-        cands = [n for n in (256, 192, 128, 64, 32, 16) if cout_pad % n == 0 and n % multiple == 0]
-        for n in cands:
-            if m_tiles * (cout_pad // n) >= self.sm_count:
-                return n
-        wide = [n for n in cands if n >= 64]
-        return wide[-1] if wide else cands[-1]
+        best, best_cost = None, None
+        for n in (256, 192, 128, 64, 32, 16):
+            if cout_pad % n or n % multiple:
+                continue
+            tiles = m_tiles * (cout_pad // n)
+            waves = -(-tiles // self.sm_count)
+            # MMA cycles ~ k_blocks * n/2 (+ fixed issue cost), epilogue ~ 6 cycles per column (overlapped unless it dominates)
+            mma = k_blocks * (max(n, 64) / 2.0 + 24)
+            epi = 6.0 * n + 400
+            cost = waves * max(mma, epi) + min(mma, epi) * 0.15 + 600
+            if best_cost is None or cost < best_cost * 0.999:
+                best, best_cost = n, cost
+        return best
 
     def conv(self, x, w, B, R, cin_pad, cout, taps, *, x2=None, cin2_pad=0, cout_pad=None, flags=0, mod=None,
-             mod_stride=0, res=None, res_t=0.3, clip=256.0, out_f32=None, out_bf16=None, out_silu=None, qkv=None,
+             mod_stride=0, res=None, res_mode=L.VB_RES_NONE, res_t=0.3, clip=None, outs=(), out_f32=None, qkv=None,
              k_real=None):
+        """outs: sequence of (tensor, kind, scale)."""
         cout_pad = cout_pad or _pad(cout, 16)
-        multiple = qkv["D"] if qkv else 16
-        bn = self.pick_block_n(cout_pad, B * R * R, multiple)
-        d = L.ConvDesc(x=x.data_ptr(), x2=L.ptr(x2), w=w.data_ptr(), mod=L.ptr(mod) if not isinstance(mod, int) else mod,
-                       res=L.ptr(res), out_f32=L.ptr(out_f32), out_bf16=L.ptr(out_bf16), out_silu=L.ptr(out_silu),
-                       B=B, H=R, W=R, cin_pad=cin_pad, cin2_pad=cin2_pad, cout_pad=cout_pad, taps=taps, block_n=bn,
-                       epi_mode=L.VB_EPI_QKVNORM if qkv else L.VB_EPI_PLAIN, flags=flags, mod_stride=mod_stride,
-                       ld_res=cout_pad, ld_f32=cout_pad, ld_bf16=cout_pad, ld_silu=cout_pad, res_t=res_t,
-                       clip=clip if clip is not None else 3.0e38)
+        fullrow = res_mode == L.VB_RES_PIXNORM or any(k >= L.VB_OUT_NORM for _, k, _ in outs)
+        multiple = qkv["D"] if qkv else (64 if outs else 16)
+        k_blocks = taps * (cin_pad + cin2_pad) // 64
+        bn = self.pick_block_n(cout_pad, B * R * R, k_blocks, multiple, fullrow)
+        assert bn is not None and (not fullrow or bn <= FULLROW_MAX), (cout_pad, bn)
+        if clip is not None:
+            flags |= L.VB_F_CLIP
+        d = L.ConvDesc(x=x.data_ptr(), x2=L.ptr(x2), w=w.data_ptr(), mod=mod if isinstance(mod, int) else L.ptr(mod),
+                       res=L.ptr(res), out_f32=L.ptr(out_f32), B=B, H=R, W=R, cin_pad=cin_pad, cin2_pad=cin2_pad,
+                       cout_pad=cout_pad, taps=taps, block_n=bn, epi_mode=L.VB_EPI_QKVNORM if qkv else L.VB_EPI_PLAIN,
+                       flags=flags, mod_stride=mod_stride, ld_f32=cout_pad, res_mode=res_mode, res_t=res_t,
+                       clip=clip if clip is not None else 0.0)
+        for i, (t, kind, scale) in enumerate(outs):
+            d.out[i] = t.data_ptr()
+            d.out_kind[i] = kind
+            d.out_scale[i] = scale
         if qkv:
             parts = qkv["parts"]
             d.head_dim, d.parts, d.seg_div = qkv["D"], parts, qkv.get("seg_div", 1)
@@ -155,19 +183,19 @@ class Plan:
         self.alg_flops += fl
         P = B * R * R
         by = 2.0 * P * (cin_pad + cin2_pad) + 2.0 * cout_pad * taps * (cin_pad + cin2_pad)
-        by += P * cout_pad * (4.0 * (res is not None) + 4.0 * (out_f32 is not None) + 2.0 * (out_bf16 is not None)
-                              + 2.0 * (out_silu is not None) + (2.0 if qkv else 0.0))
-        self.op_info.append(("conv%d" % (3 if taps == 9 else 1), f"{R}x{R} k{taps * (cin_pad + cin2_pad)} n{cout_pad} bn{bn}", fl, by))
+        by += P * cout_pad * (2.0 * (res is not None) + 2.0 * len(outs) + 4.0 * (out_f32 is not None) + (2.0 if qkv else 0.0))
+        self.op_info.append(("conv%d" % (3 if taps == 9 else 1),
+                             f"{R}x{R} k{taps * (cin_pad + cin2_pad)} n{cout_pad} bn{bn} o{len(outs)}r{res_mode}", fl, by))
 
-    def eltwise(self, kind, a, B, R, ca, *, b=None, cb=0, wa=1.0, wb=1.0, out_f32=None, out_bf16=None, out_silu=None):
-        d = L.EwDesc(a=a.data_ptr(), b=L.ptr(b), out_f32=L.ptr(out_f32), out_bf16=L.ptr(out_bf16),
-                     out_silu=L.ptr(out_silu), kind=kind, B=B, H=R, W=R, ca=ca, cb=cb, wa=wa, wb=wb)
+    def eltwise(self, kind, a, B, R, ca, *, b=None, cb=0, wa=1.0, wb=1.0, out=None, out_silu=None):
+        d = L.EwDesc(a=a.data_ptr(), b=L.ptr(b), out=L.ptr(out), out_silu=L.ptr(out_silu), kind=kind, B=B, H=R, W=R,
+                     ca=ca, cb=cb, wa=wa, wb=wb)
         L.check(self.lib.vb_plan_add_eltwise(self.handle, C.byref(d)), "vb_plan_add_eltwise")
         P = B * R * R
-        cin_tot, cout_tot = ca + cb, ca + cb
-        rd = 4.0 * P * cin_tot * (1.0 if kind != L.VB_EW_UP else 0.25) * (4.0 if kind == L.VB_EW_DOWN_PIXNORM else 1.0)
-        wr = P * cout_tot * (4.0 * (out_f32 is not None) + 2.0 * (out_bf16 is not None) + 2.0 * (out_silu is not None))
-        self.op_info.append(("eltwise", f"kind{kind} {R}x{R} c{cin_tot}", 0.0, rd + wr))
+        ctot = ca + cb
+        rd = 2.0 * P * ctot * (0.25 if kind == L.VB_EW_UP else 4.0 if kind == L.VB_EW_DOWN_PIXNORM else 1.0)
+        wr = 2.0 * P * ctot * ((out is not None) + (out_silu is not None))
+        self.op_info.append(("eltwise", f"kind{kind} {R}x{R} c{ctot}", 0.0, rd + wr))
 
     def attention(self, q, k, v, y, B, heads, sq, sk, D, zero_keys):
         d = L.AttnDesc(q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), y=y.data_ptr(), B=B, heads=heads, sq=sq, sk=sk,
@@ -208,149 +236,174 @@ class Plan:
         return mod, offs, total
 
     # ------------------------------------------------------------------ one UNet / encoder
+    @staticmethod
+    def cat_weights(na, nb, t):
+        """mp_cat scale factors (training/models.py:78-84)."""
+        cc = math.sqrt((na + nb) / ((1 - t) ** 2 + t ** 2))
+        return cc / math.sqrt(na) * (1 - t), cc / math.sqrt(nb) * t
+
     def run_unet(self, unet, x_in, B, mod, offs, mod_total, features=None, feat_seg=1, zero_feature_keys=False,
                  collect_features=False):
-        """Emit the ops of UNet.forward.  x_in: bf16 NHWC [B,R,R,64] (image + ones, zero padded).
-        features: list of Act (bf16 form) consumed by cross-attention blocks in order.
-        Returns (raw output Act or None, collected feature Acts)."""
+        """Emit the ops of UNet.forward.  x_in: 16-bit NHWC [B,R,R,64] (image + ones, zero padded).
+        features: list of Act consumed by cross-attention blocks in order.
+        Returns (raw network output fp32 [P,16] or None, collected feature Acts)."""
         specs = unet.enc_specs + unet.dec_specs
+        t_cat = unet.concat_balance
+        # mp_cat weights are needed when the PRODUCERS run (they are folded into mp_silu copies / conv_skip weights)
+        pending, skip_scale, cat_scale = [], {}, {}
+        width = None
+        for s in specs:
+            if s.group == "enc":
+                pending.append(s)
+                width = s.cout
+            else:
+                if s.skip_ch:
+                    e = pending.pop()
+                    wa, wb = self.cat_weights(width, e.cout, t_cat)
+                    skip_scale[e.name] = wb
+                    cat_scale[s.name] = (wa, wb)
+                width = s.cout
         feats_out, skips = [], []
         features = list(features or [])
         cur = None
-        for i, s in enumerate(specs):
+
+        def want(i):
+            """Output forms block i must emit: list of (attribute, kind, scale) in slot order."""
+            s = specs[i]
             nxt = specs[i + 1] if i + 1 < len(specs) else None
+            fullrow = s.cout <= FULLROW_MAX
+            forms = [("raw", L.VB_OUT_RAW, 1.0)]
+            if nxt is not None:
+                if nxt.flavor == "enc" and nxt.resample == "keep" and not nxt.has_conv_skip and fullrow:
+                    forms.append(("nsilu", L.VB_OUT_NORM_SILU, 1.0))
+                elif nxt.flavor == "dec" and nxt.resample == "keep" and not nxt.skip_ch:
+                    forms.append(("silu", L.VB_OUT_SILU, 1.0))
+                elif nxt.flavor == "dec" and nxt.skip_ch:
+                    forms.append(("silu", L.VB_OUT_SILU, cat_scale[nxt.name][0]))
+            if s.group == "enc" and s.name in skip_scale:
+                forms.append(("silu", L.VB_OUT_SILU, skip_scale[s.name]))
+            return list(dict.fromkeys(forms))            # e.g. 8x8_block2: silu(1.0) serves both in0 and the first mp_cat
+
+        def alloc_outs(out, forms):
+            outs = []
+            for attr, kind, scale in forms:
+                t = self.a16(out.B, out.R, out.C)
+                if attr == "silu":
+                    out.silu[scale] = t
+                else:
+                    setattr(out, attr, t)
+                outs.append((t, kind, scale))
+            return outs
+
+        for i, s in enumerate(specs):
             mod_ = unet.enc[s.name] if s.group == "enc" else unet.dec[s.name]
-            # which physical forms does the consumer of this block's output need?
-            need_f32 = need_b16 = need_silu = False
-            if nxt is None:
-                need_b16 = unet.out_conv is not None          # out_conv operand
-            elif nxt.flavor == "enc":
-                if nxt.resample == "keep" and nxt.has_conv_skip:
-                    need_b16 = True                            # 1x1 skip GEMM operand
-                else:
-                    need_f32 = True                            # PIXNORM / DOWN_PIXNORM input
-            else:
-                if nxt.resample == "up" or nxt.skip_ch:
-                    need_f32 = True                            # UP / CAT input
-                else:
-                    need_f32 = need_silu = True                # residual + conv_res0 operand
-            if s.group == "enc":
-                need_f32 = True                                # every encoder output is a skip connection
-            is_feature = collect_features and s.heads > 0
-            if is_feature:
-                need_b16 = True                                # x_attn_kv GEMM operand in the denoising UNet
             out = Act(B, s.res, s.cout)
+            out.is_skip = s.group == "enc"
+            out.is_feature = collect_features and s.heads > 0
             R, Cc = s.res, s.cout
-            temps = []                                         # buffers that die with this block
-            popped_skip = None
+            temps, popped_skip = [], None
 
             if s.kind == "conv":
                 w = self.prep_weight(mod_.weight)
-                out.f32 = self.f32(B, R, Cc)
-                self.conv(x_in, w, B, R, 64, Cc, 9, out_f32=out.f32, k_real=9 * s.cin)
-                out.is_skip = True
+                self.conv(x_in, w, B, R, 64, Cc, 9, outs=alloc_outs(out, want(i)), k_real=9 * s.cin)
                 cur = out
                 skips.append(out)
                 continue
 
-            # ---------------- main branch input -> residual base (fp32) + conv_res0 operand (bf16 mp_silu)
+            fullrow = Cc <= FULLROW_MAX
+            x2 = None
+            k2 = 0
+            # ---------------- main branch: residual base + conv_res0 operand(s)
             if s.flavor == "enc":
-                base = self.f32(B, R, Cc)
-                a0 = self.b16(B, R, Cc)
-                temps += [base, a0]
                 if s.resample == "down":
-                    self.eltwise(L.VB_EW_DOWN_PIXNORM, cur.f32, B, R, Cc, out_f32=base, out_silu=a0)
+                    base, a0 = self.a16(B, R, Cc), self.a16(B, R, Cc)
+                    temps += [base, a0]
+                    self.eltwise(L.VB_EW_DOWN_PIXNORM, cur.raw, B, R, Cc, out=base, out_silu=a0)
+                    res, res_mode = base, L.VB_RES_PLAIN
                 elif s.has_conv_skip:
-                    tmp = self.f32(B, R, Cc)
-                    temps.append(tmp)
+                    base, a0 = self.a16(B, R, Cc), self.a16(B, R, Cc)
+                    temps += [base, a0]
                     w = self.prep_weight(mod_.conv_skip.weight)
-                    self.conv(cur.bf16, w, B, R, _pad(s.cin, 64), Cc, 1, out_f32=tmp, k_real=s.cin)
-                    self.eltwise(L.VB_EW_PIXNORM, tmp, B, R, Cc, out_f32=base, out_silu=a0)
+                    if fullrow:      # x = normalize(conv_skip(x)) in one GEMM
+                        self.conv(cur.raw, w, B, R, _pad(s.cin, 64), Cc, 1, k_real=s.cin,
+                                  outs=[(base, L.VB_OUT_NORM, 1.0), (a0, L.VB_OUT_NORM_SILU, 1.0)])
+                    else:
+                        tmp = self.a16(B, R, Cc)
+                        temps.append(tmp)
+                        self.conv(cur.raw, w, B, R, _pad(s.cin, 64), Cc, 1, k_real=s.cin, outs=[(tmp, L.VB_OUT_RAW, 1.0)])
+                        self.eltwise(L.VB_EW_PIXNORM, tmp, B, R, Cc, out=base, out_silu=a0)
+                    res, res_mode = base, L.VB_RES_PLAIN
+                elif cur.nsilu is not None:          # pixel-norm fused on both sides
+                    a0, res, res_mode = cur.nsilu, cur.raw, L.VB_RES_PIXNORM
                 else:
-                    self.eltwise(L.VB_EW_PIXNORM, cur.f32, B, R, Cc, out_f32=base, out_silu=a0)
+                    base, a0 = self.a16(B, R, Cc), self.a16(B, R, Cc)
+                    temps += [base, a0]
+                    self.eltwise(L.VB_EW_PIXNORM, cur.raw, B, R, Cc, out=base, out_silu=a0)
+                    res, res_mode = base, L.VB_RES_PLAIN
                 k0 = Cc
             else:
                 if s.resample == "up":
-                    base = self.f32(B, R, Cc)
-                    a0 = self.b16(B, R, Cc)
+                    base, a0 = self.a16(B, R, Cc), self.a16(B, R, Cc)
                     temps += [base, a0]
-                    self.eltwise(L.VB_EW_UP, cur.f32, B, R, Cc, out_f32=base, out_silu=a0)
-                    k0 = Cc
+                    self.eltwise(L.VB_EW_UP, cur.raw, B, R, Cc, out=base, out_silu=a0)
+                    res, res_mode, k0 = base, L.VB_RES_PLAIN, Cc
                 elif s.skip_ch:
                     skip = skips.pop()
                     popped_skip = skip
                     na, nb = cur.C, skip.C
-                    assert nb == s.skip_ch and na + nb == s.cin
-                    t = unet.concat_balance
-                    cc = math.sqrt((na + nb) / ((1 - t) ** 2 + t ** 2))
-                    wa, wb = cc / math.sqrt(na) * (1 - t), cc / math.sqrt(nb) * t
-                    cat16 = self.b16(B, R, s.cin)
-                    a0 = self.b16(B, R, s.cin)
-                    temps += [cat16, a0]
-                    self.eltwise(L.VB_EW_CAT, cur.f32, B, R, na, b=skip.f32, cb=nb, wa=wa, wb=wb, out_bf16=cat16,
-                                 out_silu=a0)
-                    base = self.f32(B, R, Cc)
+                    assert nb == s.skip_ch and na + nb == s.cin and na % 64 == 0 and nb % 64 == 0
+                    wa, wb = cat_scale[s.name]
+                    a0, x2, k0, k2 = cur.silu[wa], skip.silu[wb], na, nb
+                    base = self.a16(B, R, Cc)
                     temps.append(base)
-                    w = self.prep_weight(mod_.conv_skip.weight)
-                    self.conv(cat16, w, B, R, s.cin, Cc, 1, out_f32=base, k_real=s.cin)
-                    k0 = s.cin
+                    w = self.prep_weight(mod_.conv_skip.weight, split=na, scales=(wa, wb))
+                    self.conv(cur.raw, w, B, R, na, Cc, 1, x2=skip.raw, cin2_pad=nb, outs=[(base, L.VB_OUT_RAW, 1.0)])
+                    res, res_mode = base, L.VB_RES_PLAIN
                 else:
-                    base, a0, k0 = cur.f32, cur.silu, Cc
+                    a0, res, res_mode, k0 = cur.silu[1.0], cur.raw, L.VB_RES_PLAIN, Cc
             assert k0 % 64 == 0, f"{s.name}: {k0} input channels are not a multiple of 64"
 
             # ---------------- residual branch
-            y0 = self.b16(B, R, Cc)
+            y0 = self.a16(B, R, Cc)
             temps.append(y0)
-            w0 = self.prep_weight(mod_.conv_res0.weight)
+            w0 = self.prep_weight(mod_.conv_res0.weight, split=k0 if x2 is not None else None)
             mo = offs[(s.group, s.name)]
-            self.conv(a0, w0, B, R, k0, Cc, 9, flags=L.VB_F_MODSILU, mod=mod.data_ptr() + 4 * mo, mod_stride=mod_total,
-                      out_bf16=y0)
+            self.conv(a0, w0, B, R, k0, Cc, 9, x2=x2, cin2_pad=k2, flags=L.VB_F_MODSILU, mod=mod.data_ptr() + 4 * mo,
+                      mod_stride=mod_total, outs=[(y0, L.VB_OUT_RAW, 1.0)])
             w1 = self.prep_weight(mod_.conv_res1.weight)
-            attn = s.heads > 0
             clip = mod_.clip_act
-            if not attn:
-                out.f32 = self.f32(B, R, Cc) if need_f32 else None
-                out.bf16 = self.b16(B, R, Cc) if need_b16 else None
-                out.silu = self.b16(B, R, Cc) if need_silu else None
-                self.conv(y0, w1, B, R, Cc, Cc, 9, flags=L.VB_F_RESIDUAL | (L.VB_F_CLIP if clip is not None else 0),
-                          res=base, res_t=mod_.res_balance, clip=clip, out_f32=out.f32, out_bf16=out.bf16,
-                          out_silu=out.silu)
+            if s.heads == 0:
+                self.conv(y0, w1, B, R, Cc, Cc, 9, res=res, res_mode=res_mode, res_t=mod_.res_balance, clip=clip,
+                          outs=alloc_outs(out, want(i)))
             else:
-                xr = self.f32(B, R, Cc)
-                xr16 = self.b16(B, R, Cc)
-                temps += [xr, xr16]
-                self.conv(y0, w1, B, R, Cc, Cc, 9, flags=L.VB_F_RESIDUAL, res=base, res_t=mod_.res_balance, out_f32=xr,
-                          out_bf16=xr16)
+                xr = self.a16(B, R, Cc)
+                temps.append(xr)
+                self.conv(y0, w1, B, R, Cc, Cc, 9, res=res, res_mode=res_mode, res_t=mod_.res_balance,
+                          outs=[(xr, L.VB_OUT_RAW, 1.0)])
                 S, D, h = R * R, s.head_dim, s.heads
                 nseg = feat_seg if s.xattn else 0
                 real_seg = 0 if zero_feature_keys else nseg
                 sk = S * (1 + real_seg)
-                q = self.act(B * h * S, D, torch.bfloat16)
-                k = self.act(B * h * sk, D, torch.bfloat16)
-                v = self.act(B * h * sk, D, torch.bfloat16)
+                q = self.act(B * h * S, D)
+                k = self.act(B * h * sk, D)
+                v = self.act(B * h * sk, D)
                 wq = self.prep_weight(mod_.attn_qkv.weight, perm=(3, D))
-                self.conv(xr16, wq, B, R, Cc, 3 * Cc, 1, qkv=dict(D=D, parts=3, out=[q, k, v], seq=[S, sk, sk], off=[0, 0, 0]))
+                self.conv(xr, wq, B, R, Cc, 3 * Cc, 1, qkv=dict(D=D, parts=3, out=[q, k, v], seq=[S, sk, sk], off=[0, 0, 0]))
                 if s.xattn and not zero_feature_keys:
                     f = features.pop(0)
                     assert f.C == Cc and f.R == R, f"{s.name}: feature map mismatch"
                     wkv = self.prep_weight(mod_.x_attn_kv.weight, perm=(2, D))
-                    self.conv(f.bf16, wkv, f.B, R, Cc, 2 * Cc, 1,
+                    self.conv(f.raw, wkv, f.B, R, Cc, 2 * Cc, 1,
                               qkv=dict(D=D, parts=2, out=[k, v], seq=[sk, sk], off=[S, S], seg_div=feat_seg))
-                    temps.append(f.bf16)                       # each feature map feeds exactly one block
-                elif s.xattn:
-                    # unconditional model: x_attn_kv(0) == 0 -> analytic zero keys; count the FLOPs the reference spends
-                    pass
-                y = self.b16(B, R, Cc)
+                    temps.append(f.raw)                        # each feature map feeds exactly one block
+                y = self.a16(B, R, Cc)
                 temps += [q, k, v, y]
+                # unconditional model: x_attn_kv(0) == 0 -> the S*nseg zero keys are accounted for analytically
                 self.attention(q, k, v, y, B, h, S, sk, D, S * nseg if zero_feature_keys else 0)
                 wp = self.prep_weight(mod_.attn_proj.weight)
-                out.f32 = self.f32(B, R, Cc) if need_f32 else None
-                out.bf16 = self.b16(B, R, Cc) if need_b16 else None
-                out.silu = self.b16(B, R, Cc) if need_silu else None
-                self.conv(y, wp, B, R, Cc, Cc, 1, flags=L.VB_F_RESIDUAL | (L.VB_F_CLIP if clip is not None else 0),
-                          res=xr, res_t=mod_.attn_balance, clip=clip, out_f32=out.f32, out_bf16=out.bf16,
-                          out_silu=out.silu)
-            if is_feature:
+                self.conv(y, wp, B, R, Cc, Cc, 1, res=xr, res_mode=L.VB_RES_PLAIN, res_t=mod_.attn_balance, clip=clip,
+                          outs=alloc_outs(out, want(i)))
+            if out.is_feature:
                 feats_out.append(out)
             if s.group == "enc":
                 skips.append(out)
@@ -358,23 +411,21 @@ class Plan:
             # lives on as a skip connection (encoder outputs) or as a source-view feature
             self.release(*temps)
             if popped_skip is not None:
-                self.release(popped_skip.f32, None if popped_skip.is_feature else popped_skip.bf16, popped_skip.silu)
+                self.release(*popped_skip.tensors(keep_raw=popped_skip.is_feature))
             if cur is not None and not cur.is_skip:
-                self.release(cur.f32, None if cur.is_feature else cur.bf16, cur.silu)
-            out.is_skip = s.group == "enc"
-            out.is_feature = is_feature
+                self.release(*cur.tensors(keep_raw=cur.is_feature))
             cur = out
 
         raw = None
         if unet.out_conv is not None:
             wo = self.prep_weight(unet.out_conv.weight, gain=float(unet.out_gain.detach().float().item()), cout_pad=16)
             raw = self.buf((B * cur.R * cur.R, 16), torch.float32)
-            self.conv(cur.bf16, wo, B, cur.R, cur.C, unet.out_conv.out_channels, 9, cout_pad=16, out_f32=raw)
+            self.conv(cur.raw, wo, B, cur.R, cur.C, unet.out_conv.out_channels, 9, cout_pad=16, out_f32=raw)
         return raw, feats_out
 
     # ------------------------------------------------------------------ whole NVPrecond call
     def _build(self):
-        net, B, Bx, dev = self.net, self.B, self.Bx, self.device
+        net, B, Bx = self.net, self.B, self.Bx
         R = net.img_resolution
         sd = float(net.sigma_data)
         # persistent I/O buffers (callers copy into / out of these)
@@ -393,7 +444,7 @@ class Plan:
         features, feat_seg = None, 1
         if net.encoder is not None:
             enc = net.encoder
-            src16 = self.buf((Bx * R * R, 64), torch.bfloat16)
+            src16 = self.buf((Bx * R * R, 64), self.op_dtype)
             d = L.PrecondInDesc(x=self.in_src.data_ptr(), cond=None, noise=None, sigma=None, out=src16.data_ptr(), B=Bx,
                                 R=R, cpad=64, sigma_n=1, sigma_stride=0, img_stride=3 * R * R, sigma_data=sd, noisy_sr=0.0)
             L.check(self.lib.vb_plan_add_precond_in(self.handle, C.byref(d)), "vb_plan_add_precond_in")
@@ -404,7 +455,7 @@ class Plan:
             feat_seg = 2 if self.dual else 1
 
         unet = net.unet
-        x16 = self.buf((B * R * R, 64), torch.bfloat16)
+        x16 = self.buf((B * R * R, 64), self.op_dtype)
         step = 2 if self.dual else 1
         d = L.PrecondInDesc(x=self.in_x.data_ptr(), cond=L.ptr(self.in_cond), noise=L.ptr(self.in_noise),
                             sigma=self.in_sigma.data_ptr(), out=x16.data_ptr(), B=B, R=R, cpad=64, sigma_n=B,
