@@ -206,6 +206,8 @@ typedef struct vb_precond_in_desc {
   const float* sigma; /* [B] or [1]; NULL => no c_in scaling (encoder input) */
   void* out;          /* 16-bit NHWC [B][R][R][cpad] */
   int32_t B, R, cpad, sigma_n, sigma_stride;
+  int32_t im2col;     /* 1: write the 3x3 neighbourhood (channel index ci*9+tap, zero outside the image) so that the first
+                         3x3 conv (models.py:351,394) becomes a K=64 1x1 GEMM instead of 9 taps of 64 padded channels */
   int64_t img_stride; /* elements between consecutive images of x (allows x[::2]) */
   float sigma_data, noisy_sr;
 } vb_precond_in_desc;

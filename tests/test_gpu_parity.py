@@ -90,6 +90,9 @@ CONV_CASES = [
     (1, 256, 64, 64, 9, 64, 0, 2, 1, (1, 4, 2)),        # SR resolution
     (40, 16, 384, 384, 9, 128, 0, 1, 1, (1, 2)),        # persistent loop, several tiles per CTA, 3 N tiles
     (40, 16, 384, 384, 9, 192, 1, 0, 0, (1,)),
+    (2, 128, 128, 128, 9, 128, 0, 2, 1, (1, 4, 2)),     # 128-pixel rows: haloed row box serves 3 taps, streamed weights
+    (3, 256, 64, 64, 9, 64, 1, 0, 0, (1,)),             # ... with the layer's weights resident in shared memory
+    (1, 128, 192, 64, 9, 64, 0, 1, 1, (1, 2)),          # K = 3 chunks x 9 taps, resident weights do not fit -> streamed
 ]
 
 
@@ -462,8 +465,10 @@ def test_full_size_presets_vs_oracle(env, preset, B):
     eager = net(src, x, sigma, geom, **kw)
     assert torch.equal(full, eager)
     if not cfg.get("super_res"):
+        # a different batch size may pick other tile shapes / K orders (tap-grouped main loop): equal up to the
+        # 16-bit rounding of the stream, not bitwise
         sub = net(src[:3], x[:3], sigma[:3], geom[:3])
-        assert rel(sub, full[:3]) < 1e-5
+        assert rel(sub, full[:3]) < 2e-3
 
 
 def test_generate_images_nvs_pipeline(env):

@@ -1,4 +1,10 @@
-"""Micro-benchmark of vb_conv on the layer shapes that dominate the step (B=32 unless given)."""
+"""Micro-benchmark of vb_conv on the layer shapes that dominate the step (B=32 unless given).
+
+Env: VB_B batch, VB_REPS repetitions, VB_ONLY comma list of shape indices, VB_EPI comma list of epilogues:
+  simple  one raw output                         mod    conv_res0: modulation + mp_silu -> raw
+  r1s     mp_sum(res) + clip -> raw, silu        r2ns   mp_sum(pixel_norm(res)) + clip -> raw, norm_silu
+  r2nss   ... -> raw, norm_silu, silu            (library knobs: VB_TAP_MODE, VB_DBG, VB_GENERIC_EPI)
+"""
 import ctypes as C
 import os
 import sys
@@ -14,11 +20,13 @@ dev = torch.device("cuda")
 stream = torch.cuda.current_stream().cuda_stream
 SHAPES = [  # R, cin, cout, taps, bn
     (256, 64, 64, 9, 64), (128, 128, 128, 9, 128), (64, 128, 128, 9, 128), (32, 256, 256, 9, 256),
-    (16, 384, 384, 9, 128), (8, 512, 512, 9, 32), (8, 512, 512, 9, 128), (16, 384, 1152, 1, 192), (256, 128, 64, 1, 64),
+    (16, 384, 384, 9, 128), (8, 512, 512, 9, 64), (8, 512, 512, 9, 128), (16, 384, 1152, 1, 192), (256, 128, 64, 1, 64),
+    (256, 128, 64, 9, 64), (64, 192, 192, 9, 192), (16, 384, 384, 9, 192), (64, 128, 128, 1, 128),
 ]
 B = int(os.environ.get("VB_B", "32"))
 reps = int(os.environ.get("VB_REPS", "10"))
 only = os.environ.get("VB_ONLY")
+epis = os.environ.get("VB_EPI", "r2ns").split(",")
 for idx, (R, cin, cout, taps, bn) in enumerate(SHAPES):
     if only is not None and str(idx) not in only.split(","):
         continue
@@ -26,27 +34,40 @@ for idx, (R, cin, cout, taps, bn) in enumerate(SHAPES):
     x = torch.randn(B, R, R, cin, device=dev).to(dt)
     w = (torch.randn(cout, taps * cin, device=dev) * 0.03).to(dt)
     res = torch.randn(B * R * R, cout, device=dev).to(dt)
-    o0 = torch.empty(B * R * R, cout, dtype=dt, device=dev)
-    o1 = torch.empty(B * R * R, cout, dtype=dt, device=dev)
+    mod = torch.rand(B, cout, device=dev) + 0.5
+    outs = [torch.empty(B * R * R, cout, dtype=dt, device=dev) for _ in range(3)]
     fullrow = cout == bn and cout <= 256
-    d = L.ConvDesc(x=x.data_ptr(), w=w.data_ptr(), res=res.data_ptr(), B=B, H=R, W=R, cin_pad=cin, cin2_pad=0,
-                   cout_pad=cout, taps=taps, block_n=bn, epi_mode=0, flags=L.VB_F_CLIP,
-                   res_mode=L.VB_RES_PIXNORM if fullrow else L.VB_RES_PLAIN, res_t=0.3, clip=256.0)
-    d.out[0], d.out_kind[0] = o0.data_ptr(), L.VB_OUT_RAW
-    d.out[1], d.out_kind[1] = o1.data_ptr(), (L.VB_OUT_NORM_SILU if fullrow else L.VB_OUT_SILU)
-    d.out_scale[1] = 1.0
-    plan = C.c_void_p()
-    L.check(lib.vb_plan_create(C.byref(plan)), "create")
-    L.check(lib.vb_plan_add_conv(plan, C.byref(d)), "add")
-    for _ in range(3):
-        L.check(lib.vb_plan_run(plan, 0, -1, stream), "run")
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        L.check(lib.vb_plan_run(plan, 0, -1, stream), "run")
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    fl = 2.0 * B * R * R * cout * cin * taps
-    print(f"[{idx}] {R}x{R} cin{cin} cout{cout} taps{taps} bn{bn} B{B}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s", flush=True)
-    lib.vb_plan_destroy(plan)
+    for epi in epis:
+        d = L.ConvDesc(x=x.data_ptr(), w=w.data_ptr(), B=B, H=R, W=R, cin_pad=cin, cin2_pad=0, cout_pad=cout, taps=taps,
+                       block_n=bn, epi_mode=0, flags=0, res_mode=0, res_t=0.3, clip=256.0)
+        kinds = [L.VB_OUT_RAW]
+        if epi == "mod":
+            d.flags, d.mod, d.mod_stride = L.VB_F_MODSILU, mod.data_ptr(), cout
+        elif epi != "simple":
+            d.flags, d.res = L.VB_F_CLIP, res.data_ptr()
+            d.res_mode = L.VB_RES_PIXNORM if (epi.startswith("r2") and fullrow) else L.VB_RES_PLAIN
+            for ch in epi[2:]:
+                kinds.append(L.VB_OUT_SILU if ch == "s" else (L.VB_OUT_NORM_SILU if fullrow else L.VB_OUT_SILU))
+                if ch == "n":
+                    break
+            if epi.endswith("nss"):
+                kinds.append(L.VB_OUT_SILU)
+        for i, k in enumerate(kinds):
+            d.out[i], d.out_kind[i], d.out_scale[i] = outs[i].data_ptr(), k, 1.0
+        plan = C.c_void_p()
+        L.check(lib.vb_plan_create(C.byref(plan)), "create")
+        L.check(lib.vb_plan_add_conv(plan, C.byref(d)), "add")
+        for _ in range(3):
+            L.check(lib.vb_plan_run(plan, 0, -1, stream), "run")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            L.check(lib.vb_plan_run(plan, 0, -1, stream), "run")
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        fl = 2.0 * B * R * R * cout * cin * taps
+        by = 2.0 * B * R * R * (cin + cout * (len(kinds) + (d.res_mode != 0)))
+        print(f"[{idx}] {R}x{R} cin{cin} cout{cout} taps{taps} bn{bn} B{B} {epi:6s}: {ms*1e3:8.1f} us  "
+              f"{fl/ms/1e9:7.1f} TFLOP/s  {by/ms/1e6:6.0f} GB/s", flush=True)
+        lib.vb_plan_destroy(plan)

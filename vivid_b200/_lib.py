@@ -54,8 +54,8 @@ class EmbDesc(C.Structure):
 
 class PrecondInDesc(C.Structure):
     _fields_ = [("x", vp), ("cond", vp), ("noise", vp), ("sigma", vp), ("out", vp), ("B", i32), ("R", i32),
-                ("cpad", i32), ("sigma_n", i32), ("sigma_stride", i32), ("img_stride", i64), ("sigma_data", f32),
-                ("noisy_sr", f32)]
+                ("cpad", i32), ("sigma_n", i32), ("sigma_stride", i32), ("im2col", i32), ("img_stride", i64),
+                ("sigma_data", f32), ("noisy_sr", f32)]
 
 
 class PrecondOutDesc(C.Structure):

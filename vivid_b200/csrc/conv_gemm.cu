@@ -10,18 +10,23 @@
 // K = taps * input channels (64 per pipeline stage; up to two channel-concatenated sources, which
 // is how mp_cat, :78-84, is folded into the consumer instead of being materialised).
 //
-// CTA = 8 warps, persistent over tiles (static round-robin schedule):
+// CTA = 12 warps, persistent over tiles (static round-robin schedule):
 //   warp 0   TMA producer (one lane)            warp 1   MMA issuer (one lane)
-//   warp 2   TMEM allocator                     warps 4-7 epilogue (one thread per pixel row)
+//   warp 2   TMEM allocator                     warps 4-11 epilogue: two warps per TMEM lane quadrant,
+//                                                          each owning one 32-column half of every 64-column chunk
 // Pipelines: smem full/empty ring (TMA <-> MMA), a double-buffered TMEM accumulator (MMA <->
 // epilogue) so the epilogue of tile i overlaps the main loop of tile i+1, and inside the epilogue
 // a residual-tile TMA ring plus an output staging ring drained by TMA stores.
 //
-// Why the staged epilogue: one thread owns one pixel row of the accumulator (TMEM lane), so direct
-// global loads/stores touch 32 different cache lines per warp instruction; ncu showed L1TEX at 69 %
-// and the tensor pipe at 9.5 % on the K=576 layers (profiles/r01_conv_epilogue_before.txt).  TMA
-// moves whole swizzled 128-byte rows and never enters L1TEX.
+// Epilogue structure (round-1 ncu, profiles/r01_conv_epilogue_*.txt): with K as small as 576 the main
+// loop of a tile is ~1.2-1.7 k cycles, so the epilogue is co-critical.  v1 (per-thread global I/O) sat at
+// L1TEX 69 %; v2 (TMA-staged I/O, 4 warps, up to three passes over TMEM, run-time switches) was issue/latency
+// bound with one warp per scheduler at ~20 instructions per element.  v3 (this file): 8 warps, ONE pass over
+// TMEM — the clamped result is kept packed (16-bit) in registers for the deferred pixel-norm outputs — and
+// the epilogue is compiled per (residual mode, modulation, output kinds) variant so the hot loop is
+// straight-line code.
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 
 #include "common.h"
@@ -36,12 +41,18 @@ constexpr int kBlockK = 64;
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kChunkBytes = kBlockM * 128;            // one 64-column 16-bit sub-tile: 16 KiB
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 256;
-constexpr int kEpiThreads = 128;
+constexpr int kMaxBSlots = 12;
+constexpr int kThreads = 384;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kFirstEpiWarp = 4;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;                       // columns between the two accumulator buffers
-constexpr int kSmemMax = 227 * 1024 - 2048;           // dynamic smem we allow ourselves (barriers are static)
-constexpr int kEpiBarrier = 1;                        // named barrier id of the 4 epilogue warps
+constexpr int kStaticSmem = 4096;                     // barriers + statistic exchange (static __shared__), rounded up
+constexpr int kSmemMax = 227 * 1024 - 1024 - kStaticSmem;   // dynamic smem we allow ourselves (1 KiB alignment slack)
+constexpr int kMaxResSlots = 4;                       // residual TMA ring depth (16 KiB sub-tiles)
+constexpr int kEpiBarrier = 1;                        // named barrier of all epilogue warps
+constexpr int kPairBarrier = 2;                       // +quadrant: the two warps sharing a TMEM lane quadrant
 
 struct ConvKernelParams {
   int B, H, W;
@@ -51,20 +62,27 @@ struct ConvKernelParams {
   int taps, kc_a, kc_b;
   int block_n;
   int num_stages, stage_bytes, b_bytes;
+  // tap_mode != 0: one haloed activation box per (kc, group) serves three taps through shifted UMMA descriptor
+  // windows (the SWIZZLE_128B phase is a function of the absolute smem address, so a descriptor may start at any
+  // 128-byte row: tools/exp/umma_window_test.cu).  1: rows of >=128 pixels, box {bw+2} px, taps dx=-1,0,1, window
+  // step 1 row.  2: multi-row tiles, box {bh+2} x {bw}, taps dy=-1,0,1, window step bw rows.
+  // Two rings: a_slots activation boxes (a_slot_bytes each) and b_slots weight tap tiles (b_bytes each);
+  // b_resident: the whole weight matrix of this layer stays in shared memory for the life of the CTA.
+  int tap_mode, a_slots, a_slot_bytes, a_tx_bytes, b_slots, b_off, b_resident, win_rows;
   uint32_t idesc;
   int epi_mode, flags;
   const float* mod;
   int mod_stride;
   int res_mode;         // VB_RES_*
-  int res_resident;     // residual chunks of a tile fit the 2-buffer ring and are loaded once per tile
+  int res_slots;        // residual ring depth (power of two)
   int nslots;           // staged output slots in use
   int out_kind[3];
   float out_scale[3];
-  int stage_depth;      // staging ring depth in chunks (1 or 2)
+  int gslots;           // sub-tiles per staging region (a region = the outputs of one chunk in one pass)
   int res_off, stg_off; // byte offsets of the residual ring / staging ring inside dynamic smem
   float* out_f32;
   int ld_f32;
-  float res_a, res_b, clip;
+  float res_a, res_b, clamp;
   float inv_sqrt_c;     // 1/sqrt(cout) for the pixel norms
   int head_dim, parts, seg_div, heads;
   op_t* part0;
@@ -73,6 +91,7 @@ struct ConvKernelParams {
   int part_seq[3];
   int part_off[3];
   float norm_scale;   // 1/sqrt(head_dim)
+  int dbg;            // ablation switches for micro-benchmarks (VB_DBG): 1 = epilogue does no work, 2 = no TMA stores
 };
 
 struct TileCoord {
@@ -94,83 +113,40 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int 
   return t;
 }
 
-// 32 columns [c, c+32) of one pixel row: accumulator -> (modulation, mp_silu) -> mp_sum with the residual -> clip.
-// `rrow` points at this row's 128-byte slot of the swizzled residual sub-tile (64 columns), `half` selects which 32.
-__device__ __forceinline__ void compute_v32(const ConvKernelParams& p, uint32_t taddr, int col, int n, bool valid,
-                                            const uint8_t* rrow, int row, int half, float res_inv, float* v) {
-  tmem_ld32(taddr, v);
-  tmem_ld_wait();
-  if (p.flags & VB_F_MODSILU) {
-    const float4* m = reinterpret_cast<const float4*>(p.mod + static_cast<size_t>(valid ? n : 0) * p.mod_stride + col);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 mm = __ldg(m + j);
-      v[4 * j + 0] = mp_silu_fast(v[4 * j + 0] * mm.x);
-      v[4 * j + 1] = mp_silu_fast(v[4 * j + 1] * mm.y);
-      v[4 * j + 2] = mp_silu_fast(v[4 * j + 2] * mm.z);
-      v[4 * j + 3] = mp_silu_fast(v[4 * j + 3] * mm.w);
-    }
-  }
-  if (p.res_mode != VB_RES_NONE) {
-    const float ra = p.res_a * res_inv;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint4 q = *reinterpret_cast<const uint4*>(rrow + (((half * 4 + j) ^ (row & 7)) << 4));
-      const float2 a = unpack_op2(q.x), b = unpack_op2(q.y), c = unpack_op2(q.z), d = unpack_op2(q.w);
-      v[8 * j + 0] = a.x * ra + v[8 * j + 0] * p.res_b;
-      v[8 * j + 1] = a.y * ra + v[8 * j + 1] * p.res_b;
-      v[8 * j + 2] = b.x * ra + v[8 * j + 2] * p.res_b;
-      v[8 * j + 3] = b.y * ra + v[8 * j + 3] * p.res_b;
-      v[8 * j + 4] = c.x * ra + v[8 * j + 4] * p.res_b;
-      v[8 * j + 5] = c.y * ra + v[8 * j + 5] * p.res_b;
-      v[8 * j + 6] = d.x * ra + v[8 * j + 6] * p.res_b;
-      v[8 * j + 7] = d.y * ra + v[8 * j + 7] * p.res_b;
-    }
-  }
-  if (p.flags & VB_F_CLIP) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -p.clip), p.clip);
-  }
+// Two floats -> one packed 16-bit pair, saturating to the finite range (no inf in the stream).
+__device__ __forceinline__ uint32_t pack_sat2(float lo, float hi) {
+#ifdef VB_OP_BF16
+  return pack_op2(lo, hi);
+#else
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+#endif
 }
 
-// Sum of squares of this row's 64 residual columns (for VB_RES_PIXNORM).
-__device__ __forceinline__ float res_sumsq64(const uint8_t* rrow, int row) {
+// Plain round-to-nearest pack for values already clamped to the finite range.
+__device__ __forceinline__ uint32_t pack_op2_nosat(float lo, float hi) {
+#ifdef VB_OP_BF16
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+#else
+  __half2 h = __floats2half2_rn(lo, hi);
+#endif
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Byte offset of 16-byte unit `u` (0..7) of a 128-byte row in a SWIZZLE_128B sub-tile.
+__device__ __forceinline__ int swz(int u, int row) { return (u ^ (row & 7)) << 4; }
+
+// Sum of squares of this row's 32 residual columns [half*32, half*32+32) (VB_RES_PIXNORM statistic).
+__device__ __forceinline__ float res_sumsq32(const uint8_t* rrow, int row, int half) {
   float ss = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const uint4 q = *reinterpret_cast<const uint4*>(rrow + ((j ^ (row & 7)) << 4));
+  for (int j = 0; j < 4; ++j) {
+    const uint4 q = *reinterpret_cast<const uint4*>(rrow + swz(half * 4 + j, row));
     const float2 a = unpack_op2(q.x), b = unpack_op2(q.y), c = unpack_op2(q.z), d = unpack_op2(q.w);
     ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
   }
   return ss;
-}
-
-// Transform 32 values for one output slot and write them (16-bit) into this row of the staging sub-tile.
-template <int KIND>
-__device__ __forceinline__ void stage_out32_k(float scale, float inv_v, const float* v, uint8_t* srow, int row, int half) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float t[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float x = v[8 * j + e];
-      t[e] = KIND == VB_OUT_RAW ? x
-             : KIND == VB_OUT_SILU ? mp_silu_fast(x * scale)
-             : KIND == VB_OUT_NORM ? x * inv_v
-                                   : mp_silu_fast(x * inv_v);
-    }
-    *reinterpret_cast<uint4*>(srow + (((half * 4 + j) ^ (row & 7)) << 4)) =
-        make_uint4(pack_op2(t[0], t[1]), pack_op2(t[2], t[3]), pack_op2(t[4], t[5]), pack_op2(t[6], t[7]));
-  }
-}
-__device__ __forceinline__ void stage_out32(int kind, float scale, float inv_v, const float* v, uint8_t* srow, int row,
-                                            int half) {
-  switch (kind) {
-    case VB_OUT_RAW: stage_out32_k<VB_OUT_RAW>(scale, inv_v, v, srow, row, half); break;
-    case VB_OUT_SILU: stage_out32_k<VB_OUT_SILU>(scale, inv_v, v, srow, row, half); break;
-    case VB_OUT_NORM: stage_out32_k<VB_OUT_NORM>(scale, inv_v, v, srow, row, half); break;
-    default: stage_out32_k<VB_OUT_NORM_SILU>(scale, inv_v, v, srow, row, half); break;
-  }
 }
 
 // QKVNORM: one (head, q|k|v) group of D accumulator columns of one token: normalise over D in fp32
@@ -218,6 +194,12 @@ struct OutMaps {
   CUtensorMap m[3];
 };
 
+__device__ __forceinline__ bool kind_direct(int k) { return k == VB_OUT_RAW || k == VB_OUT_SILU; }
+__device__ __forceinline__ bool kind_norm(int k) { return k == VB_OUT_NORM || k == VB_OUT_NORM_SILU; }
+
+// Template arguments >= 0 fix the epilogue variant at compile time; -1 reads it from the parameters (generic
+// fallback for combinations the plans never emit).  STAGED = 0 is the QKVNORM / narrow fp32 epilogue.
+template <int STAGED, int RES_T, int MOD_T, int K0_T, int K1_T, int K2_T>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_res,
@@ -225,9 +207,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t bfull_bar[kMaxBSlots];
+  __shared__ __align__(8) uint64_t bempty_bar[kMaxBSlots];
   __shared__ __align__(8) uint64_t tmem_full[2];
   __shared__ __align__(8) uint64_t tmem_empty[2];
-  __shared__ __align__(8) uint64_t res_full[2];
+  __shared__ __align__(8) uint64_t res_full[kMaxResSlots];
+  __shared__ __align__(8) uint64_t res_empty[kMaxResSlots];
+  __shared__ float xchg[2][2][kBlockM];     // [residual | result statistic][column half][row]
   __shared__ uint32_t tmem_slot;
 
   // SWIZZLE_128B tiles need 1024-byte alignment.
@@ -243,14 +229,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int s = 0; s < p.nslots; ++s) tma_prefetch_desc(&map_out.m[s]);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.num_stages; ++s) {
+    for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    for (int s = 0; s < kMaxBSlots; ++s) {
+      mbar_init(&bfull_bar[s], 1);
+      mbar_init(&bempty_bar[s], 1);
+    }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], kEpiThreads);
+      mbar_init(&tmem_empty[b], kEpiWarps);
+    }
+    for (int b = 0; b < kMaxResSlots; ++b) {
       mbar_init(&res_full[b], 1);
+      mbar_init(&res_empty[b], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -265,7 +258,50 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    const bool elected = elect_one_sync();
+    if (elected && p.tap_mode != 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      const int kct = p.kc_a + p.kc_b;
+      if (p.b_resident) {
+        // every tap tile of this layer's weights, once (n_tiles == 1)
+        const int nb = 9 * kct;
+        mbar_expect_tx(&bfull_bar[0], static_cast<uint32_t>(nb) * p.b_bytes);
+        for (int i = 0; i < nb; ++i) tma_load_2d(&map_w, &bfull_bar[0], smem + p.b_off + i * p.b_bytes, i * kBlockK, 0);
+      }
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int g = 0; g < 3; ++g) {
+          for (int kc = 0; kc < kct; ++kc) {
+            mbar_wait(&empty_bar[as], aph ^ 1u);
+            uint8_t* sa = smem + as * p.a_slot_bytes;
+            mbar_expect_tx(&full_bar[as], p.a_tx_bytes);
+            const int cx = p.tap_mode == 1 ? t.x0 - 1 : t.x0 + g - 1;
+            const int cy = p.tap_mode == 1 ? t.y0 + g - 1 : t.y0 - 1;
+            if (kc < p.kc_a)
+              tma_load_4d(&map_a, &full_bar[as], sa, kc * kBlockK, cx, cy, t.n0);
+            else
+              tma_load_4d(&map_a2, &full_bar[as], sa, (kc - p.kc_a) * kBlockK, cx, cy, t.n0);
+            if (++as == p.a_slots) {
+              as = 0;
+              aph ^= 1u;
+            }
+            if (!p.b_resident) {
+              for (int i = 0; i < 3; ++i) {
+                const int tap = p.tap_mode == 1 ? g * 3 + i : i * 3 + g;
+                mbar_wait(&bempty_bar[bs], bph ^ 1u);
+                mbar_expect_tx(&bfull_bar[bs], p.b_bytes);
+                tma_load_2d(&map_w, &bfull_bar[bs], smem + p.b_off + bs * p.b_bytes, (tap * kct + kc) * kBlockK, t.col0);
+                if (++bs == p.b_slots) {
+                  bs = 0;
+                  bph ^= 1u;
+                }
+              }
+            }
+          }
+        }
+      }
+    } else if (elected) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = kAStageBytes + p.b_bytes;
@@ -296,7 +332,62 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    const bool elected = elect_one_sync();
+    if (elected && p.tap_mode != 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int it = 0;
+      const int kct = p.kc_a + p.kc_b;
+      if (p.b_resident) {
+        mbar_wait(&bfull_bar[0], 0);
+        tc_fence_after();
+      }
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t bphase = static_cast<uint32_t>(it >> 1) & 1u;
+        mbar_wait(&tmem_empty[buf], bphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
+        uint32_t accumulate = 0;
+        for (int g = 0; g < 3; ++g) {
+          for (int kc = 0; kc < kct; ++kc) {
+            mbar_wait(&full_bar[as], aph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + as * p.a_slot_bytes);
+            for (int i = 0; i < 3; ++i) {
+              uint32_t sb;
+              if (p.b_resident) {
+                const int tap = p.tap_mode == 1 ? g * 3 + i : i * 3 + g;
+                sb = smem_u32(smem + p.b_off + (tap * kct + kc) * p.b_bytes);
+              } else {
+                mbar_wait(&bfull_bar[bs], bph);
+                tc_fence_after();
+                sb = smem_u32(smem + p.b_off + bs * p.b_bytes);
+              }
+              const uint32_t wa = sa + static_cast<uint32_t>(i * p.win_rows) * 128u;
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                umma_f16_ss(d_tmem, umma_desc_sw128(wa + k * 32), umma_desc_sw128(sb + k * 32), p.idesc, accumulate);
+                accumulate = 1;
+              }
+              if (!p.b_resident) {
+                umma_commit(&bempty_bar[bs]);
+                if (++bs == p.b_slots) {
+                  bs = 0;
+                  bph ^= 1u;
+                }
+              }
+            }
+            umma_commit(&empty_bar[as]);
+            if (++as == p.a_slots) {
+              as = 0;
+              aph ^= 1u;
+            }
+          }
+        }
+        umma_commit(&tmem_full[buf]);
+      }
+    } else if (elected) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -327,173 +418,271 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         umma_commit(&tmem_full[buf]);       // accumulator complete -> epilogue
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= kFirstEpiWarp) {
     // ------------------------------------------------------------------ epilogue
-    const int quad = warp & 3;
+    const int quad = warp & 3;                                      // TMEM lane quadrant this warp may read
+    const int half = (warp - kFirstEpiWarp) >> 2;                   // which 32 columns of every 64-column chunk
     const int row = quad * 32 + lane;
-    const bool leader = threadIdx.x == kThreads - kEpiThreads;      // first epilogue thread issues the TMA traffic
+    const bool leader = elect_one_sync() && warp == kFirstEpiWarp;  // one thread issues the epilogue's TMA traffic
     const int rx = row % p.bw;
     const int r2 = row / p.bw;
     const int ry = r2 % p.bh;
     const int rn = r2 / p.bh;
-    const int chunks = p.block_n >> 6;                              // 64-column sub-tiles (staged path only)
-    const bool staged = p.epi_mode == VB_EPI_PLAIN && p.nslots > 0;
-    const bool has_res = p.res_mode != VB_RES_NONE;
-    bool needs_norm = false;
-    for (int s = 0; s < p.nslots; ++s) needs_norm |= p.out_kind[s] >= VB_OUT_NORM;
-    uint8_t* res_ring = smem + p.res_off;
-    uint8_t* stg_ring = smem + p.stg_off;
-    uint32_t res_items = 0;      // residual sub-tiles consumed so far (ring position / phase), streaming mode
-    uint32_t res_tiles = 0;      // tiles seen (phase of the resident residual buffers)
-    uint32_t stg_chunks = 0;     // staging chunks produced so far (ring position)
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t bphase = static_cast<uint32_t>(it >> 1) & 1u;
-      const TileCoord t = decode_tile(p, tile);
-      const int n = t.n0 + rn;
-      const bool valid = n < p.B;
-      const int s_img = (t.y0 + ry) * p.W + t.x0 + rx;
-      const size_t pix = static_cast<size_t>(n) * p.H * p.W + s_img;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * kAccStride);
 
-      if (!staged) {
+    if (!STAGED) {
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t bphase = static_cast<uint32_t>(it >> 1) & 1u;
+        const TileCoord t = decode_tile(p, tile);
+        const int n = t.n0 + rn;
+        const bool valid = n < p.B;
+        const int s_img = (t.y0 + ry) * p.W + t.x0 + rx;
+        const size_t pix = static_cast<size_t>(n) * p.H * p.W + s_img;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * kAccStride);
         mbar_wait(&tmem_full[buf], bphase);
         tc_fence_after();
         if (p.epi_mode == VB_EPI_QKVNORM) {
           if (p.head_dim == 64) {
-            for (int c = 0; c < p.block_n; c += 64) epi_group_qkv<64>(p, taddr + c, t.col0 + c, n, s_img, valid);
+            for (int c = half * 64; c < p.block_n; c += 128) epi_group_qkv<64>(p, taddr + c, t.col0 + c, n, s_img, valid);
           } else {
-            for (int c = 0; c < p.block_n; c += 32) epi_group_qkv<32>(p, taddr + c, t.col0 + c, n, s_img, valid);
+            for (int c = half * 32; c < p.block_n; c += 64) epi_group_qkv<32>(p, taddr + c, t.col0 + c, n, s_img, valid);
           }
         } else {
-          for (int c = 0; c < p.block_n; c += 16) epi_f32_16(p, taddr + c, t.col0 + c, pix, valid);
+          for (int c = half * 16; c < p.block_n; c += 32) epi_f32_16(p, taddr + c, t.col0 + c, pix, valid);
         }
         tc_fence_before();
-        mbar_arrive(&tmem_empty[buf]);
-        continue;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       }
+    } else {
+      const int res_mode = RES_T >= 0 ? RES_T : p.res_mode;
+      const bool modsilu = MOD_T >= 0 ? MOD_T != 0 : (p.flags & VB_F_MODSILU) != 0;
+      const int k0 = K0_T >= 0 ? K0_T : p.out_kind[0];
+      const int k1 = K1_T >= 0 ? K1_T : p.out_kind[1];
+      const int k2 = K2_T >= 0 ? K2_T : p.out_kind[2];
+      const bool has_res = res_mode != VB_RES_NONE;
+      const bool needs_norm = kind_norm(k0) || kind_norm(k1) || kind_norm(k2);
+      const bool any_direct = kind_direct(k0) || kind_direct(k1) || kind_direct(k2);
+      const int chunks = p.block_n >> 6;                            // 64-column sub-tiles
+      uint8_t* res_ring = smem + p.res_off;
+      uint8_t* stg_ring = smem + p.stg_off;
+      const uint32_t rmask = static_cast<uint32_t>(p.res_slots - 1);
+      const uint32_t rshift = p.res_slots == 4 ? 2u : 1u;
+      const int items = chunks * (res_mode == VB_RES_PIXNORM ? 2 : 1);   // residual (pass, chunk) items per tile
+      uint32_t res_q = 0;          // residual items consumed so far by this thread (ring position / phase)
+      uint32_t res_issued = 0;     // residual items whose TMA load has been issued (leader only)
+      uint32_t groups = 0;         // staging regions produced so far (ring position)
+      const float clampv = p.clamp;
 
-      // ---- residual sub-tiles: resident (<= 2 chunks, loaded once per tile) or streamed through the 2-buffer ring
-      const int n_pass = 1 + (needs_norm ? 1 : 0) + (p.res_mode == VB_RES_PIXNORM ? 1 : 0);
-      const int items = chunks * n_pass;                             // streaming: (pass, chunk) items of this tile
-      if (has_res && leader) {
-        if (p.res_resident) {
-          for (int c = 0; c < chunks; ++c) {
-            mbar_expect_tx(&res_full[c], kChunkBytes);
-            tma_load_4d(&map_res, &res_full[c], res_ring + c * kChunkBytes, t.col0 + c * 64, t.x0, t.y0, t.n0);
-          }
-        } else {
-          for (int k = 0; k < 2 && k < items; ++k) {
-            const uint32_t slot = (res_items + k) & 1u;
+      // The leader keeps the residual ring full ACROSS tile boundaries: the next tile's residual is in flight while
+      // this tile is being finished.
+      auto res_topup = [&]() {
+        if (has_res && leader) {
+          while (res_issued < res_q + static_cast<uint32_t>(p.res_slots)) {
+            const uint32_t ti = res_issued / items;                  // CTA-local index of the tile owning the item
+            const int tl = blockIdx.x + static_cast<int>(ti) * gridDim.x;
+            if (tl >= p.total_tiles) break;
+            const TileCoord tt = decode_tile(p, tl);
+            const uint32_t slot = res_issued & rmask;
+            mbar_wait(&res_empty[slot], ((res_issued >> rshift) & 1u) ^ 1u);
             mbar_expect_tx(&res_full[slot], kChunkBytes);
-            tma_load_4d(&map_res, &res_full[slot], res_ring + slot * kChunkBytes, t.col0 + (k % chunks) * 64, t.x0, t.y0, t.n0);
+            tma_load_4d(&map_res, &res_full[slot], res_ring + slot * kChunkBytes,
+                        tt.col0 + static_cast<int>((res_issued % items) % chunks) * 64, tt.x0, tt.y0, tt.n0);
+            ++res_issued;
           }
         }
-      }
-      int item = 0;
-      // Makes residual chunk c of the current pass readable; returns this row's 128-byte slot.
-      auto res_acquire = [&](int c) -> const uint8_t* {
-        if (!has_res) return nullptr;
-        if (p.res_resident) {
-          if (item < chunks) mbar_wait(&res_full[c], res_tiles & 1u);       // first touch this tile
-          return res_ring + c * kChunkBytes + row * 128;
-        }
-        const uint32_t k = res_items + item;
-        mbar_wait(&res_full[k & 1u], (k >> 1) & 1u);
-        return res_ring + (k & 1u) * kChunkBytes + row * 128;
       };
-      // Streaming mode: everybody is done with the ring slot of the current item -> refill it with item+2.
-      auto res_release = [&](bool already_synced) {
-        if (has_res && !p.res_resident) {
-          if (!already_synced) named_bar_sync(kEpiBarrier, kEpiThreads);
-          if (leader && item + 2 < items) {
-            const uint32_t slot = (res_items + item) & 1u;
-            mbar_expect_tx(&res_full[slot], kChunkBytes);
-            tma_load_4d(&map_res, &res_full[slot], res_ring + slot * kChunkBytes, t.col0 + ((item + 2) % chunks) * 64, t.x0,
-                        t.y0, t.n0);
-          }
-        }
-        ++item;
+      // Makes the next residual item readable; returns this row's 128-byte slot of it.
+      auto res_acquire = [&]() -> const uint8_t* {
+        res_topup();
+        mbar_wait(&res_full[res_q & rmask], (res_q >> rshift) & 1u);
+        return res_ring + (res_q & rmask) * kChunkBytes + row * 128;
       };
-
-      // ---- pass: pixel-norm statistic of the residual row (VB_RES_PIXNORM)
-      float res_inv = 1.0f;
-      if (p.res_mode == VB_RES_PIXNORM) {
-        float ss = 0.f;
-        for (int c = 0; c < chunks; ++c) {
-          const uint8_t* rrow = res_acquire(c);
-          ss += res_sumsq64(rrow, row);
-          res_release(false);
-        }
-        res_inv = 1.0f / (1e-4f + sqrtf(ss) * p.inv_sqrt_c);
-      }
-
-      mbar_wait(&tmem_full[buf], bphase);
-      tc_fence_after();
-
-      // ---- pass: pixel-norm statistic of the result row (VB_OUT_NORM*)
-      float inv_v = 1.0f;
-      if (needs_norm) {
-        float ss = 0.f;
-        for (int c = 0; c < chunks; ++c) {
-          const uint8_t* rrow = res_acquire(c);
-#pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
-            float v[32];
-            compute_v32(p, taddr + c * 64 + half * 32, t.col0 + c * 64 + half * 32, n, valid, rrow, row, half, res_inv, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) ss += v[j] * v[j];
-          }
-          res_release(false);
-        }
-        inv_v = 1.0f / (1e-4f + sqrtf(ss) * p.inv_sqrt_c);
-      }
-
-      // ---- pass: outputs -> staging ring -> TMA stores
-      for (int c = 0; c < chunks; ++c) {
-        const uint8_t* rrow = res_acquire(c);
-        // the staging entry about to be overwritten must have been read out by its TMA store
-        if (stg_chunks >= static_cast<uint32_t>(p.stage_depth)) {
-          if (leader) {
-            if (p.stage_depth == 2)
-              bulk_wait_read<1>();
-            else
-              bulk_wait_read<0>();
-          }
-          named_bar_sync(kEpiBarrier, kEpiThreads);
-        }
-        uint8_t* stg = stg_ring + (stg_chunks % p.stage_depth) * p.nslots * kChunkBytes;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          float v[32];
-          compute_v32(p, taddr + c * 64 + half * 32, t.col0 + c * 64 + half * 32, n, valid, rrow, row, half, res_inv, v);
-          if (p.out_f32 != nullptr && valid) {
-            float4* o = reinterpret_cast<float4*>(p.out_f32 + pix * p.ld_f32 + t.col0 + c * 64 + half * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          for (int s = 0; s < p.nslots; ++s)
-            stage_out32(p.out_kind[s], p.out_scale[s], inv_v, v, stg + s * kChunkBytes + row * 128, row, half);
-        }
-        if (c == chunks - 1) {
-          tc_fence_before();
-          mbar_arrive(&tmem_empty[buf]);      // accumulator fully consumed: MMA may start the tile after next
-        }
-        fence_proxy_async();                  // generic-proxy smem writes -> visible to the TMA engine
+      auto res_release = [&]() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&res_empty[res_q & rmask]);
+        ++res_q;
+      };
+      // Region of the staging ring the next group of sub-tiles goes to.  Its previous contents (group - 2) were read
+      // out by their TMA stores before the barrier of group - 1 (the leader waits for that just before arriving).
+      auto stg_region = [&]() -> uint8_t* { return stg_ring + (groups & 1u) * p.gslots * kChunkBytes; };
+      // All 256 threads wrote their part of the region: publish it to the async proxy and let the leader store it.
+      auto stg_commit = [&](const TileCoord& t, int c, bool norm_pass) {
+        fence_proxy_async();
+        if (leader) bulk_wait_read<0>();
         named_bar_sync(kEpiBarrier, kEpiThreads);
-        if (leader) {
-          for (int s = 0; s < p.nslots; ++s)
-            tma_store_4d(&map_out.m[s], stg + s * kChunkBytes, t.col0 + c * 64, t.x0, t.y0, t.n0);
+        if (leader && !(p.dbg & 2)) {
+          const uint8_t* reg = stg_region();
+          int di = 0;
+          if (norm_pass ? kind_norm(k0) : kind_direct(k0)) tma_store_4d(&map_out.m[0], reg + (di++) * kChunkBytes, t.col0 + c * 64, t.x0, t.y0, t.n0);
+          if (norm_pass ? kind_norm(k1) : kind_direct(k1)) tma_store_4d(&map_out.m[1], reg + (di++) * kChunkBytes, t.col0 + c * 64, t.x0, t.y0, t.n0);
+          if (norm_pass ? kind_norm(k2) : kind_direct(k2)) tma_store_4d(&map_out.m[2], reg + (di++) * kChunkBytes, t.col0 + c * 64, t.x0, t.y0, t.n0);
           bulk_commit();
         }
-        res_release(true);
-        ++stg_chunks;
+        ++groups;
+      };
+
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t bphase = static_cast<uint32_t>(it >> 1) & 1u;
+        const TileCoord t = decode_tile(p, tile);
+        const int n = t.n0 + rn;
+        const bool valid = n < p.B;
+        const size_t pix = static_cast<size_t>(n) * p.H * p.W + (t.y0 + ry) * p.W + t.x0 + rx;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                               static_cast<uint32_t>(buf * kAccStride + half * 32);
+        if (!(p.dbg & 1)) res_topup();
+
+        if (p.dbg & 1) {
+          mbar_wait(&tmem_full[buf], bphase);
+          tc_fence_after();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+          continue;
+        }
+
+        // ---- pass R: pixel-norm statistic of the residual row (VB_RES_PIXNORM)
+        float res_scale = p.res_a;
+        if (res_mode == VB_RES_PIXNORM) {
+          float ss = 0.f;
+          for (int c = 0; c < chunks; ++c) {
+            const uint8_t* rrow = res_acquire();
+            ss += res_sumsq32(rrow, row, half);
+            res_release();
+          }
+          xchg[0][half][row] = ss;
+          named_bar_sync(kPairBarrier + quad, 64);
+          ss += xchg[0][half ^ 1][row];
+          res_scale = p.res_a / (1e-4f + sqrtf(ss) * p.inv_sqrt_c);
+        }
+
+        mbar_wait(&tmem_full[buf], bphase);
+        tc_fence_after();
+
+        // ---- pass M: accumulator -> modulation / mp_silu -> mp_sum with the residual -> clamp; RAW / SILU outputs leave
+        // now, the clamped value stays packed in registers for the pixel-norm outputs.
+        uint32_t keep[4][16];
+        float ssv = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < chunks) {
+            const uint8_t* rrow = has_res ? res_acquire() : nullptr;
+            float v[32];
+            tmem_ld32(taddr + c * 64, v);
+            tmem_ld_wait();
+            if (c == chunks - 1) {                  // accumulator fully read: the MMA warp may start the tile after next
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+            }
+            const int col = t.col0 + c * 64 + half * 32;
+            if (modsilu) {
+              const float4* m = reinterpret_cast<const float4*>(p.mod + static_cast<size_t>(valid ? n : 0) * p.mod_stride + col);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 mm = __ldg(m + j);
+                v[4 * j + 0] = mp_silu_fast(v[4 * j + 0] * mm.x);
+                v[4 * j + 1] = mp_silu_fast(v[4 * j + 1] * mm.y);
+                v[4 * j + 2] = mp_silu_fast(v[4 * j + 2] * mm.z);
+                v[4 * j + 3] = mp_silu_fast(v[4 * j + 3] * mm.w);
+              }
+            }
+            if (has_res) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 q = *reinterpret_cast<const uint4*>(rrow + swz(half * 4 + j, row));
+                const float2 a = unpack_op2(q.x), b = unpack_op2(q.y), cc = unpack_op2(q.z), d = unpack_op2(q.w);
+                v[8 * j + 0] = fmaf(a.x, res_scale, v[8 * j + 0] * p.res_b);
+                v[8 * j + 1] = fmaf(a.y, res_scale, v[8 * j + 1] * p.res_b);
+                v[8 * j + 2] = fmaf(b.x, res_scale, v[8 * j + 2] * p.res_b);
+                v[8 * j + 3] = fmaf(b.y, res_scale, v[8 * j + 3] * p.res_b);
+                v[8 * j + 4] = fmaf(cc.x, res_scale, v[8 * j + 4] * p.res_b);
+                v[8 * j + 5] = fmaf(cc.y, res_scale, v[8 * j + 5] * p.res_b);
+                v[8 * j + 6] = fmaf(d.x, res_scale, v[8 * j + 6] * p.res_b);
+                v[8 * j + 7] = fmaf(d.y, res_scale, v[8 * j + 7] * p.res_b);
+              }
+              res_release();
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -clampv), clampv);
+            if (needs_norm) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) ssv = fmaf(v[j], v[j], ssv);
+            }
+            if (p.out_f32 != nullptr && valid) {
+              float4* o = reinterpret_cast<float4*>(p.out_f32 + pix * p.ld_f32 + col);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            uint32_t r16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r16[j] = pack_op2_nosat(v[2 * j], v[2 * j + 1]);
+            if (needs_norm) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) keep[c][j] = r16[j];
+            }
+            if (any_direct) {
+              uint8_t* srow = stg_region() + row * 128;
+              auto put = [&](int kind, float scale) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint4 o;
+                  if (kind == VB_OUT_RAW) {
+                    o = make_uint4(r16[4 * j], r16[4 * j + 1], r16[4 * j + 2], r16[4 * j + 3]);
+                  } else {
+                    o.x = pack_sat2(mp_silu_fast(v[8 * j + 0] * scale), mp_silu_fast(v[8 * j + 1] * scale));
+                    o.y = pack_sat2(mp_silu_fast(v[8 * j + 2] * scale), mp_silu_fast(v[8 * j + 3] * scale));
+                    o.z = pack_sat2(mp_silu_fast(v[8 * j + 4] * scale), mp_silu_fast(v[8 * j + 5] * scale));
+                    o.w = pack_sat2(mp_silu_fast(v[8 * j + 6] * scale), mp_silu_fast(v[8 * j + 7] * scale));
+                  }
+                  *reinterpret_cast<uint4*>(srow + swz(half * 4 + j, row)) = o;
+                }
+                srow += kChunkBytes;
+              };
+              if (kind_direct(k0)) put(k0, p.out_scale[0]);
+              if (kind_direct(k1)) put(k1, p.out_scale[1]);
+              if (kind_direct(k2)) put(k2, p.out_scale[2]);
+              stg_commit(t, c, false);
+            }
+          }
+        }
+
+        // ---- pass N: pixel-norm outputs from the packed registers
+        if (needs_norm) {
+          xchg[1][half][row] = ssv;
+          named_bar_sync(kPairBarrier + quad, 64);
+          ssv += xchg[1][half ^ 1][row];
+          const float inv_v = 1.0f / (1e-4f + sqrtf(ssv) * p.inv_sqrt_c);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c < chunks) {
+              uint8_t* srow = stg_region() + row * 128;
+              auto putn = [&](int kind) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint32_t o[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 x = unpack_op2(keep[c][4 * j + e]);
+                    const float a = x.x * inv_v, b = x.y * inv_v;
+                    o[e] = kind == VB_OUT_NORM ? pack_sat2(a, b) : pack_sat2(mp_silu_fast(a), mp_silu_fast(b));
+                  }
+                  *reinterpret_cast<uint4*>(srow + swz(half * 4 + j, row)) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                srow += kChunkBytes;
+              };
+              if (kind_norm(k0)) putn(k0);
+              if (kind_norm(k1)) putn(k1);
+              if (kind_norm(k2)) putn(k2);
+              stg_commit(t, c, true);
+            }
+          }
+        }
       }
-      res_items += has_res && !p.res_resident ? items : 0;
-      ++res_tiles;
+      if (leader) bulk_wait_read<0>();          // staging smem must outlive the last TMA store's read
     }
-    if (leader) bulk_wait_read<0>();          // staging smem must outlive the last TMA store's read
   }
 
   tc_fence_before();
@@ -506,10 +695,55 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
 }  // namespace
 
+typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const OutMaps,
+                             const ConvKernelParams);
+
+struct Variant {
+  int staged, res, mod, k0, k1, k2;     // -1 = any (run-time switch inside the kernel)
+  ConvKernelFn fn;
+  bool attr_done;
+};
+#define VB_VARIANT(S, R, M, A, B, C) {S, R, M, A, B, C, conv_gemm_kernel<S, R, M, A, B, C>, false}
+// The epilogue combinations the plans emit (engine.py) get straight-line code; anything else runs the generic one.
+static Variant g_variants[] = {
+    VB_VARIANT(0, -1, -1, -1, -1, -1),                                   // QKVNORM / narrow fp32
+    VB_VARIANT(1, 0, 1, VB_OUT_RAW, 0, 0),                               // conv_res0: modulation + mp_silu
+    VB_VARIANT(1, 0, 0, VB_OUT_RAW, 0, 0),                               // conv_skip, first conv
+    VB_VARIANT(1, 0, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, 0),
+    VB_VARIANT(1, 0, 0, VB_OUT_RAW, VB_OUT_SILU, 0),
+    VB_VARIANT(1, 0, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, VB_OUT_SILU),
+    VB_VARIANT(1, 0, 0, VB_OUT_NORM, VB_OUT_NORM_SILU, 0),               // enc conv_skip + pixel-norm
+    VB_VARIANT(1, 1, 0, VB_OUT_RAW, 0, 0),                               // conv_res1 / attn_proj: mp_sum (+clip)
+    VB_VARIANT(1, 1, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, 0),
+    VB_VARIANT(1, 1, 0, VB_OUT_RAW, VB_OUT_SILU, 0),
+    VB_VARIANT(1, 1, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, VB_OUT_SILU),
+    VB_VARIANT(1, 1, 0, VB_OUT_RAW, VB_OUT_SILU, VB_OUT_SILU),
+    VB_VARIANT(1, 2, 0, VB_OUT_RAW, 0, 0),                               // ... with the residual pixel-norm recomputed
+    VB_VARIANT(1, 2, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, 0),
+    VB_VARIANT(1, 2, 0, VB_OUT_RAW, VB_OUT_SILU, 0),
+    VB_VARIANT(1, 2, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, VB_OUT_SILU),
+    VB_VARIANT(1, 2, 0, VB_OUT_RAW, VB_OUT_SILU, VB_OUT_SILU),
+    VB_VARIANT(1, -1, -1, -1, -1, -1),                                   // generic staged epilogue (must stay last)
+};
+#undef VB_VARIANT
+
+static Variant* find_variant(int staged, int res, int mod, const int* kinds) {
+  static const bool generic_only = getenv("VB_GENERIC_EPI") != nullptr;       // A/B testing
+  for (Variant& v : g_variants) {
+    if (v.staged != staged) continue;
+    if (!staged) return &v;
+    if (v.res < 0) return &v;
+    if (generic_only) continue;
+    if (v.res == res && v.mod == mod && v.k0 == kinds[0] && v.k1 == kinds[1] && v.k2 == kinds[2]) return &v;
+  }
+  return nullptr;
+}
+
 struct ConvLaunch {
   CUtensorMap map_a, map_a2, map_w, map_res;
   OutMaps map_out;
   ConvKernelParams p;
+  ConvKernelFn fn;
   int grid;
   int smem_bytes;
   double flops;
@@ -524,6 +758,53 @@ static int encode_act_map(CUtensorMap* map, const void* base, int C, int W, int 
                                static_cast<uint64_t>(C) * 2 * W * H};
   const uint32_t box[4] = {64, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bn)};
   return encode_tmap_16(map, base, 4, dims, strides, box);
+}
+
+// Choose the main-loop shared-memory layout inside `budget` bytes.  Returns false if not even the minimum fits
+// (or, with want_good, if only a shallow pipeline would fit — the caller then retries with a smaller epilogue ring).
+static bool plan_mainloop(ConvKernelParams& p, int budget, bool want_good) {
+  static const int forced = getenv("VB_TAP_MODE") ? atoi(getenv("VB_TAP_MODE")) : -1;    // -1 auto, 0 off (A/B testing)
+  p.tap_mode = 0;
+  const int kct = p.kc_a + p.kc_b;
+  if (p.taps == 9 && p.bn == 1 && forced != 0) {
+    const int mode = p.bh == 1 ? 1 : 2;
+    const int rows = mode == 1 ? p.bw + 2 : (p.bh + 2) * p.bw;
+    const int a_tx = rows * 128;
+    const int a_slot = (a_tx + 1023) / 1024 * 1024;
+    const int resident = 9 * kct * p.b_bytes;
+    bool ok = false;
+    if (p.n_tiles == 1 && resident <= 96 * 1024 && budget - resident >= 3 * a_slot) {
+      p.b_resident = 1;
+      p.a_slots = std::min(kMaxStages, (budget - resident) / a_slot);
+      p.b_slots = 0;
+      ok = true;
+    } else {
+      p.b_resident = 0;
+      for (int as = 4; as >= 2 && !ok; --as) {
+        const int bs = std::min(kMaxBSlots, (budget - as * a_slot) / p.b_bytes);
+        if (bs >= (as >= 3 ? 6 : 5)) {
+          p.a_slots = as;
+          p.b_slots = bs;
+          ok = as >= 3 || !want_good;
+        }
+      }
+    }
+    // mode 2 only pays when the haloed box is clearly smaller than three separate tap boxes and the pipeline stays deep
+    if (ok && (mode == 1 || forced == 2 || (p.bh >= 4 && p.block_n <= 128))) {
+      p.tap_mode = mode;
+      p.a_slot_bytes = a_slot;
+      p.a_tx_bytes = a_tx;
+      p.win_rows = mode == 1 ? 1 : p.bw;
+      p.b_off = p.a_slots * a_slot;
+      return true;
+    }
+    p.tap_mode = 0;
+    p.b_resident = 0;
+  }
+  const int stages = std::min(kMaxStages, budget / p.stage_bytes);
+  if (stages < 2 || (want_good && stages < 3)) return false;
+  p.num_stages = stages;
+  return true;
 }
 
 int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
@@ -573,8 +854,16 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
   const float inv = 1.0f / sqrtf((1.f - t) * (1.f - t) + t * t);
   p.res_a = (1.f - t) * inv;
   p.res_b = t * inv;
-  p.clip = d->clip;
+  // the clip of Block.forward (models.py:204-205) and the saturation of the 16-bit stream are one clamp
+#ifdef VB_OP_BF16
+  const float finite_max = 3.0e38f;
+#else
+  const float finite_max = 65504.f;
+#endif
+  p.clamp = (d->flags & VB_F_CLIP) ? std::min(d->clip, finite_max) : finite_max;
   p.inv_sqrt_c = 1.0f / sqrtf(static_cast<float>(d->cout_pad));
+  p.res_slots = 2;
+  p.dbg = getenv("VB_DBG") ? atoi(getenv("VB_DBG")) : 0;
 
   auto fail = [&](int code) {
     delete l;
@@ -588,24 +877,32 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
     }                                \
   } while (0)
 
-  int epi_bytes = 0;
+  int kinds[3] = {0, 0, 0};
+  bool staged = false;
   if (d->epi_mode == VB_EPI_PLAIN) {
     if (d->flags & VB_F_MODSILU) VB_REQUIRE_L(d->mod != nullptr && d->mod_stride % 4 == 0, "vb_conv: MODSILU needs mod (stride %% 4)");
     bool needs_norm = false;
+    int n_direct = 0, n_norm = 0;
     for (int s = 0; s < 3; ++s) {
       if (d->out[s] == nullptr || d->out_kind[s] == VB_OUT_NONE) continue;
       VB_REQUIRE_L(d->out_kind[s] >= VB_OUT_RAW && d->out_kind[s] <= VB_OUT_NORM_SILU, "vb_conv: bad out_kind[%d]", s);
       VB_REQUIRE_L(p.nslots == s, "vb_conv: output slots must be filled in order");
-      p.out_kind[p.nslots] = d->out_kind[s];
+      p.out_kind[p.nslots] = kinds[p.nslots] = d->out_kind[s];
       p.out_scale[p.nslots] = d->out_scale[s] != 0.f ? d->out_scale[s] : 1.0f;
-      needs_norm |= d->out_kind[s] >= VB_OUT_NORM;
+      if (d->out_kind[s] >= VB_OUT_NORM) {
+        needs_norm = true;
+        ++n_norm;
+      } else {
+        ++n_direct;
+      }
       ++p.nslots;
     }
+    staged = p.nslots > 0;
     p.res_mode = d->res_mode;
     VB_REQUIRE_L(d->res_mode >= VB_RES_NONE && d->res_mode <= VB_RES_PIXNORM, "vb_conv: bad res_mode");
     VB_REQUIRE_L((d->res_mode != VB_RES_NONE) == (d->res != nullptr), "vb_conv: res and res_mode must come together");
     VB_REQUIRE_L(p.nslots > 0 || d->out_f32 != nullptr, "vb_conv: no output tensor");
-    if (p.nslots > 0) {
+    if (staged) {
       VB_REQUIRE_L(d->block_n % 64 == 0, "vb_conv: staged 16-bit outputs need block_n %% 64 == 0 (got %d)", d->block_n);
       if (d->out_f32) VB_REQUIRE_L(d->ld_f32 % 4 == 0, "vb_conv: ld_f32 must keep 16-byte alignment");
     } else {
@@ -615,18 +912,20 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
     if (needs_norm || d->res_mode == VB_RES_PIXNORM)
       VB_REQUIRE_L(p.n_tiles == 1, "vb_conv: pixel-norm fusion needs the whole channel extent in one tile (cout_pad %d, block_n %d)",
                    d->cout_pad, d->block_n);
-    const int chunks = d->block_n / 64;
-    p.res_resident = chunks <= 2 ? 1 : 0;
-    if (p.nslots > 0) {
-      const int res_bytes = d->res_mode != VB_RES_NONE ? 2 * kChunkBytes : 0;
-      p.stage_depth = 2;
-      int stages = (kSmemMax - res_bytes - 2 * p.nslots * kChunkBytes) / p.stage_bytes;
-      if (stages < 3) {
-        p.stage_depth = 1;
-        stages = (kSmemMax - res_bytes - p.nslots * kChunkBytes) / p.stage_bytes;
+    if (staged) {
+      // Epilogue shared memory: residual ring + two staging regions of gslots sub-tiles.  A deep residual ring hides the
+      // L2 latency of the residual loads when the per-chunk work is short; it is the first thing to shrink.
+      p.gslots = std::max(n_direct, n_norm);
+      const int stg_bytes = 2 * p.gslots * kChunkBytes;
+      const bool has_res = d->res_mode != VB_RES_NONE;
+      p.res_slots = has_res ? 4 : 2;
+      if (!plan_mainloop(p, kSmemMax - (has_res ? p.res_slots * kChunkBytes : 0) - stg_bytes, /*want_good=*/true)) {
+        p.res_slots = 2;
+        VB_REQUIRE_L(plan_mainloop(p, kSmemMax - (has_res ? p.res_slots * kChunkBytes : 0) - stg_bytes, false),
+                     "vb_conv: shared memory budget exceeded");
       }
-      VB_REQUIRE_L(stages >= 2, "vb_conv: shared memory budget exceeded");
-      epi_bytes = res_bytes + p.stage_depth * p.nslots * kChunkBytes;
+    } else {
+      VB_REQUIRE_L(plan_mainloop(p, kSmemMax, false), "vb_conv: shared memory budget exceeded");
     }
   } else {
     VB_REQUIRE_L(d->head_dim == 64 || d->head_dim == 32, "vb_conv: head_dim must be 32 or 64");
@@ -647,18 +946,27 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
       p.part_off[j] = d->part_off[j];
     }
     p.norm_scale = 1.0f / sqrtf(static_cast<float>(d->head_dim));
+    VB_REQUIRE_L(plan_mainloop(p, kSmemMax, false), "vb_conv: shared memory budget exceeded");
   }
-  p.num_stages = std::max(2, std::min(kMaxStages, (kSmemMax - epi_bytes) / p.stage_bytes));
-  p.res_off = p.num_stages * p.stage_bytes;
-  p.stg_off = p.res_off + (p.res_mode != VB_RES_NONE ? 2 * kChunkBytes : 0);
+  const int main_bytes = p.tap_mode != 0 ? p.b_off + (p.b_resident ? 9 * (p.kc_a + p.kc_b) : p.b_slots) * p.b_bytes
+                                         : p.num_stages * p.stage_bytes;
+  p.res_off = main_bytes;
+  p.stg_off = p.res_off + (p.res_mode != VB_RES_NONE ? p.res_slots * kChunkBytes : 0);
+
+  Variant* var = find_variant(staged ? 1 : 0, p.res_mode, (d->flags & VB_F_MODSILU) ? 1 : 0, kinds);
+  VB_REQUIRE_L(var != nullptr, "vb_conv: no kernel variant");
+  l->fn = var->fn;
 
   // Tensor maps.  Activations / residual / outputs: {C, W, H, N} with a {64, bw, bh, bn} box;
   // weights: {K, cout_pad} with a {64, block_n} box.
-  int rc = encode_act_map(&l->map_a, d->x, d->cin_pad, d->W, d->H, d->B, p.bw, p.bh, p.bn);
+  // (tap modes: the operand box carries the halo — {bw+2, 1} or {bw, bh+2} — and serves three taps)
+  const int abw = p.tap_mode == 1 ? p.bw + 2 : p.bw;
+  const int abh = p.tap_mode == 2 ? p.bh + 2 : p.bh;
+  int rc = encode_act_map(&l->map_a, d->x, d->cin_pad, d->W, d->H, d->B, abw, abh, p.bn);
   if (rc != VB_OK) return fail(rc);
   l->map_a2 = l->map_a;
   if (d->cin2_pad > 0) {
-    rc = encode_act_map(&l->map_a2, d->x2, d->cin2_pad, d->W, d->H, d->B, p.bw, p.bh, p.bn);
+    rc = encode_act_map(&l->map_a2, d->x2, d->cin2_pad, d->W, d->H, d->B, abw, abh, p.bn);
     if (rc != VB_OK) return fail(rc);
   }
   l->map_res = l->map_a;
@@ -682,23 +990,22 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
 #undef VB_REQUIRE_L
 
   l->grid = std::min(p.total_tiles, num_sms());
-  l->smem_bytes = p.stg_off + p.stage_depth * p.nslots * kChunkBytes + 1024;
+  l->smem_bytes = p.stg_off + (staged ? 2 * p.gslots * kChunkBytes : 0) + 1024;
   l->flops = 2.0 * d->B * d->H * d->W * static_cast<double>(d->cout_pad) * d->taps * (d->cin_pad + d->cin2_pad);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax + 1024);
+  if (!var->attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax + 1024);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(conv_gemm_kernel) failed: %s", cudaGetErrorString(e));
       return fail(VB_ERR_CUDA);
     }
-    attr_done = true;
+    var->attr_done = true;
   }
   *out = l;
   return VB_OK;
 }
 
 int conv_launch(const ConvLaunch* l, cudaStream_t s) {
-  conv_gemm_kernel<<<l->grid, kThreads, l->smem_bytes, s>>>(l->map_a, l->map_a2, l->map_w, l->map_res, l->map_out, l->p);
+  l->fn<<<l->grid, kThreads, l->smem_bytes, s>>>(l->map_a, l->map_a2, l->map_w, l->map_res, l->map_out, l->p);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }

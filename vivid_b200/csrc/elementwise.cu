@@ -222,23 +222,38 @@ __global__ void __launch_bounds__(256) precond_in_kernel(const vb_precond_in_des
     const float sg = d.sigma[d.sigma_n == 1 ? 0 : n * d.sigma_stride];
     c_in = rsqrtf(d.sigma_data * d.sigma_data + sg * sg);
   }
-  float ch[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const float* xp = d.x + n * d.img_stride + s;
-  ch[0] = xp[0] * c_in;
-  ch[1] = xp[hw] * c_in;
-  ch[2] = xp[2 * hw] * c_in;
-  int k = 3;
-  if (d.cond != nullptr) {
-    const float* cp = d.cond + n * 3 * hw + s;
-    const float* np = d.noise ? d.noise + n * 3 * hw + s : nullptr;
-    for (int c = 0; c < 3; ++c) ch[3 + c] = cp[c * hw] + (np ? d.noisy_sr * np[c * hw] : 0.f);
-    k = 6;
+  const float* xp = d.x + n * d.img_stride;
+  const float* cp = d.cond ? d.cond + n * 3 * hw : nullptr;
+  const float* np = d.noise ? d.noise + n * 3 * hw : nullptr;
+  const int nch = cp ? 7 : 4;           // [x*c_in (3), cond + noisy_sr*noise (3, SR only), ones]
+  auto channel = [&](int c, long long at) -> float {
+    if (c < 3) return xp[c * hw + at] * c_in;
+    if (c == nch - 1) return 1.0f;     // bias-as-channel (training/models.py:394)
+    return cp[(c - 3) * hw + at] + (np ? d.noisy_sr * np[(c - 3) * hw + at] : 0.f);
+  };
+  op_t* o = static_cast<op_t*>(d.out) + pix * d.cpad;
+  if (!d.im2col) {
+    float ch[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < nch; ++c) ch[c] = channel(c, s);
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+    o4[0] = make_uint4(pack_op2(ch[0], ch[1]), pack_op2(ch[2], ch[3]), pack_op2(ch[4], ch[5]), pack_op2(ch[6], ch[7]));
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = 1; i < d.cpad / 8; ++i) o4[i] = z;
+    return;
   }
-  ch[k] = 1.0f;   // bias-as-channel (training/models.py:394)
-  uint4* o = reinterpret_cast<uint4*>(static_cast<op_t*>(d.out) + pix * d.cpad);
-  o[0] = make_uint4(pack_op2(ch[0], ch[1]), pack_op2(ch[2], ch[3]), pack_op2(ch[4], ch[5]), pack_op2(ch[6], ch[7]));
-  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = 1; i < d.cpad / 8; ++i) o[i] = z;
+  // im2col: channel ci*9 + tap holds input channel ci at the tap's neighbour (zero outside the image, as conv padding does)
+  const int y = static_cast<int>(s / d.R), x = static_cast<int>(s - static_cast<long long>(y) * d.R);
+  for (int base = 0; base < d.cpad; base += 8) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = base + e;
+      const int ci = k / 9, tap = k - ci * 9;
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      v[e] = (ci < nch && yy >= 0 && yy < d.R && xx >= 0 && xx < d.R) ? channel(ci, static_cast<long long>(yy) * d.R + xx) : 0.f;
+    }
+    *reinterpret_cast<uint4*>(o + base) = make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));
+  }
 }
 
 __global__ void __launch_bounds__(256) precond_out_kernel(const vb_precond_out_desc d) {
@@ -384,6 +399,7 @@ int embed_launch(const vb_emb_desc* d, cudaStream_t s) {
 int precond_in_launch(const vb_precond_in_desc* d, cudaStream_t s) {
   VB_REQUIRE(d != nullptr && d->x && d->out, "vb_precond_in: null tensor");
   VB_REQUIRE(d->B > 0 && d->R > 0 && d->cpad >= 8 && d->cpad % 8 == 0, "vb_precond_in: bad extent");
+  VB_REQUIRE(!d->im2col || d->cpad >= 9 * (d->cond ? 7 : 4), "vb_precond_in: im2col needs cpad >= 9 * channels");
   const long long pixels = static_cast<long long>(d->B) * d->R * d->R;
   precond_in_kernel<<<static_cast<unsigned>((pixels + 255) / 256), 256, 0, s>>>(*d);
   VB_CHECK_CUDA(cudaGetLastError());

@@ -244,7 +244,7 @@ class Plan:
 
     def run_unet(self, unet, x_in, B, mod, offs, mod_total, features=None, feat_seg=1, zero_feature_keys=False,
                  collect_features=False):
-        """Emit the ops of UNet.forward.  x_in: 16-bit NHWC [B,R,R,64] (image + ones, zero padded).
+        """Emit the ops of UNet.forward.  x_in: 16-bit NHWC [B,R,R,64] (im2col of image + ones channels, zero padded).
         features: list of Act consumed by cross-attention blocks in order.
         Returns (raw network output fp32 [P,16] or None, collected feature Acts)."""
         specs = unet.enc_specs + unet.dec_specs
@@ -304,8 +304,9 @@ class Plan:
             temps, popped_skip = [], None
 
             if s.kind == "conv":
-                w = self.prep_weight(mod_.weight)
-                self.conv(x_in, w, B, R, 64, Cc, 9, outs=alloc_outs(out, want(i)), k_real=9 * s.cin)
+                # x_in holds the im2col'd 3x3 neighbourhood (vb_precond_in, im2col=1): the first conv is a K=64 1x1 GEMM
+                w = self.prep_weight(mod_.weight.detach().reshape(Cc, s.cin * 9, 1, 1))
+                self.conv(x_in, w, B, R, 64, Cc, 1, outs=alloc_outs(out, want(i)), k_real=9 * s.cin)
                 cur = out
                 skips.append(out)
                 continue
@@ -446,7 +447,7 @@ class Plan:
             enc = net.encoder
             src16 = self.buf((Bx * R * R, 64), self.op_dtype)
             d = L.PrecondInDesc(x=self.in_src.data_ptr(), cond=None, noise=None, sigma=None, out=src16.data_ptr(), B=Bx,
-                                R=R, cpad=64, sigma_n=1, sigma_stride=0, img_stride=3 * R * R, sigma_data=sd, noisy_sr=0.0)
+                                R=R, cpad=64, sigma_n=1, sigma_stride=0, im2col=1, img_stride=3 * R * R, sigma_data=sd, noisy_sr=0.0)
             L.check(self.lib.vb_plan_add_precond_in(self.handle, C.byref(d)), "vb_plan_add_precond_in")
             self.op_info.append(("precond", "in", 0.0, d.B * R * R * (12.0 + 128.0)))
             mod, offs, total = self.embed(enc, Bx, self.in_sigma, 1, self.in_geom if ldim_enc else None, Bx, ldim_enc,
@@ -459,7 +460,7 @@ class Plan:
         step = 2 if self.dual else 1
         d = L.PrecondInDesc(x=self.in_x.data_ptr(), cond=L.ptr(self.in_cond), noise=L.ptr(self.in_noise),
                             sigma=self.in_sigma.data_ptr(), out=x16.data_ptr(), B=B, R=R, cpad=64, sigma_n=B,
-                            sigma_stride=step, img_stride=3 * R * R * step, sigma_data=sd,
+                            sigma_stride=step, im2col=1, img_stride=3 * R * R * step, sigma_data=sd,
                             noisy_sr=float(net.noisy_sr if net.noisy_sr is not None else 0.0))
         L.check(self.lib.vb_plan_add_precond_in(self.handle, C.byref(d)), "vb_plan_add_precond_in")
         self.op_info.append(("precond", "in", 0.0, d.B * R * R * (12.0 + 128.0)))
