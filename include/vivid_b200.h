@@ -124,6 +124,10 @@ typedef struct vb_conv_desc {
   float res_t, clip;
 } vb_conv_desc;
 int vb_conv(const vb_conv_desc* d, void* stream);
+/* Diagnostics (micro-benchmarks only): with the environment variable VB_DBG & 16 set when an op is prepared, the conv
+ * kernel records the longest CTA lifetime in SM cycles; this call synchronises, returns the maximum since the last
+ * call (HOST pointer) and resets it. */
+int vb_debug_conv_cycles(unsigned long long* out);
 
 /* ------------------------------------------------------------------------
  * Fused cosine attention — replaces einsum/softmax/einsum (snapshot

@@ -66,8 +66,12 @@ for idx, (R, cin, cout, taps, bn) in enumerate(SHAPES):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
+        cyc = C.c_ulonglong(0)
+        if int(os.environ.get("VB_DBG", "0")) & 16:
+            L.check(lib.vb_debug_conv_cycles(C.byref(cyc)), "cycles")
         fl = 2.0 * B * R * R * cout * cin * taps
         by = 2.0 * B * R * R * (cin + cout * (len(kinds) + (d.res_mode != 0)))
         print(f"[{idx}] {R}x{R} cin{cin} cout{cout} taps{taps} bn{bn} B{B} {epi:6s}: {ms*1e3:8.1f} us  "
-              f"{fl/ms/1e9:7.1f} TFLOP/s  {by/ms/1e6:6.0f} GB/s", flush=True)
+              f"{fl/ms/1e9:7.1f} TFLOP/s  {by/ms/1e6:6.0f} GB/s" +
+              (f"  {cyc.value} cyc -> {cyc.value/ms/1e3:.0f} MHz" if cyc.value else ""), flush=True)
         lib.vb_plan_destroy(plan)

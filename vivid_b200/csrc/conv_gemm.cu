@@ -54,11 +54,15 @@ constexpr int kMaxResSlots = 4;                       // residual TMA ring depth
 constexpr int kEpiBarrier = 1;                        // named barrier of all epilogue warps
 constexpr int kPairBarrier = 2;                       // +quadrant: the two warps sharing a TMEM lane quadrant
 
+// VB_DBG & 16: longest CTA lifetime (SM cycles) of the launches since the last vb_debug_conv_cycles() call.
+__device__ unsigned long long g_conv_cycles;
+
 struct ConvKernelParams {
   int B, H, W;
   int bw, bh, bn;
   int tiles_x, tiles_y;
   int n_tiles, total_tiles;
+  int pair, total_q;    // CTA-pair mode (cluster of 2, cta_group::2 MMA); work items per CTA / per pair
   int taps, kc_a, kc_b;
   int block_n;
   int num_stages, stage_bytes, b_bytes;
@@ -79,6 +83,7 @@ struct ConvKernelParams {
   int out_kind[3];
   float out_scale[3];
   int gslots;           // sub-tiles per staging region (a region = the outputs of one chunk in one pass)
+  int stg_regions;      // staging regions in the ring (3: the store of the previous region may still be reading; 2: it may not)
   int res_off, stg_off; // byte offsets of the residual ring / staging ring inside dynamic smem
   float* out_f32;
   int ld_f32;
@@ -91,7 +96,8 @@ struct ConvKernelParams {
   int part_seq[3];
   int part_off[3];
   float norm_scale;   // 1/sqrt(head_dim)
-  int dbg;            // ablation switches for micro-benchmarks (VB_DBG): 1 = epilogue does no work, 2 = no TMA stores
+  int dbg;            // ablation switches for micro-benchmarks (VB_DBG): 1 = epilogue does no work, 2 = no TMA stores,
+                      // 16 = record CTA lifetimes
 };
 
 struct TileCoord {
@@ -190,6 +196,126 @@ __device__ __forceinline__ void epi_f32_16(const ConvKernelParams& p, uint32_t t
   for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
+// Linear tile index (M tile major over N tiles) of work item q for CTA `rank`.  Single CTA: q itself.  CTA pair: the
+// pair takes M tiles 2m and 2m+1 of one N tile; an odd tail decodes to an image index >= B, where TMA zero-fills the
+// loads and drops the stores.
+__device__ __forceinline__ int tile_of(const ConvKernelParams& p, int q, uint32_t rank) {
+  if (!p.pair) return q;
+  const int mq = q / p.n_tiles;
+  return (2 * mq + static_cast<int>(rank)) * p.n_tiles + (q - mq * p.n_tiles);
+}
+
+// The single MMA-issuing thread.  Its instruction stream is co-critical for narrow tiles (an N=64 MMA retires in 48
+// cycles), so descriptors advance by adds on the low word and nothing is re-derived inside the K loop.
+template <bool PAIR>
+__device__ __forceinline__ void mma_role(const ConvKernelParams& p, uint8_t* smem, uint32_t tmem_base, int q0, int qstride,
+                                         uint64_t* full_bar, uint64_t* empty_bar, uint64_t* bfull_bar, uint64_t* bempty_bar,
+                                         uint64_t* tmem_full, uint64_t* tmem_empty) {
+  auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+    if (PAIR) umma_f16_ss_pair(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), p.idesc, acc);
+    else umma_f16_ss(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), p.idesc, acc);
+  };
+  auto commit = [&](uint64_t* bar) {
+    if (PAIR) umma_commit_pair(bar); else umma_commit(bar);
+  };
+  const int kct = p.kc_a + p.kc_b;
+  const uint32_t b_tile_lo = static_cast<uint32_t>(p.b_bytes) >> 4;
+  int it = 0;
+  if (p.tap_mode != 0) {
+    const uint32_t a_base = umma_desc_lo(smem_u32(smem));
+    const uint32_t a_slot_lo = static_cast<uint32_t>(p.a_slot_bytes) >> 4;
+    const uint32_t win_lo = static_cast<uint32_t>(p.win_rows) * 8u;          // rows of 128 B
+    const uint32_t b_base = umma_desc_lo(smem_u32(smem + p.b_off));
+    // resident weights: tile index of (g, i, kc) is (tap * kct + kc) with tap = 3g+i (mode 1) or 3i+g (mode 2)
+    const uint32_t b_g_lo = static_cast<uint32_t>(p.tap_mode == 1 ? 3 * kct : kct) * b_tile_lo;
+    const uint32_t b_i_lo = static_cast<uint32_t>(p.tap_mode == 1 ? kct : 3 * kct) * b_tile_lo;
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    if (p.b_resident) {
+      mbar_wait(&bfull_bar[0], 0);
+      tc_fence_after();
+    }
+    for (int q = q0; q < p.total_q; q += qstride, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&tmem_empty[buf], (static_cast<uint32_t>(it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
+      uint32_t accumulate = 0;
+      for (int g = 0; g < 3; ++g) {
+        uint32_t b_gk = b_base + static_cast<uint32_t>(g) * b_g_lo;
+        for (int kc = 0; kc < kct; ++kc, b_gk += b_tile_lo) {
+          mbar_wait(&full_bar[as], aph);
+          tc_fence_after();
+          const uint32_t a_lo = a_base + static_cast<uint32_t>(as) * a_slot_lo;
+          if (p.b_resident) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                mma(d_tmem, a_lo + i * win_lo + 2 * k, b_gk + i * b_i_lo + 2 * k, accumulate);
+                accumulate = 1;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              mbar_wait(&bfull_bar[bs], bph);
+              tc_fence_after();
+              const uint32_t b_lo = b_base + static_cast<uint32_t>(bs) * b_tile_lo;
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                mma(d_tmem, a_lo + i * win_lo + 2 * k, b_lo + 2 * k, accumulate);
+                accumulate = 1;
+              }
+              commit(&bempty_bar[bs]);
+              if (++bs == p.b_slots) {
+                bs = 0;
+                bph ^= 1u;
+              }
+            }
+          }
+          commit(&empty_bar[as]);
+          if (++as == p.a_slots) {
+            as = 0;
+            aph ^= 1u;
+          }
+        }
+      }
+      commit(&tmem_full[buf]);
+    }
+  } else {
+    const uint32_t s_base = umma_desc_lo(smem_u32(smem));
+    const uint32_t stage_lo = static_cast<uint32_t>(p.stage_bytes) >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    const int k_blocks = p.taps * kct;
+    for (int q = q0; q < p.total_q; q += qstride, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&tmem_empty[buf], (static_cast<uint32_t>(it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
+      uint32_t accumulate = 0;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_lo = s_base + static_cast<uint32_t>(stage) * stage_lo;
+        const uint32_t b_lo = a_lo + (kAStageBytes >> 4);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          mma(d_tmem, a_lo + 2 * k, b_lo + 2 * k, accumulate);
+          accumulate = 1;
+        }
+        commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+        if (++stage == p.num_stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      commit(&tmem_full[buf]);       // accumulator complete -> epilogue
+    }
+  }
+}
+
 struct OutMaps {
   CUtensorMap m[3];
 };
@@ -220,6 +346,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const long long t_start = (p.dbg & 16) ? clock64() : 0;
+  // CTA pair (p.pair): the two CTAs of a cluster work on two adjacent 128-pixel tiles of the same output-channel tile.
+  // Each loads its own activation operand and HALF of the weight tile; the leader (rank 0) issues one M=256
+  // cta_group::2 MMA for both, so every CTA reads (128 + block_n/2) operand rows per K step from its shared memory
+  // instead of (128 + block_n) — the SS-mode MMA is shared-memory-bandwidth bound below N=256 (tools/exp/umma_rate.cu).
+  const uint32_t rank = p.pair ? cluster_ctarank() : 0u;
+  const int q0 = p.pair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int qstride = p.pair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -239,7 +373,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], kEpiWarps);
+      mbar_init(&tmem_empty[b], p.pair ? 2 * kEpiWarps : kEpiWarps);   // pair: the epilogue warps of both CTAs
     }
     for (int b = 0; b < kMaxResSlots; ++b) {
       mbar_init(&res_full[b], 1);
@@ -248,175 +382,116 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(&tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (p.pair) {
+      tmem_alloc_pair(&tmem_slot, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(&tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (p.pair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    const bool elected = elect_one_sync();
-    if (elected && p.tap_mode != 0) {
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
+    if (elect_one_sync()) {
+      // pair: both CTAs complete their bytes on the LEADER's full barriers, which the leader arms for both halves
+      const uint32_t full0 = p.pair ? mapa_u32(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
+      const uint32_t bfull0 = p.pair ? mapa_u32(smem_u32(&bfull_bar[0]), 0) : smem_u32(&bfull_bar[0]);
+      const uint32_t txmul = p.pair ? 2u : 1u;
+      const int wrow = p.pair ? static_cast<int>(rank) * (p.block_n >> 1) : 0;    // this CTA's rows of the weight tile
+      auto load_a = [&](const CUtensorMap* m, uint32_t bar, void* dst, int c0, int c1, int c2, int c3) {
+        if (p.pair) tma_load_4d_pair(m, bar, dst, c0, c1, c2, c3);
+        else asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                          ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+      };
+      auto load_w = [&](uint32_t bar, void* dst, int c0, int c1) {
+        if (p.pair) tma_load_2d_pair(&map_w, bar, dst, c0, c1);
+        else asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                          ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(&map_w)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+      };
       const int kct = p.kc_a + p.kc_b;
-      if (p.b_resident) {
-        // every tap tile of this layer's weights, once (n_tiles == 1)
-        const int nb = 9 * kct;
-        mbar_expect_tx(&bfull_bar[0], static_cast<uint32_t>(nb) * p.b_bytes);
-        for (int i = 0; i < nb; ++i) tma_load_2d(&map_w, &bfull_bar[0], smem + p.b_off + i * p.b_bytes, i * kBlockK, 0);
-      }
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        for (int g = 0; g < 3; ++g) {
-          for (int kc = 0; kc < kct; ++kc) {
-            mbar_wait(&empty_bar[as], aph ^ 1u);
-            uint8_t* sa = smem + as * p.a_slot_bytes;
-            mbar_expect_tx(&full_bar[as], p.a_tx_bytes);
-            const int cx = p.tap_mode == 1 ? t.x0 - 1 : t.x0 + g - 1;
-            const int cy = p.tap_mode == 1 ? t.y0 + g - 1 : t.y0 - 1;
-            if (kc < p.kc_a)
-              tma_load_4d(&map_a, &full_bar[as], sa, kc * kBlockK, cx, cy, t.n0);
-            else
-              tma_load_4d(&map_a2, &full_bar[as], sa, (kc - p.kc_a) * kBlockK, cx, cy, t.n0);
-            if (++as == p.a_slots) {
-              as = 0;
-              aph ^= 1u;
-            }
-            if (!p.b_resident) {
-              for (int i = 0; i < 3; ++i) {
-                const int tap = p.tap_mode == 1 ? g * 3 + i : i * 3 + g;
-                mbar_wait(&bempty_bar[bs], bph ^ 1u);
-                mbar_expect_tx(&bfull_bar[bs], p.b_bytes);
-                tma_load_2d(&map_w, &bfull_bar[bs], smem + p.b_off + bs * p.b_bytes, (tap * kct + kc) * kBlockK, t.col0);
-                if (++bs == p.b_slots) {
-                  bs = 0;
-                  bph ^= 1u;
+      if (p.tap_mode != 0) {
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0;
+        if (p.b_resident) {
+          // every tap tile of this layer's weights, once (n_tiles == 1)
+          const int nb = 9 * kct;
+          if (rank == 0) mbar_expect_tx(&bfull_bar[0], static_cast<uint32_t>(nb) * p.b_bytes * txmul);
+          for (int i = 0; i < nb; ++i) load_w(bfull0, smem + p.b_off + i * p.b_bytes, i * kBlockK, wrow);
+        }
+        for (int q = q0; q < p.total_q; q += qstride) {
+          const TileCoord t = decode_tile(p, tile_of(p, q, rank));
+          for (int g = 0; g < 3; ++g) {
+            for (int kc = 0; kc < kct; ++kc) {
+              mbar_wait(&empty_bar[as], aph ^ 1u);
+              uint8_t* sa = smem + as * p.a_slot_bytes;
+              if (rank == 0) mbar_expect_tx(&full_bar[as], p.a_tx_bytes * txmul);
+              const int cx = p.tap_mode == 1 ? t.x0 - 1 : t.x0 + g - 1;
+              const int cy = p.tap_mode == 1 ? t.y0 + g - 1 : t.y0 - 1;
+              if (kc < p.kc_a)
+                load_a(&map_a, full0 + as * 8, sa, kc * kBlockK, cx, cy, t.n0);
+              else
+                load_a(&map_a2, full0 + as * 8, sa, (kc - p.kc_a) * kBlockK, cx, cy, t.n0);
+              if (++as == p.a_slots) {
+                as = 0;
+                aph ^= 1u;
+              }
+              if (!p.b_resident) {
+                for (int i = 0; i < 3; ++i) {
+                  const int tap = p.tap_mode == 1 ? g * 3 + i : i * 3 + g;
+                  mbar_wait(&bempty_bar[bs], bph ^ 1u);
+                  if (rank == 0) mbar_expect_tx(&bfull_bar[bs], p.b_bytes * txmul);
+                  load_w(bfull0 + bs * 8, smem + p.b_off + bs * p.b_bytes, (tap * kct + kc) * kBlockK, t.col0 + wrow);
+                  if (++bs == p.b_slots) {
+                    bs = 0;
+                    bph ^= 1u;
+                  }
                 }
               }
             }
           }
         }
-      }
-    } else if (elected) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx_bytes = kAStageBytes + p.b_bytes;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        int kcol = 0;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
-          const int dx = p.taps == 9 ? tap % 3 - 1 : 0;
-          for (int kc = 0; kc < p.kc_a + p.kc_b; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            uint8_t* sa = smem + stage * p.stage_bytes;
-            uint8_t* sb = sa + kAStageBytes;
-            mbar_expect_tx(&full_bar[stage], tx_bytes);
-            if (kc < p.kc_a)
-              tma_load_4d(&map_a, &full_bar[stage], sa, kc * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
-            else
-              tma_load_4d(&map_a2, &full_bar[stage], sa, (kc - p.kc_a) * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
-            tma_load_2d(&map_w, &full_bar[stage], sb, kcol, t.col0);
-            kcol += kBlockK;
-            if (++stage == p.num_stages) {
-              stage = 0;
-              phase ^= 1u;
+      } else {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx_bytes = (kAStageBytes + p.b_bytes) * txmul;
+        for (int q = q0; q < p.total_q; q += qstride) {
+          const TileCoord t = decode_tile(p, tile_of(p, q, rank));
+          int kcol = 0;
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
+            const int dx = p.taps == 9 ? tap % 3 - 1 : 0;
+            for (int kc = 0; kc < kct; ++kc) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              uint8_t* sa = smem + stage * p.stage_bytes;
+              uint8_t* sb = sa + kAStageBytes;
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
+              if (kc < p.kc_a)
+                load_a(&map_a, full0 + stage * 8, sa, kc * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
+              else
+                load_a(&map_a2, full0 + stage * 8, sa, (kc - p.kc_a) * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
+              load_w(full0 + stage * 8, sb, kcol, t.col0 + wrow);
+              kcol += kBlockK;
+              if (++stage == p.num_stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    const bool elected = elect_one_sync();
-    if (elected && p.tap_mode != 0) {
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      int it = 0;
-      const int kct = p.kc_a + p.kc_b;
-      if (p.b_resident) {
-        mbar_wait(&bfull_bar[0], 0);
-        tc_fence_after();
-      }
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t bphase = static_cast<uint32_t>(it >> 1) & 1u;
-        mbar_wait(&tmem_empty[buf], bphase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
-        uint32_t accumulate = 0;
-        for (int g = 0; g < 3; ++g) {
-          for (int kc = 0; kc < kct; ++kc) {
-            mbar_wait(&full_bar[as], aph);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + as * p.a_slot_bytes);
-            for (int i = 0; i < 3; ++i) {
-              uint32_t sb;
-              if (p.b_resident) {
-                const int tap = p.tap_mode == 1 ? g * 3 + i : i * 3 + g;
-                sb = smem_u32(smem + p.b_off + (tap * kct + kc) * p.b_bytes);
-              } else {
-                mbar_wait(&bfull_bar[bs], bph);
-                tc_fence_after();
-                sb = smem_u32(smem + p.b_off + bs * p.b_bytes);
-              }
-              const uint32_t wa = sa + static_cast<uint32_t>(i * p.win_rows) * 128u;
-#pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k) {
-                umma_f16_ss(d_tmem, umma_desc_sw128(wa + k * 32), umma_desc_sw128(sb + k * 32), p.idesc, accumulate);
-                accumulate = 1;
-              }
-              if (!p.b_resident) {
-                umma_commit(&bempty_bar[bs]);
-                if (++bs == p.b_slots) {
-                  bs = 0;
-                  bph ^= 1u;
-                }
-              }
-            }
-            umma_commit(&empty_bar[as]);
-            if (++as == p.a_slots) {
-              as = 0;
-              aph ^= 1u;
-            }
-          }
-        }
-        umma_commit(&tmem_full[buf]);
-      }
-    } else if (elected) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      const int k_blocks = p.taps * (p.kc_a + p.kc_b);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t bphase = static_cast<uint32_t>(it >> 1) & 1u;
-        mbar_wait(&tmem_empty[buf], bphase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
-          const uint32_t sb = sa + kAStageBytes;
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t adesc = umma_desc_sw128(sa + k * 32);
-            const uint64_t bdesc = umma_desc_sw128(sb + k * 32);
-            umma_f16_ss(d_tmem, adesc, bdesc, p.idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
-          if (++stage == p.num_stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
-        umma_commit(&tmem_full[buf]);       // accumulator complete -> epilogue
-      }
+    // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
+    if (elect_one_sync() && rank == 0) {
+      if (p.pair)
+        mma_role<true>(p, smem, tmem_base, q0, qstride, full_bar, empty_bar, bfull_bar, bempty_bar, tmem_full, tmem_empty);
+      else
+        mma_role<false>(p, smem, tmem_base, q0, qstride, full_bar, empty_bar, bfull_bar, bempty_bar, tmem_full, tmem_empty);
     }
   } else if (warp >= kFirstEpiWarp) {
     // ------------------------------------------------------------------ epilogue
@@ -429,12 +504,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int ry = r2 % p.bh;
     const int rn = r2 / p.bh;
     int it = 0;
+    // accumulator buffer drained: tell the MMA issuer (pair: the leader CTA's barrier counts the warps of both CTAs)
+    const uint32_t tmem_empty_leader = p.pair ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
+    auto acc_release = [&](int buf) {
+      if (p.pair) mbar_arrive_cluster_addr(tmem_empty_leader + buf * 8);
+      else mbar_arrive(&tmem_empty[buf]);
+    };
 
     if (!STAGED) {
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int q = q0; q < p.total_q; q += qstride, ++it) {
         const int buf = it & 1;
         const uint32_t bphase = static_cast<uint32_t>(it >> 1) & 1u;
-        const TileCoord t = decode_tile(p, tile);
+        const TileCoord t = decode_tile(p, tile_of(p, q, rank));
         const int n = t.n0 + rn;
         const bool valid = n < p.B;
         const int s_img = (t.y0 + ry) * p.W + t.x0 + rx;
@@ -453,7 +534,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        if (lane == 0) acc_release(buf);
       }
     } else {
       const int res_mode = RES_T >= 0 ? RES_T : p.res_mode;
@@ -472,7 +553,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int items = chunks * (res_mode == VB_RES_PIXNORM ? 2 : 1);   // residual (pass, chunk) items per tile
       uint32_t res_q = 0;          // residual items consumed so far by this thread (ring position / phase)
       uint32_t res_issued = 0;     // residual items whose TMA load has been issued (leader only)
-      uint32_t groups = 0;         // staging regions produced so far (ring position)
+      uint32_t greg = 0;           // staging region the next group of sub-tiles goes to (ring position)
       const float clampv = p.clamp;
 
       // The leader keeps the residual ring full ACROSS tile boundaries: the next tile's residual is in flight while
@@ -481,9 +562,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (has_res && leader) {
           while (res_issued < res_q + static_cast<uint32_t>(p.res_slots)) {
             const uint32_t ti = res_issued / items;                  // CTA-local index of the tile owning the item
-            const int tl = blockIdx.x + static_cast<int>(ti) * gridDim.x;
-            if (tl >= p.total_tiles) break;
-            const TileCoord tt = decode_tile(p, tl);
+            const int ql = q0 + static_cast<int>(ti) * qstride;
+            if (ql >= p.total_q) break;
+            const TileCoord tt = decode_tile(p, tile_of(p, ql, rank));
             const uint32_t slot = res_issued & rmask;
             mbar_wait(&res_empty[slot], ((res_issued >> rshift) & 1u) ^ 1u);
             mbar_expect_tx(&res_full[slot], kChunkBytes);
@@ -504,13 +585,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (lane == 0) mbar_arrive(&res_empty[res_q & rmask]);
         ++res_q;
       };
-      // Region of the staging ring the next group of sub-tiles goes to.  Its previous contents (group - 2) were read
-      // out by their TMA stores before the barrier of group - 1 (the leader waits for that just before arriving).
-      auto stg_region = [&]() -> uint8_t* { return stg_ring + (groups & 1u) * p.gslots * kChunkBytes; };
+      // Region of the staging ring the next group of sub-tiles goes to.  With three regions the leader only has to know
+      // that the store issued TWO groups ago has finished reading its region (the one the next group will overwrite)
+      // before it lets everybody past the barrier — the most recent store stays in flight.  (With a two-region ring and
+      // a wait for ALL stores, 14 % of the kernel's stall samples sat on this barrier: profiles/r01_conv_stage_ring.txt.)
+      auto stg_region = [&]() -> uint8_t* { return stg_ring + greg * p.gslots * kChunkBytes; };
       // All 256 threads wrote their part of the region: publish it to the async proxy and let the leader store it.
       auto stg_commit = [&](const TileCoord& t, int c, bool norm_pass) {
         fence_proxy_async();
-        if (leader) bulk_wait_read<0>();
+        if (leader) {
+          if (p.stg_regions == 3) bulk_wait_read<1>(); else bulk_wait_read<0>();
+        }
         named_bar_sync(kEpiBarrier, kEpiThreads);
         if (leader && !(p.dbg & 2)) {
           const uint8_t* reg = stg_region();
@@ -520,13 +605,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (norm_pass ? kind_norm(k2) : kind_direct(k2)) tma_store_4d(&map_out.m[2], reg + (di++) * kChunkBytes, t.col0 + c * 64, t.x0, t.y0, t.n0);
           bulk_commit();
         }
-        ++groups;
+        if (++greg == static_cast<uint32_t>(p.stg_regions)) greg = 0;
       };
 
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int q = q0; q < p.total_q; q += qstride, ++it) {
         const int buf = it & 1;
         const uint32_t bphase = static_cast<uint32_t>(it >> 1) & 1u;
-        const TileCoord t = decode_tile(p, tile);
+        const TileCoord t = decode_tile(p, tile_of(p, q, rank));
         const int n = t.n0 + rn;
         const bool valid = n < p.B;
         const size_t pix = static_cast<size_t>(n) * p.H * p.W + (t.y0 + ry) * p.W + t.x0 + rx;
@@ -539,7 +624,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           tc_fence_after();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+          if (lane == 0) acc_release(buf);
           continue;
         }
 
@@ -575,7 +660,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if (c == chunks - 1) {                  // accumulator fully read: the MMA warp may start the tile after next
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+              if (lane == 0) acc_release(buf);
             }
             const int col = t.col0 + c * 64 + half * 32;
             if (modsilu) {
@@ -686,11 +771,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (p.pair) cluster_sync_all(); else __syncthreads();   // pair: the peer's barriers / TMEM stay valid until both are done
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (p.pair) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
+  if ((p.dbg & 16) && threadIdx.x == 0) atomicMax(&g_conv_cycles, static_cast<unsigned long long>(clock64() - t_start));
 }
 
 }  // namespace
@@ -773,7 +859,7 @@ static bool plan_mainloop(ConvKernelParams& p, int budget, bool want_good) {
     const int a_slot = (a_tx + 1023) / 1024 * 1024;
     const int resident = 9 * kct * p.b_bytes;
     bool ok = false;
-    if (p.n_tiles == 1 && resident <= 96 * 1024 && budget - resident >= 3 * a_slot) {
+    if (p.n_tiles == 1 && budget - resident >= 3 * a_slot) {
       p.b_resident = 1;
       p.a_slots = std::min(kMaxStages, (budget - resident) / a_slot);
       p.b_slots = 0;
@@ -805,6 +891,12 @@ static bool plan_mainloop(ConvKernelParams& p, int budget, bool want_good) {
   if (stages < 2 || (want_good && stages < 3)) return false;
   p.num_stages = stages;
   return true;
+}
+
+// Quality of a main-loop layout (higher is better): resident weights >> shared haloed boxes >> per-tap stages, then depth.
+static int mainloop_score(const ConvKernelParams& p) {
+  if (p.tap_mode != 0) return (p.b_resident ? 2000 : 1000) + 10 * std::min(p.a_slots, 5) + std::min(p.b_slots, 12);
+  return 10 * std::min(p.num_stages, 6);
 }
 
 int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
@@ -841,9 +933,18 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
   p.kc_a = d->cin_pad / 64;
   p.kc_b = d->cin2_pad / 64;
   p.block_n = d->block_n;
-  p.b_bytes = d->block_n * 128;
-  p.stage_bytes = kAStageBytes + p.b_bytes;
-  p.idesc = umma_idesc_op(kBlockM, d->block_n);
+  static const int forced_pair = getenv("VB_PAIR") ? atoi(getenv("VB_PAIR")) : -1;      // -1 auto, 0 off, 1 on (A/B testing)
+  const int m_tiles = p.tiles_x * p.tiles_y * tiles_nb;
+  // each CTA's half of the weight tile must be whole 8-row swizzle groups, and there must be two M tiles to pair up
+  const bool pair_possible = d->block_n % 32 == 0 && m_tiles >= 2;
+  auto set_pair = [&](int pair) {
+    p.pair = pair;
+    p.total_q = pair ? (m_tiles + 1) / 2 * p.n_tiles : p.total_tiles;
+    p.b_bytes = (pair ? d->block_n / 2 : d->block_n) * 128;
+    p.stage_bytes = kAStageBytes + p.b_bytes;
+    p.idesc = umma_idesc_op(pair ? 2 * kBlockM : kBlockM, d->block_n);
+  };
+  set_pair(0);
   p.epi_mode = d->epi_mode;
   p.flags = d->flags;
   p.mod = d->mod;
@@ -916,15 +1017,46 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
       // Epilogue shared memory: residual ring + two staging regions of gslots sub-tiles.  A deep residual ring hides the
       // L2 latency of the residual loads when the per-chunk work is short; it is the first thing to shrink.
       p.gslots = std::max(n_direct, n_norm);
-      const int stg_bytes = 2 * p.gslots * kChunkBytes;
       const bool has_res = d->res_mode != VB_RES_NONE;
-      p.res_slots = has_res ? 4 : 2;
-      if (!plan_mainloop(p, kSmemMax - (has_res ? p.res_slots * kChunkBytes : 0) - stg_bytes, /*want_good=*/true)) {
-        p.res_slots = 2;
-        VB_REQUIRE_L(plan_mainloop(p, kSmemMax - (has_res ? p.res_slots * kChunkBytes : 0) - stg_bytes, false),
-                     "vb_conv: shared memory budget exceeded");
+      static const int forced_regions = getenv("VB_STG_REGIONS") ? atoi(getenv("VB_STG_REGIONS")) : 0;   // A/B testing
+      // Shared memory is split between the main loop and the epilogue rings.  Candidates, richest epilogue first; the
+      // main loop's needs win (a shallow per-tap pipeline behind a fat epilogue ring cost 2x on the SR 256x256 layers),
+      // a CTA pair is taken when it upgrades the main loop (its half-size weight tiles fit resident) or for narrow 3x3
+      // tiles, where the single-CTA MMA is shared-memory bound.
+      const int opts[4][2] = {{4, 3}, {4, 2}, {2, 3}, {2, 2}};      // {residual ring slots, staging regions}
+      int best[2] = {-1, -1};
+      ConvKernelParams best_p[2] = {p, p};
+      for (int pair = 0; pair <= (pair_possible ? 1 : 0); ++pair) {
+        for (int o = 0; o < 4; ++o) {
+          if (forced_regions == 2 && opts[o][1] != 2) continue;
+          if (!has_res && opts[o][0] != 4) continue;               // no residual: the ring size is moot
+          set_pair(pair);
+          p.res_slots = has_res ? opts[o][0] : 2;
+          p.stg_regions = opts[o][1];
+          if (!plan_mainloop(p, kSmemMax - (has_res ? p.res_slots * kChunkBytes : 0) - p.stg_regions * p.gslots * kChunkBytes,
+                             false))
+            continue;
+          const int score = 100 * mainloop_score(p) + (has_res && p.res_slots == 4 ? 40 : 0) + (p.stg_regions == 3 ? 10 : 0);
+          if (score > best[pair]) {
+            best[pair] = score;
+            best_p[pair] = p;
+          }
+        }
       }
+      int use_pair = 0;
+      if (best[1] >= 0) {
+        const ConvKernelParams& a = best_p[0];
+        const ConvKernelParams& b = best_p[1];
+        const bool upgrade = b.tap_mode != 0 && b.b_resident && !(best[0] >= 0 && a.tap_mode != 0 && a.b_resident);
+        const bool narrow = b.tap_mode != 0 && b.b_resident && d->block_n <= 64;
+        use_pair = forced_pair >= 0 ? forced_pair : ((upgrade || narrow) ? 1 : 0);
+        if (best[0] < 0) use_pair = 1;
+      }
+      const int best_score = best[use_pair];
+      p = best_p[use_pair];
+      VB_REQUIRE_L(best_score >= 0, "vb_conv: shared memory budget exceeded");
     } else {
+      if (forced_pair == 1 && pair_possible) set_pair(1);
       VB_REQUIRE_L(plan_mainloop(p, kSmemMax, false), "vb_conv: shared memory budget exceeded");
     }
   } else {
@@ -946,6 +1078,7 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
       p.part_off[j] = d->part_off[j];
     }
     p.norm_scale = 1.0f / sqrtf(static_cast<float>(d->head_dim));
+    if (forced_pair == 1 && pair_possible) set_pair(1);
     VB_REQUIRE_L(plan_mainloop(p, kSmemMax, false), "vb_conv: shared memory budget exceeded");
   }
   const int main_bytes = p.tap_mode != 0 ? p.b_off + (p.b_resident ? 9 * (p.kc_a + p.kc_b) : p.b_slots) * p.b_bytes
@@ -983,14 +1116,16 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
     const uint64_t ktot = static_cast<uint64_t>(d->taps) * (d->cin_pad + d->cin2_pad);
     const uint64_t dims[2] = {ktot, static_cast<uint64_t>(d->cout_pad)};
     const uint64_t strides[1] = {ktot * 2};
-    const uint32_t box[2] = {64, static_cast<uint32_t>(d->block_n)};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(p.pair ? d->block_n / 2 : d->block_n)};
     rc = encode_tmap_16(&l->map_w, d->w, 2, dims, strides, box);
     if (rc != VB_OK) return fail(rc);
   }
 #undef VB_REQUIRE_L
 
-  l->grid = std::min(p.total_tiles, num_sms());
-  l->smem_bytes = p.stg_off + (staged ? 2 * p.gslots * kChunkBytes : 0) + 1024;
+  // The kernel contains cta_group::2 instructions, so the driver only accepts it in clusters of two even when the CTAs work
+  // independently (pair == 0): the grid is kept even, a surplus CTA finds no work item and exits.
+  l->grid = p.pair ? std::min(2 * p.total_q, num_sms() & ~1) : std::min((p.total_tiles + 1) & ~1, num_sms() & ~1);
+  l->smem_bytes = p.stg_off + (staged ? p.stg_regions * p.gslots * kChunkBytes : 0) + 1024;
   l->flops = 2.0 * d->B * d->H * d->W * static_cast<double>(d->cout_pad) * d->taps * (d->cin_pad + d->cin2_pad);
   if (!var->attr_done) {
     cudaError_t e = cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax + 1024);
@@ -1005,8 +1140,20 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
 }
 
 int conv_launch(const ConvLaunch* l, cudaStream_t s) {
-  l->fn<<<l->grid, kThreads, l->smem_bytes, s>>>(l->map_a, l->map_a2, l->map_w, l->map_res, l->map_out, l->p);
-  VB_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(l->grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = l->smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, l->fn, l->map_a, l->map_a2, l->map_w, l->map_res, l->map_out, l->p));
   return VB_OK;
 }
 
@@ -1014,6 +1161,14 @@ void conv_free(ConvLaunch* l) { delete l; }
 double conv_flops(const ConvLaunch* l) { return l->flops; }
 
 }  // namespace vb
+
+extern "C" int vb_debug_conv_cycles(unsigned long long* out) {
+  VB_REQUIRE(out != nullptr, "vb_debug_conv_cycles: null out");
+  unsigned long long zero = 0;
+  VB_CHECK_CUDA(cudaMemcpyFromSymbol(out, vb::g_conv_cycles, sizeof(*out)));
+  VB_CHECK_CUDA(cudaMemcpyToSymbol(vb::g_conv_cycles, &zero, sizeof(zero)));
+  return VB_OK;
+}
 
 extern "C" int vb_conv(const vb_conv_desc* d, void* stream) {
   vb::ConvLaunch* l = nullptr;
