@@ -102,7 +102,6 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version banner there)
         torch.distributed.init_process_group("nccl", device_id=dev)
     B, T = args.batch, args.num_steps
     net, gnet, sr = make_net("vivid-base", 0, dev), make_net("vivid-uncond", 1, dev), make_net("vivid-sr", 2, dev)
@@ -241,7 +240,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(dict(base=net, uncond=gnet, sr=sr))
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -308,10 +307,23 @@ def run_reference(args):
                            "one denoiser call of each net at batch 1 on the host CPU", batch_per_gpu=1),
                cpu_baseline=base, e2e=dict(value=base["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                gpu_launches=0)
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_JSON_OUT = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the real stdout; everything else written to fd 1 (NCCL's version banner, library
+    printf) was redirected to stderr in main()."""
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
 
 
 def main():
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

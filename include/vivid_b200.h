@@ -45,6 +45,9 @@ const char* vb_last_error(void);
 int vb_abi_version(void);
 /* 0 when the current CUDA device is compute capability 10.x, VB_ERR_NO_DEVICE otherwise. */
 int vb_device_check(void);
+/* Measurement plumbing: occupies `stream` for the given time (one spinning thread) so that work enqueued behind it
+ * executes back to back, independent of the host's launch rate. */
+int vb_spin(int microseconds, void* stream);
 /* sizeof() of the descriptor structs below, in declaration order (0 = vb_weight_prep_desc ... 7 = vb_heun_desc);
  * lets a foreign-language binding verify its mirror of the layout.  -1 for an unknown index. */
 int vb_struct_size(int which);
@@ -128,6 +131,9 @@ int vb_conv(const vb_conv_desc* d, void* stream);
  * kernel records the longest CTA lifetime in SM cycles; this call synchronises, returns the maximum since the last
  * call (HOST pointer) and resets it. */
 int vb_debug_conv_cycles(unsigned long long* out);
+/* VB_DBG & 32: clock64 stamps of CTA 0 of the last conv launch: [0] start, [1] set-up done, [2] first operand stage
+ * landed, [3] last MMA committed, [4] first accumulator ready, [5] last store drained, [6] exit (HOST pointer, 8 values). */
+int vb_debug_conv_stamps(long long* out8);
 
 /* ------------------------------------------------------------------------
  * Fused cosine attention — replaces einsum/softmax/einsum (snapshot

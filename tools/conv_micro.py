@@ -22,6 +22,7 @@ SHAPES = [  # R, cin, cout, taps, bn
     (256, 64, 64, 9, 64), (128, 128, 128, 9, 128), (64, 128, 128, 9, 128), (32, 256, 256, 9, 256),
     (16, 384, 384, 9, 128), (8, 512, 512, 9, 64), (8, 512, 512, 9, 128), (16, 384, 1152, 1, 192), (256, 128, 64, 1, 64),
     (256, 128, 64, 9, 64), (64, 192, 192, 9, 192), (16, 384, 384, 9, 192), (64, 128, 128, 1, 128),
+    (8, 384, 512, 1, 64), (16, 384, 384, 1, 192), (8, 512, 512, 1, 64),
 ]
 B = int(os.environ.get("VB_B", "32"))
 reps = int(os.environ.get("VB_REPS", "10"))
@@ -69,9 +70,14 @@ for idx, (R, cin, cout, taps, bn) in enumerate(SHAPES):
         cyc = C.c_ulonglong(0)
         if int(os.environ.get("VB_DBG", "0")) & 16:
             L.check(lib.vb_debug_conv_cycles(C.byref(cyc)), "cycles")
+        stamps = ""
+        if int(os.environ.get("VB_DBG", "0")) & 32:
+            ts = (C.c_longlong * 8)()
+            L.check(lib.vb_debug_conv_stamps(ts), "stamps")
+            stamps = "  stamps(cyc): " + " ".join(str(ts[i] - ts[0]) for i in range(1, 7))
         fl = 2.0 * B * R * R * cout * cin * taps
         by = 2.0 * B * R * R * (cin + cout * (len(kinds) + (d.res_mode != 0)))
         print(f"[{idx}] {R}x{R} cin{cin} cout{cout} taps{taps} bn{bn} B{B} {epi:6s}: {ms*1e3:8.1f} us  "
               f"{fl/ms/1e9:7.1f} TFLOP/s  {by/ms/1e6:6.0f} GB/s" +
-              (f"  {cyc.value} cyc -> {cyc.value/ms/1e3:.0f} MHz" if cyc.value else ""), flush=True)
+              (f"  {cyc.value} cyc -> {cyc.value/ms/1e3:.0f} MHz" if cyc.value else "") + stamps, flush=True)
         lib.vb_plan_destroy(plan)

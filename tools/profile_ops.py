@@ -18,9 +18,18 @@ for i, name in enumerate(("vivid-base", "vivid-uncond", "vivid-sr")):
     p.run(graph=False)
     torch.cuda.synchronize()
     prof = p.profile(repeats=3)
+    for _ in range(2):
+        p.run(graph=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        p.run(graph=True)
+    e1.record()
+    torch.cuda.synchronize()
+    graph_ms = e0.elapsed_time(e1) / 5
     tot = sum(r[4] for r in prof)
     fl = sum(r[2] for r in prof)
-    print(f"== {name} B={B}: {tot:.2f} ms/call, {fl/tot/1e9:.1f} TFLOP/s overall, {len(prof)} ops, "
+    print(f"== {name} B={B}: {tot:.2f} ms/call, {fl/tot/1e9:.1f} TFLOP/s overall, {len(prof)} ops, graph replay {graph_ms:.2f} ms/call, "
           f"mem {torch.cuda.memory_allocated()/2**30:.1f} GiB")
     agg = {}
     for kind, label, f, by, ms in prof:

@@ -56,6 +56,9 @@ constexpr int kPairBarrier = 2;                       // +quadrant: the two warp
 
 // VB_DBG & 16: longest CTA lifetime (SM cycles) of the launches since the last vb_debug_conv_cycles() call.
 __device__ unsigned long long g_conv_cycles;
+// VB_DBG & 32: clock64 time stamps of CTA 0's phases (see vb_debug_conv_cycles).
+__device__ long long g_conv_ts[8];
+#define VB_TS(i) do { if (p.dbg & 32) { if (blockIdx.x == 0) g_conv_ts[i] = clock64(); } } while (0)
 
 struct ConvKernelParams {
   int B, H, W;
@@ -205,49 +208,255 @@ __device__ __forceinline__ int tile_of(const ConvKernelParams& p, int q, uint32_
   return (2 * mq + static_cast<int>(rank)) * p.n_tiles + (q - mq * p.n_tiles);
 }
 
-// The single MMA-issuing thread.  Its instruction stream is co-critical for narrow tiles (an N=64 MMA retires in 48
-// cycles), so descriptors advance by adds on the low word and nothing is re-derived inside the K loop.
+// ------------------------------------------------------------------------------------------------ single-thread roles
+// The TMA producers and the MMA issuer are ONE thread each; a lone warp issues a dependent instruction every ~5 cycles,
+// so their instruction streams are the pipeline's clock: the first version (one producer thread, barrier addresses
+// re-derived from the shared-window base and %cluster_ctarank at every use, run-time branches on the layer's mode)
+// spent ~65 instructions (~450 cycles) per 64-channel K block — slower than the four MMAs of the block for every tile
+// narrower than N=256 (ncu source view, profiles/r01_conv_roles.txt).  Hence: barrier and shared-memory addresses are
+// plain 32-bit values computed once, the operand loads are split over two warps (activations: warp 0, weights: warp 3),
+// the pair / single-CTA instruction forms are template arguments, and ring positions advance by adds.
+struct RoleCtx {
+  uint32_t smem;        // shared::cta address of the (1024-byte aligned) dynamic shared memory
+  uint32_t full, empty, bfull, bempty, tmem_full, tmem_empty;   // local barrier arrays (shared::cta addresses)
+  uint32_t full_dst, bfull_dst;                                  // where TMA completes its bytes (pair: leader CTA's)
+  uint32_t tmem_base;
+  uint32_t rank;
+  int q0, qstride;
+};
+
+// Pins a computed address in a register: without it the compiler re-derives every barrier address from the shared
+// window base and SR_CgaCtaId (5 instructions) at each use inside the single-thread loops.
+__device__ __forceinline__ uint32_t pinned(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (true) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins > VB_SPIN_LIMIT) __trap();       // a stuck pipeline traps instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void mbar_expect_tx_addr(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 template <bool PAIR>
-__device__ __forceinline__ void mma_role(const ConvKernelParams& p, uint8_t* smem, uint32_t tmem_base, int q0, int qstride,
-                                         uint64_t* full_bar, uint64_t* empty_bar, uint64_t* bfull_bar, uint64_t* bempty_bar,
-                                         uint64_t* tmem_full, uint64_t* tmem_empty) {
+__device__ __forceinline__ void tma_act(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+  if (PAIR)
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+        "%6}], [%2];" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+template <bool PAIR>
+__device__ __forceinline__ void tma_wgt(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1) {
+  if (PAIR)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar) {
+  if (PAIR)
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(static_cast<uint16_t>(3))
+                 : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// Activation producer (warp 0).  Simple mode: one {64 ch, tile} box per (tap, K chunk) stage; it also arms the stage's
+// barrier for the weight tile the other producer sends.  Tap mode: one haloed box per (tap group, K chunk).
+template <bool PAIR>
+__device__ __forceinline__ void producer_act(const ConvKernelParams& p, const RoleCtx& c, const CUtensorMap* map_a,
+                                             const CUtensorMap* map_a2) {
+  const bool lead = c.rank == 0;
+  const uint32_t mul = PAIR ? 2u : 1u;
+  uint32_t slot = 0, phase = 0;
+  if (p.tap_mode != 0) {
+    const uint32_t tx = static_cast<uint32_t>(p.a_tx_bytes) * mul;
+    const uint32_t nslots = p.a_slots, slot_bytes = p.a_slot_bytes;
+    uint32_t dst = c.smem;
+    for (int q = c.q0; q < p.total_q; q += c.qstride) {
+      const TileCoord t = decode_tile(p, tile_of(p, q, c.rank));
+      for (int g = 0; g < 3; ++g) {
+        const int cx = p.tap_mode == 1 ? t.x0 - 1 : t.x0 + g - 1;
+        const int cy = p.tap_mode == 1 ? t.y0 + g - 1 : t.y0 - 1;
+        for (int half = 0; half < 2; ++half) {
+          const CUtensorMap* m = half == 0 ? map_a : map_a2;
+          const int n = half == 0 ? p.kc_a : p.kc_b;
+          for (int kc = 0; kc < n; ++kc) {
+            mbar_wait_addr(c.empty + slot * 8, phase ^ 1u);
+            if (lead) mbar_expect_tx_addr(c.full + slot * 8, tx);
+            tma_act<PAIR>(m, c.full_dst + slot * 8, dst, kc * kBlockK, cx, cy, t.n0);
+            dst += slot_bytes;
+            if (++slot == nslots) {
+              slot = 0;
+              phase ^= 1u;
+              dst = c.smem;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    const uint32_t tx = static_cast<uint32_t>(kAStageBytes + p.b_bytes) * mul;
+    const uint32_t nslots = p.num_stages, slot_bytes = p.stage_bytes;
+    uint32_t dst = c.smem;
+    for (int q = c.q0; q < p.total_q; q += c.qstride) {
+      const TileCoord t = decode_tile(p, tile_of(p, q, c.rank));
+      int dy = p.taps == 9 ? -1 : 0, dx = dy;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        for (int half = 0; half < 2; ++half) {
+          const CUtensorMap* m = half == 0 ? map_a : map_a2;
+          const int n = half == 0 ? p.kc_a : p.kc_b;
+          for (int kc = 0; kc < n; ++kc) {
+            mbar_wait_addr(c.empty + slot * 8, phase ^ 1u);
+            if (lead) mbar_expect_tx_addr(c.full + slot * 8, tx);
+            tma_act<PAIR>(m, c.full_dst + slot * 8, dst, kc * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
+            dst += slot_bytes;
+            if (++slot == nslots) {
+              slot = 0;
+              phase ^= 1u;
+              dst = c.smem;
+            }
+          }
+        }
+        if (++dx == 2) {
+          dx = -1;
+          ++dy;
+        }
+      }
+    }
+  }
+}
+
+// Weight producer (warp 3).  Simple mode: the {64, rows} tile of every stage (the stage barrier was armed by the
+// activation producer; complete_tx may run ahead of expect_tx within a phase).  Tap mode: its own ring of tap tiles, or
+// the whole layer once when it is resident.
+template <bool PAIR>
+__device__ __forceinline__ void producer_wgt(const ConvKernelParams& p, const RoleCtx& c, const CUtensorMap* map_w) {
+  const bool lead = c.rank == 0;
+  const uint32_t mul = PAIR ? 2u : 1u;
+  const int wrow = PAIR ? static_cast<int>(c.rank) * (p.block_n >> 1) : 0;     // this CTA's rows of the weight tile
+  const int kct = p.kc_a + p.kc_b;
+  const uint32_t b_bytes = p.b_bytes;
+  if (p.tap_mode != 0) {
+    if (p.b_resident) {
+      const int nb = 9 * kct;
+      if (lead) mbar_expect_tx_addr(c.bfull, static_cast<uint32_t>(nb) * b_bytes * mul);
+      uint32_t dst = c.smem + p.b_off;
+      for (int i = 0; i < nb; ++i, dst += b_bytes) tma_wgt<PAIR>(map_w, c.bfull_dst, dst, i * kBlockK, wrow);
+      return;
+    }
+    const uint32_t nslots = p.b_slots, base = c.smem + p.b_off;
+    const uint32_t tx = b_bytes * mul;
+    // K column of (g, i, kc): (tap * kct + kc) * 64 with tap = 3g+i (mode 1) or 3i+g (mode 2)
+    const int g_step = (p.tap_mode == 1 ? 3 * kct : kct) * kBlockK;
+    const int i_step = (p.tap_mode == 1 ? kct : 3 * kct) * kBlockK;
+    uint32_t slot = 0, phase = 0, dst = base;
+    for (int q = c.q0; q < p.total_q; q += c.qstride) {
+      const int col = decode_tile(p, tile_of(p, q, c.rank)).col0 + wrow;
+      for (int g = 0; g < 3; ++g) {
+        for (int kc = 0; kc < kct; ++kc) {
+          int kcol = g * g_step + kc * kBlockK;
+#pragma unroll
+          for (int i = 0; i < 3; ++i, kcol += i_step) {
+            mbar_wait_addr(c.bempty + slot * 8, phase ^ 1u);
+            if (lead) mbar_expect_tx_addr(c.bfull + slot * 8, tx);
+            tma_wgt<PAIR>(map_w, c.bfull_dst + slot * 8, dst, kcol, col);
+            dst += b_bytes;
+            if (++slot == nslots) {
+              slot = 0;
+              phase ^= 1u;
+              dst = base;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    const uint32_t nslots = p.num_stages, slot_bytes = p.stage_bytes, base = c.smem + kAStageBytes;
+    const int k_blocks = p.taps * kct;
+    uint32_t slot = 0, phase = 0, dst = base;
+    for (int q = c.q0; q < p.total_q; q += c.qstride) {
+      const int col = decode_tile(p, tile_of(p, q, c.rank)).col0 + wrow;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait_addr(c.empty + slot * 8, phase ^ 1u);
+        tma_wgt<PAIR>(map_w, c.full_dst + slot * 8, dst, kb * kBlockK, col);
+        dst += slot_bytes;
+        if (++slot == nslots) {
+          slot = 0;
+          phase ^= 1u;
+          dst = base;
+        }
+      }
+    }
+  }
+}
+
+// The MMA issuer (warp 1; pair: the leader CTA's).  Descriptors advance by adds on the low word.
+template <bool PAIR>
+__device__ __forceinline__ void mma_role(const ConvKernelParams& p, const RoleCtx& c) {
+  const uint32_t idesc = p.idesc;
   auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
-    if (PAIR) umma_f16_ss_pair(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), p.idesc, acc);
-    else umma_f16_ss(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), p.idesc, acc);
-  };
-  auto commit = [&](uint64_t* bar) {
-    if (PAIR) umma_commit_pair(bar); else umma_commit(bar);
+    if (PAIR) umma_f16_ss_pair(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, acc);
+    else umma_f16_ss(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, acc);
   };
   const int kct = p.kc_a + p.kc_b;
   const uint32_t b_tile_lo = static_cast<uint32_t>(p.b_bytes) >> 4;
   int it = 0;
   if (p.tap_mode != 0) {
-    const uint32_t a_base = umma_desc_lo(smem_u32(smem));
+    const uint32_t a_base = umma_desc_lo(c.smem);
     const uint32_t a_slot_lo = static_cast<uint32_t>(p.a_slot_bytes) >> 4;
     const uint32_t win_lo = static_cast<uint32_t>(p.win_rows) * 8u;          // rows of 128 B
-    const uint32_t b_base = umma_desc_lo(smem_u32(smem + p.b_off));
+    const uint32_t b_base = umma_desc_lo(c.smem + p.b_off);
     // resident weights: tile index of (g, i, kc) is (tap * kct + kc) with tap = 3g+i (mode 1) or 3i+g (mode 2)
     const uint32_t b_g_lo = static_cast<uint32_t>(p.tap_mode == 1 ? 3 * kct : kct) * b_tile_lo;
     const uint32_t b_i_lo = static_cast<uint32_t>(p.tap_mode == 1 ? kct : 3 * kct) * b_tile_lo;
-    int as = 0, bs = 0;
-    uint32_t aph = 0, bph = 0;
-    if (p.b_resident) {
-      mbar_wait(&bfull_bar[0], 0);
+    const uint32_t a_slots = p.a_slots, b_slots = p.b_slots;
+    uint32_t as = 0, bs = 0, aph = 0, bph = 0, a_lo = a_base, b_ring = b_base;
+    const bool resident = p.b_resident != 0;
+    if (resident) {
+      mbar_wait_addr(c.bfull, 0);
       tc_fence_after();
     }
-    for (int q = q0; q < p.total_q; q += qstride, ++it) {
-      const int buf = it & 1;
-      mbar_wait(&tmem_empty[buf], (static_cast<uint32_t>(it >> 1) & 1u) ^ 1u);
+    for (int q = c.q0; q < p.total_q; q += c.qstride, ++it) {
+      const uint32_t buf = it & 1;
+      mbar_wait_addr(c.tmem_empty + buf * 8, (static_cast<uint32_t>(it >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
+      const uint32_t d_tmem = c.tmem_base + buf * kAccStride;
       uint32_t accumulate = 0;
       for (int g = 0; g < 3; ++g) {
         uint32_t b_gk = b_base + static_cast<uint32_t>(g) * b_g_lo;
         for (int kc = 0; kc < kct; ++kc, b_gk += b_tile_lo) {
-          mbar_wait(&full_bar[as], aph);
+          mbar_wait_addr(c.full + as * 8, aph);
+          if (it == 0 && g == 0 && kc == 0) VB_TS(2);
           tc_fence_after();
-          const uint32_t a_lo = a_base + static_cast<uint32_t>(as) * a_slot_lo;
-          if (p.b_resident) {
+          if (resident) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
 #pragma unroll
@@ -259,59 +468,66 @@ __device__ __forceinline__ void mma_role(const ConvKernelParams& p, uint8_t* sme
           } else {
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-              mbar_wait(&bfull_bar[bs], bph);
+              mbar_wait_addr(c.bfull + bs * 8, bph);
               tc_fence_after();
-              const uint32_t b_lo = b_base + static_cast<uint32_t>(bs) * b_tile_lo;
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k) {
-                mma(d_tmem, a_lo + i * win_lo + 2 * k, b_lo + 2 * k, accumulate);
+                mma(d_tmem, a_lo + i * win_lo + 2 * k, b_ring + 2 * k, accumulate);
                 accumulate = 1;
               }
-              commit(&bempty_bar[bs]);
-              if (++bs == p.b_slots) {
+              umma_commit_addr<PAIR>(c.bempty + bs * 8);
+              b_ring += b_tile_lo;
+              if (++bs == b_slots) {
                 bs = 0;
                 bph ^= 1u;
+                b_ring = b_base;
               }
             }
           }
-          commit(&empty_bar[as]);
-          if (++as == p.a_slots) {
+          umma_commit_addr<PAIR>(c.empty + as * 8);
+          a_lo += a_slot_lo;
+          if (++as == a_slots) {
             as = 0;
             aph ^= 1u;
+            a_lo = a_base;
           }
         }
       }
-      commit(&tmem_full[buf]);
+      umma_commit_addr<PAIR>(c.tmem_full + buf * 8);
+      VB_TS(3);
     }
   } else {
-    const uint32_t s_base = umma_desc_lo(smem_u32(smem));
+    const uint32_t s_base = umma_desc_lo(c.smem);
     const uint32_t stage_lo = static_cast<uint32_t>(p.stage_bytes) >> 4;
-    int stage = 0;
-    uint32_t phase = 0;
+    const uint32_t nstages = p.num_stages;
+    uint32_t stage = 0, phase = 0, a_lo = s_base;
     const int k_blocks = p.taps * kct;
-    for (int q = q0; q < p.total_q; q += qstride, ++it) {
-      const int buf = it & 1;
-      mbar_wait(&tmem_empty[buf], (static_cast<uint32_t>(it >> 1) & 1u) ^ 1u);
+    for (int q = c.q0; q < p.total_q; q += c.qstride, ++it) {
+      const uint32_t buf = it & 1;
+      mbar_wait_addr(c.tmem_empty + buf * 8, (static_cast<uint32_t>(it >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
+      const uint32_t d_tmem = c.tmem_base + buf * kAccStride;
       uint32_t accumulate = 0;
       for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait_addr(c.full + stage * 8, phase);
+        if (it == 0 && kb == 0) VB_TS(2);
         tc_fence_after();
-        const uint32_t a_lo = s_base + static_cast<uint32_t>(stage) * stage_lo;
         const uint32_t b_lo = a_lo + (kAStageBytes >> 4);
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
           mma(d_tmem, a_lo + 2 * k, b_lo + 2 * k, accumulate);
           accumulate = 1;
         }
-        commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
-        if (++stage == p.num_stages) {
+        umma_commit_addr<PAIR>(c.empty + stage * 8);   // smem slot reusable once these MMAs retire
+        a_lo += stage_lo;
+        if (++stage == nstages) {
           stage = 0;
           phase ^= 1u;
+          a_lo = s_base;
         }
       }
-      commit(&tmem_full[buf]);       // accumulator complete -> epilogue
+      umma_commit_addr<PAIR>(c.tmem_full + buf * 8);       // accumulator complete -> epilogue
+      VB_TS(3);
     }
   }
 }
@@ -347,6 +563,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const long long t_start = (p.dbg & 16) ? clock64() : 0;
+  if (threadIdx.x == 0) VB_TS(0);
   // CTA pair (p.pair): the two CTAs of a cluster work on two adjacent 128-pixel tiles of the same output-channel tile.
   // Each loads its own activation operand and HALF of the weight tile; the leader (rank 0) issues one M=256
   // cta_group::2 MMA for both, so every CTA reads (128 + block_n/2) operand rows per K step from its shared memory
@@ -394,104 +611,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (p.pair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) VB_TS(1);
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp < 2 || warp == 3) {
+    // ------------------------------------------------------------------ producers (warps 0, 3) and MMA issuer (warp 1)
     if (elect_one_sync()) {
+      RoleCtx c;
+      c.smem = pinned(smem_u32(smem));
+      c.full = pinned(smem_u32(&full_bar[0]));
+      c.empty = pinned(smem_u32(&empty_bar[0]));
+      c.bfull = pinned(smem_u32(&bfull_bar[0]));
+      c.bempty = pinned(smem_u32(&bempty_bar[0]));
+      c.tmem_full = pinned(smem_u32(&tmem_full[0]));
+      c.tmem_empty = pinned(smem_u32(&tmem_empty[0]));
       // pair: both CTAs complete their bytes on the LEADER's full barriers, which the leader arms for both halves
-      const uint32_t full0 = p.pair ? mapa_u32(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
-      const uint32_t bfull0 = p.pair ? mapa_u32(smem_u32(&bfull_bar[0]), 0) : smem_u32(&bfull_bar[0]);
-      const uint32_t txmul = p.pair ? 2u : 1u;
-      const int wrow = p.pair ? static_cast<int>(rank) * (p.block_n >> 1) : 0;    // this CTA's rows of the weight tile
-      auto load_a = [&](const CUtensorMap* m, uint32_t bar, void* dst, int c0, int c1, int c2, int c3) {
-        if (p.pair) tma_load_4d_pair(m, bar, dst, c0, c1, c2, c3);
-        else asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                          ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-      };
-      auto load_w = [&](uint32_t bar, void* dst, int c0, int c1) {
-        if (p.pair) tma_load_2d_pair(&map_w, bar, dst, c0, c1);
-        else asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                          ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(&map_w)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-      };
-      const int kct = p.kc_a + p.kc_b;
-      if (p.tap_mode != 0) {
-        int as = 0, bs = 0;
-        uint32_t aph = 0, bph = 0;
-        if (p.b_resident) {
-          // every tap tile of this layer's weights, once (n_tiles == 1)
-          const int nb = 9 * kct;
-          if (rank == 0) mbar_expect_tx(&bfull_bar[0], static_cast<uint32_t>(nb) * p.b_bytes * txmul);
-          for (int i = 0; i < nb; ++i) load_w(bfull0, smem + p.b_off + i * p.b_bytes, i * kBlockK, wrow);
-        }
-        for (int q = q0; q < p.total_q; q += qstride) {
-          const TileCoord t = decode_tile(p, tile_of(p, q, rank));
-          for (int g = 0; g < 3; ++g) {
-            for (int kc = 0; kc < kct; ++kc) {
-              mbar_wait(&empty_bar[as], aph ^ 1u);
-              uint8_t* sa = smem + as * p.a_slot_bytes;
-              if (rank == 0) mbar_expect_tx(&full_bar[as], p.a_tx_bytes * txmul);
-              const int cx = p.tap_mode == 1 ? t.x0 - 1 : t.x0 + g - 1;
-              const int cy = p.tap_mode == 1 ? t.y0 + g - 1 : t.y0 - 1;
-              if (kc < p.kc_a)
-                load_a(&map_a, full0 + as * 8, sa, kc * kBlockK, cx, cy, t.n0);
-              else
-                load_a(&map_a2, full0 + as * 8, sa, (kc - p.kc_a) * kBlockK, cx, cy, t.n0);
-              if (++as == p.a_slots) {
-                as = 0;
-                aph ^= 1u;
-              }
-              if (!p.b_resident) {
-                for (int i = 0; i < 3; ++i) {
-                  const int tap = p.tap_mode == 1 ? g * 3 + i : i * 3 + g;
-                  mbar_wait(&bempty_bar[bs], bph ^ 1u);
-                  if (rank == 0) mbar_expect_tx(&bfull_bar[bs], p.b_bytes * txmul);
-                  load_w(bfull0 + bs * 8, smem + p.b_off + bs * p.b_bytes, (tap * kct + kc) * kBlockK, t.col0 + wrow);
-                  if (++bs == p.b_slots) {
-                    bs = 0;
-                    bph ^= 1u;
-                  }
-                }
-              }
-            }
-          }
-        }
-      } else {
-        int stage = 0;
-        uint32_t phase = 0;
-        const uint32_t tx_bytes = (kAStageBytes + p.b_bytes) * txmul;
-        for (int q = q0; q < p.total_q; q += qstride) {
-          const TileCoord t = decode_tile(p, tile_of(p, q, rank));
-          int kcol = 0;
-          for (int tap = 0; tap < p.taps; ++tap) {
-            const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
-            const int dx = p.taps == 9 ? tap % 3 - 1 : 0;
-            for (int kc = 0; kc < kct; ++kc) {
-              mbar_wait(&empty_bar[stage], phase ^ 1u);
-              uint8_t* sa = smem + stage * p.stage_bytes;
-              uint8_t* sb = sa + kAStageBytes;
-              if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
-              if (kc < p.kc_a)
-                load_a(&map_a, full0 + stage * 8, sa, kc * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
-              else
-                load_a(&map_a2, full0 + stage * 8, sa, (kc - p.kc_a) * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
-              load_w(full0 + stage * 8, sb, kcol, t.col0 + wrow);
-              kcol += kBlockK;
-              if (++stage == p.num_stages) {
-                stage = 0;
-                phase ^= 1u;
-              }
-            }
-          }
-        }
+      c.full_dst = pinned(p.pair ? mapa_u32(c.full, 0) : c.full);
+      c.bfull_dst = pinned(p.pair ? mapa_u32(c.bfull, 0) : c.bfull);
+      c.tmem_base = tmem_base;
+      c.rank = rank;
+      c.q0 = q0;
+      c.qstride = qstride;
+      if (warp == 0) {
+        if (p.pair) producer_act<true>(p, c, &map_a, &map_a2); else producer_act<false>(p, c, &map_a, &map_a2);
+      } else if (warp == 3) {
+        if (p.pair) producer_wgt<true>(p, c, &map_w); else producer_wgt<false>(p, c, &map_w);
+      } else if (rank == 0) {
+        if (p.pair) mma_role<true>(p, c); else mma_role<false>(p, c);
       }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
-    if (elect_one_sync() && rank == 0) {
-      if (p.pair)
-        mma_role<true>(p, smem, tmem_base, q0, qstride, full_bar, empty_bar, bfull_bar, bempty_bar, tmem_full, tmem_empty);
-      else
-        mma_role<false>(p, smem, tmem_base, q0, qstride, full_bar, empty_bar, bfull_bar, bempty_bar, tmem_full, tmem_empty);
     }
   } else if (warp >= kFirstEpiWarp) {
     // ------------------------------------------------------------------ epilogue
@@ -522,6 +668,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const size_t pix = static_cast<size_t>(n) * p.H * p.W + s_img;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * kAccStride);
         mbar_wait(&tmem_full[buf], bphase);
+        if (leader && it == 0) VB_TS(4);
         tc_fence_after();
         if (p.epi_mode == VB_EPI_QKVNORM) {
           if (p.head_dim == 64) {
@@ -644,6 +791,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
 
         mbar_wait(&tmem_full[buf], bphase);
+        if (leader && it == 0) VB_TS(4);
         tc_fence_after();
 
         // ---- pass M: accumulator -> modulation / mp_silu -> mp_sum with the residual -> clamp; RAW / SILU outputs leave
@@ -767,6 +915,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       }
       if (leader) bulk_wait_read<0>();          // staging smem must outlive the last TMA store's read
+      if (leader) VB_TS(5);
     }
   }
 
@@ -776,6 +925,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tc_fence_after();
     if (p.pair) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (threadIdx.x == 0) VB_TS(6);
   if ((p.dbg & 16) && threadIdx.x == 0) atomicMax(&g_conv_cycles, static_cast<unsigned long long>(clock64() - t_start));
 }
 
@@ -1167,6 +1317,11 @@ extern "C" int vb_debug_conv_cycles(unsigned long long* out) {
   unsigned long long zero = 0;
   VB_CHECK_CUDA(cudaMemcpyFromSymbol(out, vb::g_conv_cycles, sizeof(*out)));
   VB_CHECK_CUDA(cudaMemcpyToSymbol(vb::g_conv_cycles, &zero, sizeof(zero)));
+  return VB_OK;
+}
+extern "C" int vb_debug_conv_stamps(long long* out8) {
+  VB_REQUIRE(out8 != nullptr, "vb_debug_conv_stamps: null out");
+  VB_CHECK_CUDA(cudaMemcpyFromSymbol(out8, vb::g_conv_ts, 8 * sizeof(long long)));
   return VB_OK;
 }
 

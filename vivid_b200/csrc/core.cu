@@ -82,7 +82,24 @@ int encode_tmap_16(CUtensorMap* map, const void* base, int rank, const uint64_t*
   return VB_OK;
 }
 
+// One thread spinning on the global nanosecond timer: holds the stream busy so that launches enqueued behind it run
+// back to back (per-op timing in Plan.profile without the host's launch rate in the measurement).
+__global__ void spin_kernel(unsigned long long ns) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < ns);
+}
+
 }  // namespace vb
+
+extern "C" int vb_spin(int microseconds, void* stream) {
+  VB_REQUIRE(microseconds > 0 && microseconds <= 2000000, "vb_spin: duration out of range");
+  vb::spin_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<unsigned long long>(microseconds) * 1000ull);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB_OK;
+}
 
 extern "C" const char* vb_last_error(void) { return vb::g_err; }
 extern "C" int vb_abi_version(void) { return VB_ABI_VERSION; }

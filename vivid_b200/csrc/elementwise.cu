@@ -4,6 +4,8 @@
 // (:48-61), mp_silu (:66-67), mp_cat (:78-84), MPFourier + embedding linears (:96-101, 388-391,
 // 175), EDM preconditioning (NVPrecond.forward), Heun/guidance update (generate_images.py:62,
 // 93-114) and the uint8 pixel codec (training/encoders.py:58-62).
+#include <algorithm>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -182,32 +184,85 @@ __global__ void __launch_bounds__(256) emb_kernel(const vb_emb_desc d) {
   __syncthreads();
   const float t = d.label_balance;
   const float inv = rsqrtf((1.f - t) * (1.f - t) + t * t);
-  for (int j = threadIdx.x; j < d.cemb; j += blockDim.x) {
-    const float* wn = d.w_noise + static_cast<size_t>(j) * d.cnoise;
-    float e = 0.f;
-    for (int c = 0; c < d.cnoise; ++c) e += wn[c] * s_in[c];
-    if (d.w_label != nullptr) {
-      const float* wl = d.w_label + static_cast<size_t>(j) * d.label_dim;
-      float g = 0.f;
-      for (int c = 0; c < d.label_dim; ++c) g += wl[c] * s_geo[c];
-      e = (e * (1.f - t) + g * t) * inv;
+  const int lane = threadIdx.x & 31;
+  // grid.y slices the output rows; a warp owns 8 rows at a time and issues all their (coalesced) weight loads before the
+  // first reduction, so the L2 latency is paid once per 8 rows instead of once per row
+  const int rows_per_slice = (d.cemb + gridDim.y - 1) / gridDim.y;
+  const int j_end = min(d.cemb, (static_cast<int>(blockIdx.y) + 1) * rows_per_slice);
+  for (int j0 = blockIdx.y * rows_per_slice + (threadIdx.x >> 5) * 8; j0 < j_end; j0 += (blockDim.x >> 5) * 8) {
+    float e[8], g[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int j = min(j0 + r, d.cemb - 1);
+      const float* wn = d.w_noise + static_cast<size_t>(j) * d.cnoise;
+      float a = 0.f;
+      for (int c = lane; c < d.cnoise; c += 32) a += __ldg(wn + c) * s_in[c];
+      e[r] = a;
+      float b2 = 0.f;
+      if (d.w_label != nullptr) {
+        const float* wl = d.w_label + static_cast<size_t>(j) * d.label_dim;
+        for (int c = lane; c < d.label_dim; c += 32) b2 += __ldg(wl + c) * s_geo[c];
+      }
+      g[r] = b2;
     }
-    // full-precision silu here: this vector modulates every block
-    d.emb[static_cast<size_t>(b) * d.cemb + j] = e / (1.f + expf(-e)) * (1.0f / 0.596f);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float ev = warp_sum(e[r]);
+      if (d.w_label != nullptr) ev = (ev * (1.f - t) + warp_sum(g[r]) * t) * inv;
+      // full-precision silu here: this vector modulates every block
+      if (lane == 0 && j0 + r < j_end) d.emb[static_cast<size_t>(b) * d.cemb + j0 + r] = ev / (1.f + expf(-ev)) * (1.0f / 0.596f);
+    }
   }
 }
-// One warp per modulation channel m: mod[b][m] = Wmod[m] . emb[b] + 1 for every b.
+
+// mod[b][m] = Wmod[m] . emb[b] + 1 for every block's emb_linear at once (reference Block.forward, models.py:175): a
+// small fp32 GEMM, C[B x mod_total] = E[B x cemb] W^T.  Register-tiled SIMT: block = 64 channels x 32 batch rows,
+// thread = 2 channels x 4 batch rows, K in shared-memory slices of 32.  (v1 — one warp per channel with a shuffle
+// reduction per batch row — took ~85 us for 11 904 channels; the modulation must stay fp32, so no tensor cores here.)
+constexpr int kModBM = 64, kModBK = 32;
 __global__ void __launch_bounds__(256) mod_kernel(const vb_emb_desc d) {
-  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (m >= d.mod_total) return;
-  const int lane = threadIdx.x & 31;
-  const float* w = d.w_mod + static_cast<size_t>(m) * d.cemb;
-  for (int b = 0; b < d.B; ++b) {
-    const float* e = d.emb + static_cast<size_t>(b) * d.cemb;
-    float acc = 0.f;
-    for (int j = lane; j < d.cemb; j += 32) acc += __ldg(w + j) * e[j];
-    acc = warp_sum(acc);
-    if (lane == 0) d.mod[static_cast<size_t>(b) * d.mod_total + m] = acc + 1.0f;
+  __shared__ float s_w[kModBM][kModBK + 1];
+  __shared__ __align__(16) float s_e[kModBK][32];
+  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+  const int m0 = blockIdx.x * kModBM, b0 = blockIdx.y * 32;
+  const int lr = tid >> 5, lc = tid & 31;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (int k0 = 0; k0 < d.cemb; k0 += kModBK) {
+#pragma unroll
+    for (int i = 0; i < kModBM / 8; ++i) {
+      const int r = lr + 8 * i;
+      s_w[r][lc] = (m0 + r < d.mod_total && k0 + lc < d.cemb) ? __ldg(d.w_mod + static_cast<size_t>(m0 + r) * d.cemb + k0 + lc) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int bb = lr + 8 * i;
+      s_e[lc][bb] = (b0 + bb < d.B && k0 + lc < d.cemb) ? d.emb[static_cast<size_t>(b0 + bb) * d.cemb + k0 + lc] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kModBK; ++k) {
+      const float4 e = *reinterpret_cast<const float4*>(&s_e[k][tx * 4]);
+      const float w0 = s_w[ty * 2][k], w1 = s_w[ty * 2 + 1][k];
+      acc[0][0] = fmaf(w0, e.x, acc[0][0]);
+      acc[0][1] = fmaf(w0, e.y, acc[0][1]);
+      acc[0][2] = fmaf(w0, e.z, acc[0][2]);
+      acc[0][3] = fmaf(w0, e.w, acc[0][3]);
+      acc[1][0] = fmaf(w1, e.x, acc[1][0]);
+      acc[1][1] = fmaf(w1, e.y, acc[1][1]);
+      acc[1][2] = fmaf(w1, e.z, acc[1][2]);
+      acc[1][3] = fmaf(w1, e.w, acc[1][3]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int b = b0 + tx * 4 + j;
+    if (b >= d.B) continue;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int m = m0 + ty * 2 + i;
+      if (m < d.mod_total) d.mod[static_cast<size_t>(b) * d.mod_total + m] = acc[i][j] + 1.0f;
+    }
   }
 }
 
@@ -243,6 +298,48 @@ __global__ void __launch_bounds__(256) precond_in_kernel(const vb_precond_in_des
   }
   // im2col: channel ci*9 + tap holds input channel ci at the tap's neighbour (zero outside the image, as conv padding does)
   const int y = static_cast<int>(s / d.R), x = static_cast<int>(s - static_cast<long long>(y) * d.R);
+  if (d.cpad == 64) {
+    // First convs at K = 64 (4 channels -> 36, SR's 7 -> 63): every neighbour load issued up front, straight-line
+    // packing.  (The generic loop below ran at 1.2 TB/s of output on the 256x256 inputs: latency-bound behind
+    // per-element branches.)
+    bool ok[9];
+    long long off[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      ok[tap] = yy >= 0 && yy < d.R && xx >= 0 && xx < d.R;
+      off[tap] = ok[tap] ? static_cast<long long>(yy) * d.R + xx : s;
+    }
+    float v[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const float a = __ldg(xp + ci * hw + off[tap]);
+        v[ci * 9 + tap] = ok[tap] ? a * c_in : 0.f;
+        if (cp) {
+          const float c = __ldg(cp + ci * hw + off[tap]);
+          const float nz = np ? __ldg(np + ci * hw + off[tap]) : 0.f;
+          v[(ci + 3) * 9 + tap] = ok[tap] ? c + d.noisy_sr * nz : 0.f;
+        }
+      }
+    }
+    if (cp) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) v[54 + tap] = ok[tap] ? 1.0f : 0.f;
+    } else {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) v[27 + tap] = ok[tap] ? 1.0f : 0.f;
+    }
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      o4[i] = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
+                         pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
+    return;
+  }
   for (int base = 0; base < d.cpad; base += 8) {
     float v[8];
 #pragma unroll
@@ -387,10 +484,11 @@ int embed_launch(const vb_emb_desc* d, cudaStream_t s) {
   VB_REQUIRE(d->B > 0 && d->cnoise > 0 && d->cemb > 0, "vb_embed: empty problem");
   VB_REQUIRE(d->mod_total == 0 || (d->w_mod && d->mod), "vb_embed: w_mod/mod missing");
   const size_t smem = sizeof(float) * (d->cnoise + (d->w_label ? d->label_dim : 0));
-  emb_kernel<<<d->B, 256, smem, s>>>(*d);
+  emb_kernel<<<dim3(d->B, 4), 256, smem, s>>>(*d);
   VB_CHECK_CUDA(cudaGetLastError());
   if (d->mod_total > 0) {
-    mod_kernel<<<(d->mod_total * 32 + 255) / 256, 256, 0, s>>>(*d);
+    const dim3 grid((d->mod_total + kModBM - 1) / kModBM, (d->B + 31) / 32);
+    mod_kernel<<<grid, 256, 0, s>>>(*d);
     VB_CHECK_CUDA(cudaGetLastError());
   }
   return VB_OK;

@@ -486,6 +486,9 @@ class Plan:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(self.num_ops + 1)]
         best = [float("inf")] * self.num_ops
         for _ in range(repeats):
+            # a blocker holds the stream while the host enqueues the whole plan: the ops then run back to back and the
+            # events see device time only (launched one by one, every op under ~12 us measured the host's launch rate)
+            L.check(self.lib.vb_spin(max(2000, 40 * self.num_ops), stream.cuda_stream), "vb_spin")
             ev[0].record(stream)
             for i in range(self.num_ops):
                 L.check(self.lib.vb_plan_run(self.handle, i, i + 1, stream.cuda_stream), "vb_plan_run")
