@@ -96,8 +96,10 @@ int vb_weight_prep(const vb_weight_prep_desc* d, void* stream);
 enum { VB_EPI_PLAIN = 0, VB_EPI_QKVNORM = 1 };
 enum { VB_F_MODSILU = 1, VB_F_CLIP = 4 };
 /* residual input: none | mp_sum(res, v) | mp_sum(pixel_norm(res), v)  (the enc-flavour block normalises its input
- * before using it as the residual base, models.py:171,184; recomputed in the epilogue instead of stored) */
-enum { VB_RES_NONE = 0, VB_RES_PLAIN = 1, VB_RES_PIXNORM = 2 };
+ * before using it as the residual base, models.py:171,184; recomputed in the epilogue instead of stored) |
+ * mp_sum(res * res_rnorm[pixel], v): the same, with the per-pixel 1/(eps + rms) taken from the fp32 side channel the
+ * producer of `res` wrote through out_rnorm (one pass over the residual tile instead of two) */
+enum { VB_RES_NONE = 0, VB_RES_PLAIN = 1, VB_RES_PIXNORM = 2, VB_RES_SCALED = 3 };
 /* output slots: v | mp_silu(v*scale) | pixel_norm(v) | mp_silu(pixel_norm(v)).  The NORM kinds need the whole
  * channel extent in one tile (cout_pad == block_n <= 256): this is the next block's pixel-norm fused here. */
 enum { VB_OUT_NONE = 0, VB_OUT_RAW = 1, VB_OUT_SILU = 2, VB_OUT_NORM = 3, VB_OUT_NORM_SILU = 4 };
@@ -110,6 +112,8 @@ typedef struct vb_conv_desc {
   const void* res;  /* 16-bit NHWC [B*H*W][cout_pad] residual stream (TMA-staged through shared memory) */
   void* out[3];     /* 16-bit NHWC [B*H*W][cout_pad] outputs (shared-memory staged, TMA stores) */
   float* out_f32;   /* optional fp32 [B*H*W][ld_f32] copy of v, direct stores (the 3-channel out_conv) */
+  float* out_rnorm; /* optional fp32 [B*H*W]: 1/(1e-4 + rms_c(v)) per pixel, written when a NORM kind is emitted */
+  const float* res_rnorm; /* VB_RES_SCALED: fp32 [B*H*W] per-pixel scale of the residual */
   void* part_out[3]; /* QKVNORM: q,k,v (or k,v) 16-bit [B/seg_div][heads][part_seq[j]][head_dim] */
   int32_t B, H, W;
   int32_t cin_pad, cin2_pad;

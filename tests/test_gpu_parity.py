@@ -93,6 +93,9 @@ CONV_CASES = [
     (2, 128, 128, 128, 9, 128, 0, 2, 1, (1, 4, 2)),     # 128-pixel rows: haloed row box serves 3 taps, streamed weights
     (3, 256, 64, 64, 9, 64, 1, 0, 0, (1,)),             # ... with the layer's weights resident in shared memory
     (1, 128, 192, 64, 9, 64, 0, 1, 1, (1, 2)),          # K = 3 chunks x 9 taps, resident weights do not fit -> streamed
+    (2, 64, 128, 128, 9, 128, 0, 3, 1, (1, 4)),         # residual scaled by the producer's per-pixel 1/rms side channel
+    (3, 256, 64, 64, 9, 64, 0, 3, 1, (1, 4, 2)),        # ... at SR resolution (CTA pair, resident weights)
+    (9, 8, 512, 512, 9, 128, 0, 1, 1, (1, 2)),          # 8x8 level: 2 images per tile, 4 N tiles, K = 72 blocks
 ]
 
 
@@ -119,7 +122,7 @@ def test_conv_gemm_vs_conv2d(env, B, R, cin, cout, taps, bn, modsilu, res_mode, 
     if res_mode:
         res = (torch.randn(B, R, R, cout, generator=g) * 1.7).to(dev).to(dt)
         r = res.float().permute(0, 3, 1, 2)
-        if res_mode == 2:
+        if res_mode >= 2:
             r = pixnorm(r)
         y = (r * 0.7 + y * 0.3) / math.sqrt(0.7 ** 2 + 0.3 ** 2)
     if clip:
@@ -127,7 +130,14 @@ def test_conv_gemm_vs_conv2d(env, B, R, cin, cout, taps, bn, modsilu, res_mode, 
     refs = {1: y, 2: mp_silu(y * 0.8), 3: pixnorm(y), 4: mp_silu(pixnorm(y))}
     outs = [torch.full((B, R, R, cout), float("nan"), dtype=dt, device=dev) for _ in kinds]
     o32 = torch.full((B, R, R, cout), float("nan"), device=dev)
-    d = L.ConvDesc(x=x_nhwc.data_ptr(), w=wp.data_ptr(), mod=L.ptr(mod), res=L.ptr(res), out_f32=o32.data_ptr(), B=B, H=R, W=R,
+    rn_in = rn_out = None
+    if res_mode == 3:       # what the producer of `res` would have written through out_rnorm
+        rf = res.float()
+        rn_in = (1.0 / (1e-4 + rf.norm(dim=-1) / math.sqrt(cout))).contiguous()
+    if any(kd >= 3 for kd in kinds):
+        rn_out = torch.full((B, R, R), float("nan"), device=dev)
+    d = L.ConvDesc(x=x_nhwc.data_ptr(), w=wp.data_ptr(), mod=L.ptr(mod), res=L.ptr(res), out_f32=o32.data_ptr(),
+                   out_rnorm=L.ptr(rn_out), res_rnorm=L.ptr(rn_in), B=B, H=R, W=R,
                    cin_pad=cin_pad, cin2_pad=0, cout_pad=cout, taps=taps, block_n=bn, epi_mode=L.VB_EPI_PLAIN,
                    flags=(L.VB_F_MODSILU if modsilu else 0) | (L.VB_F_CLIP if clip else 0), mod_stride=cout, ld_f32=cout,
                    res_mode=res_mode, res_t=0.3, clip=1.5)
@@ -138,7 +148,9 @@ def test_conv_gemm_vs_conv2d(env, B, R, cin, cout, taps, bn, modsilu, res_mode, 
     L.check(lib.vb_conv(C.byref(d), stream()), "vb_conv")
     torch.cuda.synchronize()
     tol = 2e-3 if dt == torch.float16 else 8e-3
-    assert rel(o32.permute(0, 3, 1, 2), y) < (2e-3 if (modsilu or res_mode == 2) else 2e-5)   # tanh-based silu / rsqrt
+    assert rel(o32.permute(0, 3, 1, 2), y) < (2e-3 if (modsilu or res_mode >= 2) else 2e-5)   # tanh-based silu / rsqrt
+    if rn_out is not None:
+        assert rel(rn_out, 1.0 / (1e-4 + y.norm(dim=1) / math.sqrt(cout))) < 1e-4
     for o, kd in zip(outs, kinds):
         assert rel(o.float().permute(0, 3, 1, 2), refs[kd]) < tol, kd
     # linearity of the GEMM (size-independent property): conv(2x) == 2 conv(x) exactly

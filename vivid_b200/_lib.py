@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libvividb200.so")
 VB_F32, VB_F16, VB_BF16 = 0, 1, 2
 VB_EPI_PLAIN, VB_EPI_QKVNORM = 0, 1
 VB_F_MODSILU, VB_F_CLIP = 1, 4
-VB_RES_NONE, VB_RES_PLAIN, VB_RES_PIXNORM = 0, 1, 2
+VB_RES_NONE, VB_RES_PLAIN, VB_RES_PIXNORM, VB_RES_SCALED = 0, 1, 2, 3
 VB_OUT_NONE, VB_OUT_RAW, VB_OUT_SILU, VB_OUT_NORM, VB_OUT_NORM_SILU = 0, 1, 2, 3, 4
 VB_EW_PIXNORM, VB_EW_DOWN_PIXNORM, VB_EW_UP, VB_EW_CAT, VB_EW_SILU = 0, 1, 2, 3, 4
 
@@ -28,7 +28,7 @@ class WeightPrepDesc(C.Structure):
 
 class ConvDesc(C.Structure):
     _fields_ = [("x", vp), ("x2", vp), ("w", vp), ("mod", vp), ("res", vp), ("out", vp * 3), ("out_f32", vp),
-                ("part_out", vp * 3), ("B", i32), ("H", i32), ("W", i32), ("cin_pad", i32), ("cin2_pad", i32),
+                ("out_rnorm", vp), ("res_rnorm", vp), ("part_out", vp * 3), ("B", i32), ("H", i32), ("W", i32), ("cin_pad", i32), ("cin2_pad", i32),
                 ("cout_pad", i32), ("taps", i32), ("block_n", i32), ("epi_mode", i32), ("flags", i32),
                 ("mod_stride", i32), ("ld_f32", i32), ("res_mode", i32), ("out_kind", i32 * 3), ("head_dim", i32),
                 ("parts", i32), ("seg_div", i32), ("part_seq", i32 * 3), ("part_off", i32 * 3),

@@ -63,7 +63,7 @@ __device__ long long g_conv_ts[8];
 struct ConvKernelParams {
   int B, H, W;
   int bw, bh, bn;
-  int tiles_x, tiles_y;
+  int tiles_x, tiles_y, tx_shift, ty_shift;
   int n_tiles, total_tiles;
   int pair, total_q;    // CTA-pair mode (cluster of 2, cta_group::2 MMA); work items per CTA / per pair
   int taps, kc_a, kc_b;
@@ -90,6 +90,8 @@ struct ConvKernelParams {
   int res_off, stg_off; // byte offsets of the residual ring / staging ring inside dynamic smem
   float* out_f32;
   int ld_f32;
+  float* out_rnorm;          // per-pixel 1/(eps + rms) side channel (producer)
+  const float* res_rnorm;    // ... and its consumer (VB_RES_SCALED)
   float res_a, res_b, clamp;
   float inv_sqrt_c;     // 1/sqrt(cout) for the pixel norms
   int head_dim, parts, seg_div, heads;
@@ -108,12 +110,13 @@ struct TileCoord {
 };
 
 __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int tile) {
-  const int mt = tile / p.n_tiles;
+  // tiles_x and tiles_y are powers of two (H, W and the tile extents are); only n_tiles needs a real division
+  const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles;
   const int nt = tile - mt * p.n_tiles;
-  const int tx = mt % p.tiles_x;
-  const int t2 = mt / p.tiles_x;
-  const int ty = t2 % p.tiles_y;
-  const int tn = t2 / p.tiles_y;
+  const int tx = mt & (p.tiles_x - 1);
+  const int t2 = mt >> p.tx_shift;
+  const int ty = t2 & (p.tiles_y - 1);
+  const int tn = t2 >> p.ty_shift;
   TileCoord t;
   t.x0 = tx * p.bw;
   t.y0 = ty * p.bh;
@@ -141,6 +144,28 @@ __device__ __forceinline__ uint32_t pack_op2_nosat(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
 #endif
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// mp_silu of a packed 16-bit pair, computed in packed arithmetic: x*c*(1 + tanh(x/2)), c = 0.5/0.596 — one MUFU op and
+// three packed multiplies per TWO elements (the fp32 form costs five instructions and one MUFU op per element; the
+// epilogue of the narrow SR layers is issue-bound).  Same error class as tanh.approx.f32 followed by 16-bit rounding.
+__device__ __forceinline__ uint32_t mp_silu_pk(uint32_t x2, float scale) {
+#ifdef VB_OP_BF16
+  __nv_bfloat162 x = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&x2), __float2bfloat162_rn(scale));
+  __nv_bfloat162 h = __hmul2(x, __float2bfloat162_rn(0.5f));
+  uint32_t hu = *reinterpret_cast<uint32_t*>(&h), tu;
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(tu) : "r"(hu));
+  const __nv_bfloat162 c = __float2bfloat162_rn(0.5f / 0.596f);
+  __nv_bfloat162 y = __hmul2(x, __hfma2(*reinterpret_cast<__nv_bfloat162*>(&tu), c, c));
+#else
+  __half2 x = __hmul2(*reinterpret_cast<__half2*>(&x2), __float2half2_rn(scale));
+  __half2 h = __hmul2(x, __float2half2_rn(0.5f));
+  uint32_t hu = *reinterpret_cast<uint32_t*>(&h), tu;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(hu));
+  const __half2 c = __float2half2_rn(0.5f / 0.596f);
+  __half2 y = __hmul2(x, __hfma2(*reinterpret_cast<__half2*>(&tu), c, c));
+#endif
+  return *reinterpret_cast<uint32_t*>(&y);
 }
 
 // Byte offset of 16-byte unit `u` (0..7) of a 128-byte row in a SWIZZLE_128B sub-tile.
@@ -204,6 +229,7 @@ __device__ __forceinline__ void epi_f32_16(const ConvKernelParams& p, uint32_t t
 // loads and drops the stores.
 __device__ __forceinline__ int tile_of(const ConvKernelParams& p, int q, uint32_t rank) {
   if (!p.pair) return q;
+  if (p.n_tiles == 1) return 2 * q + static_cast<int>(rank);
   const int mq = q / p.n_tiles;
   return (2 * mq + static_cast<int>(rank)) * p.n_tiles + (q - mq * p.n_tiles);
 }
@@ -777,6 +803,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
         // ---- pass R: pixel-norm statistic of the residual row (VB_RES_PIXNORM)
         float res_scale = p.res_a;
+        if (res_mode == VB_RES_SCALED) res_scale = p.res_a * __ldg(p.res_rnorm + (valid ? pix : 0));
         if (res_mode == VB_RES_PIXNORM) {
           float ss = 0.f;
           for (int c = 0; c < chunks; ++c) {
@@ -789,6 +816,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           ss += xchg[0][half ^ 1][row];
           res_scale = p.res_a / (1e-4f + sqrtf(ss) * p.inv_sqrt_c);
         }
+
+        // modulation row of this (image, column block): fetched ahead of the accumulator wait, the next chunk's while the
+        // current one is packed and stored (L2 latency off the per-tile critical path)
+        float4 mreg[8];
+        auto mod_fetch = [&](int c) {
+          const float4* m = reinterpret_cast<const float4*>(p.mod + static_cast<size_t>(valid ? n : 0) * p.mod_stride + t.col0 +
+                                                            c * 64 + half * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mreg[j] = __ldg(m + j);
+        };
+        if (modsilu) mod_fetch(0);
 
         mbar_wait(&tmem_full[buf], bphase);
         if (leader && it == 0) VB_TS(4);
@@ -811,16 +849,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               if (lane == 0) acc_release(buf);
             }
             const int col = t.col0 + c * 64 + half * 32;
+            // conv_res0 (modulation + mp_silu, nothing else): the activation is applied to the packed 16-bit value
+            const bool mod_pk = modsilu && !has_res && !needs_norm && p.out_f32 == nullptr && !(p.flags & VB_F_CLIP);
             if (modsilu) {
-              const float4* m = reinterpret_cast<const float4*>(p.mod + static_cast<size_t>(valid ? n : 0) * p.mod_stride + col);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 mm = __ldg(m + j);
-                v[4 * j + 0] = mp_silu_fast(v[4 * j + 0] * mm.x);
-                v[4 * j + 1] = mp_silu_fast(v[4 * j + 1] * mm.y);
-                v[4 * j + 2] = mp_silu_fast(v[4 * j + 2] * mm.z);
-                v[4 * j + 3] = mp_silu_fast(v[4 * j + 3] * mm.w);
+                const float4 mm = mreg[j];
+                if (mod_pk) {
+                  v[4 * j + 0] *= mm.x;
+                  v[4 * j + 1] *= mm.y;
+                  v[4 * j + 2] *= mm.z;
+                  v[4 * j + 3] *= mm.w;
+                } else {
+                  v[4 * j + 0] = mp_silu_fast(v[4 * j + 0] * mm.x);
+                  v[4 * j + 1] = mp_silu_fast(v[4 * j + 1] * mm.y);
+                  v[4 * j + 2] = mp_silu_fast(v[4 * j + 2] * mm.z);
+                  v[4 * j + 3] = mp_silu_fast(v[4 * j + 3] * mm.w);
+                }
               }
+              if (c + 1 < chunks) mod_fetch(c + 1);
             }
             if (has_res) {
 #pragma unroll
@@ -852,6 +899,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             uint32_t r16[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) r16[j] = pack_op2_nosat(v[2 * j], v[2 * j + 1]);
+            if (mod_pk) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r16[j] = mp_silu_pk(r16[j], 1.0f);
+            }
             if (needs_norm) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) keep[c][j] = r16[j];
@@ -865,10 +916,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                   if (kind == VB_OUT_RAW) {
                     o = make_uint4(r16[4 * j], r16[4 * j + 1], r16[4 * j + 2], r16[4 * j + 3]);
                   } else {
-                    o.x = pack_sat2(mp_silu_fast(v[8 * j + 0] * scale), mp_silu_fast(v[8 * j + 1] * scale));
-                    o.y = pack_sat2(mp_silu_fast(v[8 * j + 2] * scale), mp_silu_fast(v[8 * j + 3] * scale));
-                    o.z = pack_sat2(mp_silu_fast(v[8 * j + 4] * scale), mp_silu_fast(v[8 * j + 5] * scale));
-                    o.w = pack_sat2(mp_silu_fast(v[8 * j + 6] * scale), mp_silu_fast(v[8 * j + 7] * scale));
+                    o.x = mp_silu_pk(r16[4 * j + 0], scale);
+                    o.y = mp_silu_pk(r16[4 * j + 1], scale);
+                    o.z = mp_silu_pk(r16[4 * j + 2], scale);
+                    o.w = mp_silu_pk(r16[4 * j + 3], scale);
                   }
                   *reinterpret_cast<uint4*>(srow + swz(half * 4 + j, row)) = o;
                 }
@@ -888,6 +939,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           named_bar_sync(kPairBarrier + quad, 64);
           ssv += xchg[1][half ^ 1][row];
           const float inv_v = 1.0f / (1e-4f + sqrtf(ssv) * p.inv_sqrt_c);
+          if (p.out_rnorm != nullptr && half == 0 && valid) p.out_rnorm[pix] = inv_v;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             if (c < chunks) {
@@ -898,9 +950,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                   uint32_t o[4];
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    const float2 x = unpack_op2(keep[c][4 * j + e]);
-                    const float a = x.x * inv_v, b = x.y * inv_v;
-                    o[e] = kind == VB_OUT_NORM ? pack_sat2(a, b) : pack_sat2(mp_silu_fast(a), mp_silu_fast(b));
+                    if (kind == VB_OUT_NORM) {
+                      const float2 x = unpack_op2(keep[c][4 * j + e]);
+                      o[e] = pack_sat2(x.x * inv_v, x.y * inv_v);
+                    } else {
+                      o[e] = mp_silu_pk(keep[c][4 * j + e], inv_v);
+                    }
                   }
                   *reinterpret_cast<uint4*>(srow + swz(half * 4 + j, row)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
@@ -954,11 +1009,11 @@ static Variant g_variants[] = {
     VB_VARIANT(1, 1, 0, VB_OUT_RAW, VB_OUT_SILU, 0),
     VB_VARIANT(1, 1, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, VB_OUT_SILU),
     VB_VARIANT(1, 1, 0, VB_OUT_RAW, VB_OUT_SILU, VB_OUT_SILU),
-    VB_VARIANT(1, 2, 0, VB_OUT_RAW, 0, 0),                               // ... with the residual pixel-norm recomputed
-    VB_VARIANT(1, 2, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, 0),
-    VB_VARIANT(1, 2, 0, VB_OUT_RAW, VB_OUT_SILU, 0),
-    VB_VARIANT(1, 2, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, VB_OUT_SILU),
-    VB_VARIANT(1, 2, 0, VB_OUT_RAW, VB_OUT_SILU, VB_OUT_SILU),
+    VB_VARIANT(1, 3, 0, VB_OUT_RAW, 0, 0),                               // ... with the residual scaled per pixel (fused pixel-norm;
+    VB_VARIANT(1, 3, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, 0),                //     VB_RES_PIXNORM itself runs the generic epilogue)
+    VB_VARIANT(1, 3, 0, VB_OUT_RAW, VB_OUT_SILU, 0),
+    VB_VARIANT(1, 3, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, VB_OUT_SILU),
+    VB_VARIANT(1, 3, 0, VB_OUT_RAW, VB_OUT_SILU, VB_OUT_SILU),
     VB_VARIANT(1, -1, -1, -1, -1, -1),                                   // generic staged epilogue (must stay last)
 };
 #undef VB_VARIANT
@@ -1076,6 +1131,8 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
   p.bn = kBlockM / (p.bw * p.bh);
   p.tiles_x = d->W / p.bw;
   p.tiles_y = d->H / p.bh;
+  for (p.tx_shift = 0; (1 << p.tx_shift) < p.tiles_x; ++p.tx_shift) {}
+  for (p.ty_shift = 0; (1 << p.ty_shift) < p.tiles_y; ++p.ty_shift) {}
   const int tiles_nb = (d->B + p.bn - 1) / p.bn;
   p.n_tiles = d->cout_pad / d->block_n;
   p.total_tiles = p.tiles_x * p.tiles_y * tiles_nb * p.n_tiles;
@@ -1101,6 +1158,8 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
   p.mod_stride = d->mod_stride;
   p.out_f32 = d->out_f32;
   p.ld_f32 = d->ld_f32;
+  p.out_rnorm = d->out_rnorm;
+  p.res_rnorm = d->res_rnorm;
   const float t = d->res_t;
   const float inv = 1.0f / sqrtf((1.f - t) * (1.f - t) + t * t);
   p.res_a = (1.f - t) * inv;
@@ -1150,7 +1209,8 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
     }
     staged = p.nslots > 0;
     p.res_mode = d->res_mode;
-    VB_REQUIRE_L(d->res_mode >= VB_RES_NONE && d->res_mode <= VB_RES_PIXNORM, "vb_conv: bad res_mode");
+    VB_REQUIRE_L(d->res_mode >= VB_RES_NONE && d->res_mode <= VB_RES_SCALED, "vb_conv: bad res_mode");
+    VB_REQUIRE_L((d->res_mode == VB_RES_SCALED) == (d->res_rnorm != nullptr), "vb_conv: res_rnorm and VB_RES_SCALED must come together");
     VB_REQUIRE_L((d->res_mode != VB_RES_NONE) == (d->res != nullptr), "vb_conv: res and res_mode must come together");
     VB_REQUIRE_L(p.nslots > 0 || d->out_f32 != nullptr, "vb_conv: no output tensor");
     if (staged) {
@@ -1160,6 +1220,7 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
       VB_REQUIRE_L(d->res_mode == VB_RES_NONE && !(d->flags & (VB_F_MODSILU | VB_F_CLIP)) && d->ld_f32 % 4 == 0,
                    "vb_conv: the fp32-only epilogue is plain (no residual/modulation/clip)");
     }
+    VB_REQUIRE_L(d->out_rnorm == nullptr || needs_norm, "vb_conv: out_rnorm needs a NORM output kind");
     if (needs_norm || d->res_mode == VB_RES_PIXNORM)
       VB_REQUIRE_L(p.n_tiles == 1, "vb_conv: pixel-norm fusion needs the whole channel extent in one tile (cout_pad %d, block_n %d)",
                    d->cout_pad, d->block_n);

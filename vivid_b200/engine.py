@@ -37,13 +37,14 @@ class Act:
         self.raw = None       # block output (residual stream / GEMM operand)
         self.norm = None      # pixel_norm(raw)
         self.nsilu = None     # mp_silu(pixel_norm(raw))
+        self.rnorm = None     # fp32 per-pixel 1/(eps + rms(raw)), written next to nsilu (viewed as 2 x 16-bit per pixel)
         self.silu = {}        # scale -> mp_silu(scale * raw)
         self.is_skip = False
         self.is_feature = False
 
     def tensors(self, keep_raw=False):
         out = [] if keep_raw else [self.raw]
-        return out + [self.norm, self.nsilu] + list(self.silu.values())
+        return out + [self.norm, self.nsilu, self.rnorm] + list(self.silu.values())
 
 
 _DT = {torch.float32: L.VB_F32, torch.float16: L.VB_F16, torch.bfloat16: L.VB_BF16}
@@ -152,7 +153,7 @@ class Plan:
 
     def conv(self, x, w, B, R, cin_pad, cout, taps, *, x2=None, cin2_pad=0, cout_pad=None, flags=0, mod=None,
              mod_stride=0, res=None, res_mode=L.VB_RES_NONE, res_t=0.3, clip=None, outs=(), out_f32=None, qkv=None,
-             k_real=None):
+             k_real=None, out_rnorm=None, res_rnorm=None):
         """outs: sequence of (tensor, kind, scale)."""
         cout_pad = cout_pad or _pad(cout, 16)
         fullrow = res_mode == L.VB_RES_PIXNORM or any(k >= L.VB_OUT_NORM for _, k, _ in outs)
@@ -163,7 +164,7 @@ class Plan:
         if clip is not None:
             flags |= L.VB_F_CLIP
         d = L.ConvDesc(x=x.data_ptr(), x2=L.ptr(x2), w=w.data_ptr(), mod=mod if isinstance(mod, int) else L.ptr(mod),
-                       res=L.ptr(res), out_f32=L.ptr(out_f32), B=B, H=R, W=R, cin_pad=cin_pad, cin2_pad=cin2_pad,
+                       res=L.ptr(res), out_f32=L.ptr(out_f32), out_rnorm=L.ptr(out_rnorm), res_rnorm=L.ptr(res_rnorm), B=B, H=R, W=R, cin_pad=cin_pad, cin2_pad=cin2_pad,
                        cout_pad=cout_pad, taps=taps, block_n=bn, epi_mode=L.VB_EPI_QKVNORM if qkv else L.VB_EPI_PLAIN,
                        flags=flags, mod_stride=mod_stride, ld_f32=cout_pad, res_mode=res_mode, res_t=res_t,
                        clip=clip if clip is not None else 0.0)
@@ -292,6 +293,8 @@ class Plan:
                     out.silu[scale] = t
                 else:
                     setattr(out, attr, t)
+                if attr == "nsilu":          # the consumer's residual scale travels with it (VB_RES_SCALED)
+                    out.rnorm = self.act(out.B * out.R * out.R, 2)
                 outs.append((t, kind, scale))
             return outs
 
@@ -302,11 +305,13 @@ class Plan:
             out.is_feature = collect_features and s.heads > 0
             R, Cc = s.res, s.cout
             temps, popped_skip = [], None
+            res_rnorm = None
 
             if s.kind == "conv":
                 # x_in holds the im2col'd 3x3 neighbourhood (vb_precond_in, im2col=1): the first conv is a K=64 1x1 GEMM
                 w = self.prep_weight(mod_.weight.detach().reshape(Cc, s.cin * 9, 1, 1))
-                self.conv(x_in, w, B, R, 64, Cc, 1, outs=alloc_outs(out, want(i)), k_real=9 * s.cin)
+                outs = alloc_outs(out, want(i))
+                self.conv(x_in, w, B, R, 64, Cc, 1, outs=outs, k_real=9 * s.cin, out_rnorm=out.rnorm)
                 cur = out
                 skips.append(out)
                 continue
@@ -335,7 +340,7 @@ class Plan:
                         self.eltwise(L.VB_EW_PIXNORM, tmp, B, R, Cc, out=base, out_silu=a0)
                     res, res_mode = base, L.VB_RES_PLAIN
                 elif cur.nsilu is not None:          # pixel-norm fused on both sides
-                    a0, res, res_mode = cur.nsilu, cur.raw, L.VB_RES_PIXNORM
+                    a0, res, res_mode, res_rnorm = cur.nsilu, cur.raw, L.VB_RES_SCALED, cur.rnorm
                 else:
                     base, a0 = self.a16(B, R, Cc), self.a16(B, R, Cc)
                     temps += [base, a0]
@@ -374,12 +379,13 @@ class Plan:
             w1 = self.prep_weight(mod_.conv_res1.weight)
             clip = mod_.clip_act
             if s.heads == 0:
-                self.conv(y0, w1, B, R, Cc, Cc, 9, res=res, res_mode=res_mode, res_t=mod_.res_balance, clip=clip,
-                          outs=alloc_outs(out, want(i)))
+                outs = alloc_outs(out, want(i))
+                self.conv(y0, w1, B, R, Cc, Cc, 9, res=res, res_mode=res_mode, res_rnorm=res_rnorm, res_t=mod_.res_balance,
+                          clip=clip, outs=outs, out_rnorm=out.rnorm)
             else:
                 xr = self.a16(B, R, Cc)
                 temps.append(xr)
-                self.conv(y0, w1, B, R, Cc, Cc, 9, res=res, res_mode=res_mode, res_t=mod_.res_balance,
+                self.conv(y0, w1, B, R, Cc, Cc, 9, res=res, res_mode=res_mode, res_rnorm=res_rnorm, res_t=mod_.res_balance,
                           outs=[(xr, L.VB_OUT_RAW, 1.0)])
                 S, D, h = R * R, s.head_dim, s.heads
                 nseg = feat_seg if s.xattn else 0
@@ -402,8 +408,9 @@ class Plan:
                 # unconditional model: x_attn_kv(0) == 0 -> the S*nseg zero keys are accounted for analytically
                 self.attention(q, k, v, y, B, h, S, sk, D, S * nseg if zero_feature_keys else 0)
                 wp = self.prep_weight(mod_.attn_proj.weight)
+                outs = alloc_outs(out, want(i))
                 self.conv(y, wp, B, R, Cc, Cc, 1, res=xr, res_mode=L.VB_RES_PLAIN, res_t=mod_.attn_balance, clip=clip,
-                          outs=alloc_outs(out, want(i)))
+                          outs=outs, out_rnorm=out.rnorm)
             if out.is_feature:
                 feats_out.append(out)
             if s.group == "enc":
