@@ -230,7 +230,8 @@ def test_qkv_epilogue(env, B, R, ch, heads, D, parts, seg_div, bn):
 
 @pytest.mark.parametrize("B,h,sq,sk,D,zk", [(2, 4, 1024, 2048, 64, 0), (3, 8, 64, 128, 64, 0), (2, 8, 64, 64, 64, 64),
                                            (2, 2, 16, 48, 64, 0), (1, 8, 1024, 2048, 32, 0), (2, 6, 256, 768, 64, 0),
-                                           (1, 4, 16, 16, 32, 16)])
+                                           (1, 4, 16, 16, 32, 16), (2, 4, 256, 256, 64, 512), (40, 6, 256, 512, 64, 0),
+                                           (1, 1, 128, 128, 64, 0)])
 def test_fused_attention(env, B, h, sq, sk, D, zk):
     """vb_attn vs softmax(q k^T / sqrt(D)) v on normalised q,k,v, incl. analytic zero keys and ragged lengths."""
     L, lib, dev = env

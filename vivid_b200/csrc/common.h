@@ -44,6 +44,8 @@ void conv_free(ConvLaunch* l);
 double conv_flops(const ConvLaunch* l);
 
 int attn_launch(const vb_attn_desc* d, cudaStream_t s);
+bool attn_tc_supported(const vb_attn_desc* d);
+int attn_tc_launch(const vb_attn_desc* d, cudaStream_t s);
 int eltwise_launch(const vb_ew_desc* d, cudaStream_t s);
 int embed_launch(const vb_emb_desc* d, cudaStream_t s);
 int precond_in_launch(const vb_precond_in_desc* d, cudaStream_t s);
