@@ -203,9 +203,20 @@ def run_ours(args):
     conv_n = agg["conv3"]["launches"] + agg["conv1"]["launches"]
     total_ms = sum(a["ms"] for a in agg.values())
     achieved = conv_fl / (conv_ms / 1e3) / 1e12
+    conv_by = agg["conv3"]["bytes"] + agg["conv1"]["bytes"]
+    traffic, traffic_src = None, None
+    try:        # DRAM bytes per conv launch from the committed ncu launch list of one call per net at this batch
+        with open(os.path.join(ROOT, "profiles", f"r01_launches_B{B}.json")) as f:
+            tj = json.load(f)
+        if tj.get("batch") == B:
+            traffic, traffic_src = round(tj["dram_bytes_per_launch"]), "profiles/r01_launches_B%d.json: %s" % (B, tj["source"])
+    except Exception:
+        pass
     roofline = dict(bound="tensor", kernel="conv_gemm_kernel (tcgen05 implicit-GEMM 3x3/1x1 conv)", achieved=round(achieved, 1),
                     peak=pk["tflops"], unit="TFLOP/s", frac=round(achieved / pk["tflops"], 4),
-                    peak_source=f"{pk['source']} bf16 sustained (kernel timed inside a long step)", traffic=None,
+                    peak_source=f"{pk['source']} bf16 sustained (kernel timed inside a long step)", traffic=traffic,
+                    traffic_unit="bytes per launch (dram read+write, ncu)", traffic_source=traffic_src,
+                    alg_bytes_per_launch=round(conv_by / conv_n),
                     launches_per_step=conv_n, avg_launch_us=round(conv_ms / conv_n * 1e3, 2),
                     share_of_step=round(conv_ms / total_ms, 4),
                     alg_flops_per_step=conv_fl)
