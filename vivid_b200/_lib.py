@@ -32,7 +32,7 @@ class ConvDesc(C.Structure):
                 ("cout_pad", i32), ("taps", i32), ("block_n", i32), ("epi_mode", i32), ("flags", i32),
                 ("mod_stride", i32), ("ld_f32", i32), ("res_mode", i32), ("out_kind", i32 * 3), ("head_dim", i32),
                 ("parts", i32), ("seg_div", i32), ("part_seq", i32 * 3), ("part_off", i32 * 3),
-                ("out_scale", f32 * 3), ("res_t", f32), ("clip", f32)]
+                ("out_scale", f32 * 3), ("res_t", f32), ("clip", f32), ("tune", i32)]
 
 
 class AttnDesc(C.Structure):

@@ -65,6 +65,7 @@ struct ConvKernelParams {
   int bw, bh, bn;
   int tiles_x, tiles_y, tx_shift, ty_shift;
   int n_tiles, total_tiles;
+  int tune_tap;         // plan-time tuning: 0 auto, 1 no shared haloed boxes, 2 haloed boxes wherever they fit
   int pair, total_q;    // CTA-pair mode (cluster of 2, cta_group::2 MMA); work items per CTA / per pair
   int taps, kc_a, kc_b;
   int block_n;
@@ -1054,7 +1055,8 @@ static int encode_act_map(CUtensorMap* map, const void* base, int C, int W, int 
 // Choose the main-loop shared-memory layout inside `budget` bytes.  Returns false if not even the minimum fits
 // (or, with want_good, if only a shallow pipeline would fit — the caller then retries with a smaller epilogue ring).
 static bool plan_mainloop(ConvKernelParams& p, int budget, bool want_good) {
-  static const int forced = getenv("VB_TAP_MODE") ? atoi(getenv("VB_TAP_MODE")) : -1;    // -1 auto, 0 off (A/B testing)
+  static const int env_forced = getenv("VB_TAP_MODE") ? atoi(getenv("VB_TAP_MODE")) : -1;    // -1 auto, 0 off (A/B testing)
+  const int forced = p.tune_tap == 1 ? 0 : (p.tune_tap == 2 ? 2 : env_forced);
   p.tap_mode = 0;
   const int kct = p.kc_a + p.kc_b;
   if (p.taps == 9 && p.bn == 1 && forced != 0) {
@@ -1140,7 +1142,9 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
   p.kc_a = d->cin_pad / 64;
   p.kc_b = d->cin2_pad / 64;
   p.block_n = d->block_n;
-  static const int forced_pair = getenv("VB_PAIR") ? atoi(getenv("VB_PAIR")) : -1;      // -1 auto, 0 off, 1 on (A/B testing)
+  static const int env_pair = getenv("VB_PAIR") ? atoi(getenv("VB_PAIR")) : -1;      // -1 auto, 0 off, 1 on (A/B testing)
+  const int forced_pair = (d->tune & 3) == 1 ? 0 : ((d->tune & 3) == 2 ? 1 : env_pair);
+  p.tune_tap = (d->tune >> 2) & 3;
   const int m_tiles = p.tiles_x * p.tiles_y * tiles_nb;
   // each CTA's half of the weight tile must be whole 8-row swizzle groups, and there must be two M tiles to pair up
   const bool pair_possible = d->block_n % 32 == 0 && m_tiles >= 2;

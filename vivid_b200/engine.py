@@ -20,6 +20,8 @@ Dataflow per block (reference Block.forward, training/models.py:165-206).  `raw`
 import ctypes as C
 import math
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -48,6 +50,8 @@ class Act:
 
 
 _DT = {torch.float32: L.VB_F32, torch.float16: L.VB_F16, torch.bfloat16: L.VB_BF16}
+AUTOTUNE = os.environ.get("VB_AUTOTUNE", "1") != "0"    # plan-time layout tuning of the conv layers (see Plan._tune_conv)
+_TUNE_CACHE = {}
 FULLROW_MAX = 256          # widest channel count one GEMM tile (and TMEM accumulator buffer) can hold
 
 
@@ -151,6 +155,42 @@ class Plan:
                 best, best_cost = n, cost
         return best
 
+    def _tune_conv(self, d, candidates):
+        """Plan-time autotuning of one conv layer: times every legal (block_n, single|pair) candidate on the layer's own
+        buffers (three batches of four launches behind a blocker, best batch) and returns the fastest; the first
+        candidate is the heuristic choice and keeps its place unless another is >3 % faster.  The choice changes only
+        the tiling, never the arithmetic of an output element beyond fp32 summation order."""
+        stream = torch.cuda.current_stream(self.device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = None
+        for bn, tune in candidates:
+            d.block_n, d.tune = bn, tune
+            plan = C.c_void_p()
+            L.check(self.lib.vb_plan_create(C.byref(plan)), "vb_plan_create")
+            try:
+                if self.lib.vb_plan_add_conv(plan, C.byref(d)) != 0:
+                    continue                       # not a legal layout for this layer (shared-memory budget, tiling)
+                for _ in range(2):
+                    L.check(self.lib.vb_plan_run(plan, 0, -1, stream.cuda_stream), "vb_plan_run")
+                t, reps = float("inf"), 4
+                for batch in range(4):
+                    L.check(self.lib.vb_spin(80 if batch == 0 else 20 * reps, stream.cuda_stream), "vb_spin")
+                    e0.record(stream)
+                    for _ in range(reps):
+                        L.check(self.lib.vb_plan_run(plan, 0, -1, stream.cuda_stream), "vb_plan_run")
+                    e1.record(stream)
+                    stream.synchronize()
+                    if batch > 0:
+                        t = min(t, e0.elapsed_time(e1) / reps)
+                    else:           # the first batch only sizes the others: ~0.5 ms of device time each
+                        reps = int(min(32, max(4, 0.5 / max(e0.elapsed_time(e1) / reps, 1e-3))))
+                if best is None or t < best[0] * 0.97:
+                    best = (t, bn, tune)
+            finally:
+                self.lib.vb_plan_destroy(plan)
+        assert best is not None, "no legal conv layout"
+        return best[1], best[2]
+
     def conv(self, x, w, B, R, cin_pad, cout, taps, *, x2=None, cin2_pad=0, cout_pad=None, flags=0, mod=None,
              mod_stride=0, res=None, res_mode=L.VB_RES_NONE, res_t=0.3, clip=None, outs=(), out_f32=None, qkv=None,
              k_real=None, out_rnorm=None, res_rnorm=None):
@@ -164,7 +204,8 @@ class Plan:
         if clip is not None:
             flags |= L.VB_F_CLIP
         d = L.ConvDesc(x=x.data_ptr(), x2=L.ptr(x2), w=w.data_ptr(), mod=mod if isinstance(mod, int) else L.ptr(mod),
-                       res=L.ptr(res), out_f32=L.ptr(out_f32), out_rnorm=L.ptr(out_rnorm), res_rnorm=L.ptr(res_rnorm), B=B, H=R, W=R, cin_pad=cin_pad, cin2_pad=cin2_pad,
+                       res=L.ptr(res), out_f32=L.ptr(out_f32), out_rnorm=L.ptr(out_rnorm), res_rnorm=L.ptr(res_rnorm), B=B,
+                       H=R, W=R, cin_pad=cin_pad, cin2_pad=cin2_pad,
                        cout_pad=cout_pad, taps=taps, block_n=bn, epi_mode=L.VB_EPI_QKVNORM if qkv else L.VB_EPI_PLAIN,
                        flags=flags, mod_stride=mod_stride, ld_f32=cout_pad, res_mode=res_mode, res_t=res_t,
                        clip=clip if clip is not None else 0.0)
@@ -179,6 +220,18 @@ class Plan:
                 d.part_out[j] = qkv["out"][j].data_ptr()
                 d.part_seq[j] = qkv["seq"][j]
                 d.part_off[j] = qkv["off"][j]
+        if AUTOTUNE:
+            key = (B, R, cin_pad, cin2_pad, cout_pad, taps, flags, res_mode, tuple(k for _, k, _ in outs), out_f32 is not None,
+                   (qkv["D"], qkv["parts"], qkv.get("seg_div", 1)) if qkv else None, mod is not None)
+            if key not in _TUNE_CACHE:
+                ns = [bn] if fullrow else [bn] + [n for n in (256, 192, 128, 64, 32, 16)
+                                                  if n != bn and cout_pad % n == 0 and n % multiple == 0]
+                cands = [(n, t | (tap << 2)) for n in ns for tap in ((0, 1, 2) if taps == 9 else (0,)) for t in (0, 1, 2)]
+                _TUNE_CACHE[key] = self._tune_conv(d, cands)
+                if os.environ.get("VB_TUNE_LOG"):
+                    print("tune", key[:8], "heuristic bn", ns[0], "->", _TUNE_CACHE[key], flush=True)
+            bn, d.tune = _TUNE_CACHE[key]
+            d.block_n = bn
         L.check(self.lib.vb_plan_add_conv(self.handle, C.byref(d)), "vb_plan_add_conv")
         fl = 2.0 * B * R * R * cout * (k_real if k_real is not None else taps * (cin_pad + cin2_pad))
         self.alg_flops += fl
