@@ -9,7 +9,7 @@
 #include "../../vivid_b200/csrc/ptx.cuh"
 using namespace vb;
 
-__global__ void __launch_bounds__(128) rate_kernel(long long* out, int N, int iters, int mode, int r0, int commit_every) {
+__global__ void __launch_bounds__(128) rate_kernel(long long* out, int N, int iters, int mode, int r0, int commit_every, int coff = 0) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t done, dummy[8];
   __shared__ uint32_t slot;
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(128) rate_kernel(long long* out, int N, int it
   fence_proxy_async();
   if (warp == 0) { tmem_alloc(&slot, 512); tmem_relinquish(); }
   tc_fence_before(); __syncthreads(); tc_fence_after();
-  const uint32_t tm = slot;
+  const uint32_t tm = slot + coff;
   if (warp == 1) {
     if (elect_one_sync()) {
       const uint32_t idesc = umma_idesc_op(128, N);
@@ -57,7 +57,7 @@ int main() {
   long long* d; cudaMalloc(&d, 148 * 8);
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const int iters = 2000;
-  const int Ns[] = {32, 64, 128, 256};
+  const int Ns[] = {64, 128, 192, 256};
   for (int N : Ns)
     for (int mode = 0; mode < 2; ++mode)
       for (int r0 = 0; r0 < 2; ++r0)
@@ -70,5 +70,13 @@ int main() {
           printf("N=%3d desc=%s window_row=%d commit_every=%d : %.1f .. %.1f cycles per MMA (floor %d)\n", N, mode ? "add " : "calc", r0, ce,
                  (double)mn / (iters * 4), (double)mx / (iters * 4), N / 2);
         }
+  // accumulator column offset (the row-rolling conv layout places N=192 accumulators at multiples of 64 columns)
+  for (int coff : {0, 64, 128, 192, 256, 320}) {
+    rate_kernel<<<148, 128, 100 * 1024>>>(d, 192, iters, 1, 0, 0, coff);
+    cudaDeviceSynchronize();
+    long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    long long mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+    printf("N=192 accumulator at column %3d : %.1f cycles per MMA\n", coff, (double)mx / (iters * 4));
+  }
   return 0;
 }

@@ -65,6 +65,15 @@ struct ConvKernelParams {
   int bw, bh, bn;
   int tiles_x, tiles_y, tx_shift, ty_shift;
   int n_tiles, total_tiles;
+  // rowroll != 0: input-stationary 3x3 for 64 -> 64 channels on rows of >= 128 pixels.  The CTA walks down a strip of
+  // strip_rows output rows; every INPUT row is loaded once (one haloed box) and multiplied, with the three dx windows,
+  // against [W(dy=+1) | W(dy=0) | W(dy=-1)] (N = 192, resident): its three 64-column result blocks belong to the output
+  // rows above, at and below it, which occupy CONSECUTIVE 64-column slots of a ring of eight TMEM slots — so the dy sum
+  // happens in the accumulator addressing, each activation row is read from shared memory 3 times instead of 9, and
+  // the MMA runs at its N = 192 rate instead of the shared-memory-bound N = 64 one.  Slots are cleared by the epilogue
+  // when it has read them; every MMA accumulates.
+  int rowroll, strip_rows, strip_shift, chunk_mask, chunk_shift;
+  uint32_t idesc128, idesc64;
   int tune_tap;         // plan-time tuning: 0 auto, 1 no shared haloed boxes, 2 haloed boxes wherever they fit
   int pair, total_q;    // CTA-pair mode (cluster of 2, cta_group::2 MMA); work items per CTA / per pair
   int taps, kc_a, kc_b;
@@ -235,6 +244,18 @@ __device__ __forceinline__ int tile_of(const ConvKernelParams& p, int q, uint32_
   return (2 * mq + static_cast<int>(rank)) * p.n_tiles + (q - mq * p.n_tiles);
 }
 
+// rowroll: output row i (0..strip_rows-1; -2,-1 address the two leading garbage blocks) of strip q.  Strips are
+// numbered x tile fastest, then chunk of rows, then image.
+__device__ __forceinline__ TileCoord strip_tile(const ConvKernelParams& p, int q, int i) {
+  TileCoord t;
+  t.x0 = (q & (p.tiles_x - 1)) * p.bw;
+  const int t2 = q >> p.tx_shift;
+  t.y0 = ((t2 & p.chunk_mask) << p.strip_shift) + i;
+  t.n0 = t2 >> p.chunk_shift;
+  t.col0 = 0;
+  return t;
+}
+
 // ------------------------------------------------------------------------------------------------ single-thread roles
 // The TMA producers and the MMA issuer are ONE thread each; a lone warp issues a dependent instruction every ~5 cycles,
 // so their instruction streams are the pipeline's clock: the first version (one producer thread, barrier addresses
@@ -293,6 +314,11 @@ __device__ __forceinline__ void tma_act(const CUtensorMap* m, uint32_t bar, uint
         "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_act(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 template <bool PAIR>
 __device__ __forceinline__ void tma_wgt(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1) {
   if (PAIR)
@@ -323,7 +349,30 @@ __device__ __forceinline__ void producer_act(const ConvKernelParams& p, const Ro
   const bool lead = c.rank == 0;
   const uint32_t mul = PAIR ? 2u : 1u;
   uint32_t slot = 0, phase = 0;
-  if (p.tap_mode != 0) {
+  if (p.rowroll) {
+    if (p.dbg & 4) return;                                  // ablation: no operand loads (MMA on stale shared memory)
+    const uint32_t tx = static_cast<uint32_t>(p.a_tx_bytes);
+    const uint32_t nslots = p.a_slots, slot_bytes = p.a_slot_bytes;
+    uint32_t dst = c.smem;
+    for (int q = c.q0; q < p.total_q; q += c.qstride) {
+      const TileCoord t = strip_tile(p, q, 0);
+      constexpr int kAhead = 8;                             // rows pulled into L2 ahead of the shared-memory ring: every
+      for (int j = 0; j < kAhead; ++j)                      // row is read from HBM exactly once, so without this the ring
+        tma_prefetch_act(map_a, 0, t.x0 - 1, t.y0 - 1 + j, t.n0);      // (5-6 rows) has to cover the full DRAM latency
+      for (int j = 0; j < p.strip_rows + 2; ++j) {          // input rows y0-1 .. y0+strip_rows, each loaded ONCE
+        if (j + kAhead < p.strip_rows + 2) tma_prefetch_act(map_a, 0, t.x0 - 1, t.y0 - 1 + j + kAhead, t.n0);
+        mbar_wait_addr(c.empty + slot * 8, phase ^ 1u);
+        mbar_expect_tx_addr(c.full + slot * 8, tx);
+        tma_act<false>(map_a, c.full + slot * 8, dst, 0, t.x0 - 1, t.y0 - 1 + j, t.n0);
+        dst += slot_bytes;
+        if (++slot == nslots) {
+          slot = 0;
+          phase ^= 1u;
+          dst = c.smem;
+        }
+      }
+    }
+  } else if (p.tap_mode != 0) {
     const uint32_t tx = static_cast<uint32_t>(p.a_tx_bytes) * mul;
     const uint32_t nslots = p.a_slots, slot_bytes = p.a_slot_bytes;
     uint32_t dst = c.smem;
@@ -391,6 +440,14 @@ __device__ __forceinline__ void producer_wgt(const ConvKernelParams& p, const Ro
   const int wrow = PAIR ? static_cast<int>(c.rank) * (p.block_n >> 1) : 0;     // this CTA's rows of the weight tile
   const int kct = p.kc_a + p.kc_b;
   const uint32_t b_bytes = p.b_bytes;
+  if (p.rowroll) {
+    // B tile of window dx: rows [0,64) = W(dy=+1), [64,128) = W(dy=0), [128,192) = W(dy=-1), each a {64 k, 64 rows} box
+    mbar_expect_tx_addr(c.bfull, 9u * b_bytes);
+    for (int dx = 0; dx < 3; ++dx)
+      for (int kb = 0; kb < 3; ++kb)
+        tma_wgt<false>(map_w, c.bfull, c.smem + p.b_off + (dx * 3 + kb) * b_bytes, ((2 - kb) * 3 + dx) * kBlockK, 0);
+    return;
+  }
   if (p.tap_mode != 0) {
     if (p.b_resident) {
       const int nb = 9 * kct;
@@ -456,7 +513,70 @@ __device__ __forceinline__ void mma_role(const ConvKernelParams& p, const RoleCt
   const int kct = p.kc_a + p.kc_b;
   const uint32_t b_tile_lo = static_cast<uint32_t>(p.b_bytes) >> 4;
   int it = 0;
-  if (p.tap_mode != 0) {
+  if (p.rowroll) {
+    const uint32_t a_base = umma_desc_lo(c.smem);
+    const uint32_t a_slot_lo = static_cast<uint32_t>(p.a_slot_bytes) >> 4;
+    const uint32_t b_base = umma_desc_lo(c.smem + p.b_off);
+    const uint32_t b_dx_lo = 3u * b_tile_lo;                  // one window's 192-row weight tile
+    const uint32_t i128 = p.idesc128, i64 = p.idesc64;
+    const bool no_mma = (p.dbg & 8) != 0;                      // ablation: loads and handshakes only
+    auto mma_n = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t id) {
+      if (!no_mma) umma_f16_ss(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), id, 1u);
+    };
+    const uint32_t a_slots = p.a_slots;
+    uint32_t as = 0, aph = 0, a_lo = a_base;
+    uint32_t g = 0;                                           // input rows processed so far = first of its three slots
+    mbar_wait_addr(c.bfull, 0);
+    mbar_wait_addr(c.tmem_empty, 0);                          // slots 0 and 1 of the very first row: the initial clear
+    mbar_wait_addr(c.tmem_empty + 8, 0);
+    tc_fence_after();
+    for (int q = c.q0; q < p.total_q; q += c.qstride) {
+      for (int j = 0; j < p.strip_rows + 2; ++j, ++g) {
+        const uint32_t nb = g + 2;                            // the block this row starts: its slot must have been cleared
+        mbar_wait_addr(c.tmem_empty + (nb & 7u) * 8, (nb >> 3) & 1u);
+        if (!(p.dbg & 4)) mbar_wait_addr(c.full + as * 8, aph);
+        if (g == 0) VB_TS(2);
+        tc_fence_after();
+        const uint32_t s0 = g & 7u;
+        const uint32_t d0 = c.tmem_base + s0 * 64u;
+        // (the slot case is decided once per row: decided per MMA it cost ~35 instructions per MMA in the issuing thread)
+        if (s0 <= 5u) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) mma_n(d0, a_lo + i * 8 + 2 * k, b_base + i * b_dx_lo + 2 * k, idesc);
+          }
+        } else if (s0 == 6u) {                                // slots 6,7 then wrap to 0
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              mma_n(d0, a_lo + i * 8 + 2 * k, b_base + i * b_dx_lo + 2 * k, i128);
+              mma_n(c.tmem_base, a_lo + i * 8 + 2 * k, b_base + i * b_dx_lo + 2 * k + 2u * b_tile_lo, i64);
+            }
+          }
+        } else {                                              // slot 7 then wrap to 0,1
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              mma_n(d0, a_lo + i * 8 + 2 * k, b_base + i * b_dx_lo + 2 * k, i64);
+              mma_n(c.tmem_base, a_lo + i * 8 + 2 * k, b_base + i * b_dx_lo + 2 * k + b_tile_lo, i128);
+            }
+          }
+        }
+        umma_commit_addr<false>(c.empty + as * 8);
+        umma_commit_addr<false>(c.tmem_full + s0 * 8);        // block g has received its last contribution
+        a_lo += a_slot_lo;
+        if (++as == a_slots) {
+          as = 0;
+          aph ^= 1u;
+          a_lo = a_base;
+        }
+      }
+    }
+    VB_TS(3);
+  } else if (p.tap_mode != 0) {
     const uint32_t a_base = umma_desc_lo(c.smem);
     const uint32_t a_slot_lo = static_cast<uint32_t>(p.a_slot_bytes) >> 4;
     const uint32_t win_lo = static_cast<uint32_t>(p.win_rows) * 8u;          // rows of 128 B
@@ -578,8 +698,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t bfull_bar[kMaxBSlots];
   __shared__ __align__(8) uint64_t bempty_bar[kMaxBSlots];
-  __shared__ __align__(8) uint64_t tmem_full[2];
-  __shared__ __align__(8) uint64_t tmem_empty[2];
+  __shared__ __align__(8) uint64_t tmem_full[8];      // two accumulator buffers, or (rowroll) eight 64-column slots
+  __shared__ __align__(8) uint64_t tmem_empty[8];
   __shared__ __align__(8) uint64_t res_full[kMaxResSlots];
   __shared__ __align__(8) uint64_t res_empty[kMaxResSlots];
   __shared__ float xchg[2][2][kBlockM];     // [residual | result statistic][column half][row]
@@ -615,7 +735,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_init(&bfull_bar[s], 1);
       mbar_init(&bempty_bar[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 8; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], p.pair ? 2 * kEpiWarps : kEpiWarps);   // pair: the epilogue warps of both CTAs
     }
@@ -736,9 +856,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (has_res && leader) {
           while (res_issued < res_q + static_cast<uint32_t>(p.res_slots)) {
             const uint32_t ti = res_issued / items;                  // CTA-local index of the tile owning the item
-            const int ql = q0 + static_cast<int>(ti) * qstride;
+            const int wl = p.rowroll ? static_cast<int>(ti >> p.strip_shift) : static_cast<int>(ti);
+            const int ql = q0 + wl * qstride;
             if (ql >= p.total_q) break;
-            const TileCoord tt = decode_tile(p, tile_of(p, ql, rank));
+            const TileCoord tt = p.rowroll ? strip_tile(p, ql, static_cast<int>(ti) & (p.strip_rows - 1))
+                                           : decode_tile(p, tile_of(p, ql, rank));
             const uint32_t slot = res_issued & rmask;
             mbar_wait(&res_empty[slot], ((res_issued >> rshift) & 1u) ^ 1u);
             mbar_expect_tx(&res_full[slot], kChunkBytes);
@@ -782,20 +904,49 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (++greg == static_cast<uint32_t>(p.stg_regions)) greg = 0;
       };
 
-      for (int q = q0; q < p.total_q; q += qstride, ++it) {
-        const int buf = it & 1;
-        const uint32_t bphase = static_cast<uint32_t>(it >> 1) & 1u;
-        const TileCoord t = decode_tile(p, tile_of(p, q, rank));
+      // rowroll: clears this warp's lanes x columns of accumulator slot `col` (every MMA of that mode accumulates)
+      auto slot_clear = [&](uint32_t taddr_slot) {
+        if (p.dbg & 64) return;                 // ablation: no clearing (wrong results)
+        tmem_st32_fill(taddr_slot, 0u);
+        tmem_st_wait();
+      };
+      const int nblk = p.rowroll ? p.strip_rows + 2 : 1;            // accumulator blocks per work item
+      if (p.rowroll) {                                              // all eight slots start cleared and free
+        for (int sl = 0; sl < 8; ++sl) {
+          slot_clear(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(sl * 64 + half * 32));
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[sl]);
+        }
+      }
+      for (;; ++it) {
+        const int wi = p.rowroll ? it / nblk : it;                  // CTA-local work item (tile, or strip of rows)
+        const int jb = p.rowroll ? it - wi * nblk : 0;              // block within the strip: 0,1 carry no output row
+        const int q = q0 + wi * qstride;
+        if (q >= p.total_q) break;
+        const int buf = p.rowroll ? (it & 7) : (it & 1);
+        const uint32_t bphase = static_cast<uint32_t>(p.rowroll ? it >> 3 : it >> 1) & 1u;
+        const TileCoord t = p.rowroll ? strip_tile(p, q, jb - 2) : decode_tile(p, tile_of(p, q, rank));
         const int n = t.n0 + rn;
         const bool valid = n < p.B;
         const size_t pix = static_cast<size_t>(n) * p.H * p.W + (t.y0 + ry) * p.W + t.x0 + rx;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                               static_cast<uint32_t>(buf * kAccStride + half * 32);
+                               static_cast<uint32_t>((p.rowroll ? buf * 64 : buf * kAccStride) + half * 32);
+        if (p.rowroll && jb < 2) {                                  // partial sums of rows outside the strip: discard
+          mbar_wait(&tmem_full[buf], bphase);
+          tc_fence_after();
+          slot_clear(taddr);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) acc_release(buf);
+          continue;
+        }
         if (!(p.dbg & 1)) res_topup();
 
         if (p.dbg & 1) {
           mbar_wait(&tmem_full[buf], bphase);
           tc_fence_after();
+          if (p.rowroll) slot_clear(taddr);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) acc_release(buf);
@@ -845,6 +996,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tmem_ld32(taddr + c * 64, v);
             tmem_ld_wait();
             if (c == chunks - 1) {                  // accumulator fully read: the MMA warp may start the tile after next
+              if (p.rowroll) slot_clear(taddr);
               tc_fence_before();
               __syncwarp();
               if (lane == 0) acc_release(buf);
@@ -1143,8 +1295,12 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
   p.kc_b = d->cin2_pad / 64;
   p.block_n = d->block_n;
   static const int env_pair = getenv("VB_PAIR") ? atoi(getenv("VB_PAIR")) : -1;      // -1 auto, 0 off, 1 on (A/B testing)
-  const int forced_pair = (d->tune & 3) == 1 ? 0 : ((d->tune & 3) == 2 ? 1 : env_pair);
-  p.tune_tap = (d->tune >> 2) & 3;
+  static const int env_rowroll = getenv("VB_ROWROLL") ? atoi(getenv("VB_ROWROLL")) : 0;          // A/B testing
+  const bool want_rowroll = ((d->tune >> 4) & 3) == 1 || (env_rowroll && ((d->tune >> 4) & 3) == 0 && d->taps == 9 && p.bh == 1 &&
+                            p.bw == kBlockM && d->cin_pad == 64 && d->cin2_pad == 0 && d->block_n == 64 && d->cout_pad == 64 &&
+                            d->H % 16 == 0 && d->epi_mode == VB_EPI_PLAIN);
+  const int forced_pair = want_rowroll ? 0 : ((d->tune & 3) == 1 ? 0 : ((d->tune & 3) == 2 ? 1 : env_pair));
+  p.tune_tap = want_rowroll ? 0 : (d->tune >> 2) & 3;
   const int m_tiles = p.tiles_x * p.tiles_y * tiles_nb;
   // each CTA's half of the weight tile must be whole 8-row swizzle groups, and there must be two M tiles to pair up
   const bool pair_possible = d->block_n % 32 == 0 && m_tiles >= 2;
@@ -1296,6 +1452,21 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
     if (forced_pair == 1 && pair_possible) set_pair(1);
     VB_REQUIRE_L(plan_mainloop(p, kSmemMax, false), "vb_conv: shared memory budget exceeded");
   }
+  if (want_rowroll) {
+    VB_REQUIRE_L(d->taps == 9 && p.bh == 1 && p.bw == kBlockM && d->cin_pad == 64 && d->cin2_pad == 0 && d->block_n == 64 &&
+                     d->cout_pad == 64 && d->H % 16 == 0 && staged && p.tap_mode == 1 && p.b_resident && !p.pair,
+                 "vb_conv: the row-rolling layout needs a 3x3, 64 -> 64 channel layer on rows of >= 128 pixels");
+    p.rowroll = 1;
+    p.strip_rows = d->H % 32 == 0 ? 32 : 16;
+    for (p.strip_shift = 0; (1 << p.strip_shift) < p.strip_rows; ++p.strip_shift) {}
+    const int chunks = d->H / p.strip_rows;
+    p.chunk_mask = chunks - 1;
+    for (p.chunk_shift = 0; (1 << p.chunk_shift) < chunks; ++p.chunk_shift) {}
+    p.total_q = p.tiles_x * chunks * d->B;
+    p.idesc = umma_idesc_op(kBlockM, 192);
+    p.idesc128 = umma_idesc_op(kBlockM, 128);
+    p.idesc64 = umma_idesc_op(kBlockM, 64);
+  }
   const int main_bytes = p.tap_mode != 0 ? p.b_off + (p.b_resident ? 9 * (p.kc_a + p.kc_b) : p.b_slots) * p.b_bytes
                                          : p.num_stages * p.stage_bytes;
   p.res_off = main_bytes;
@@ -1339,7 +1510,8 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
 
   // The kernel contains cta_group::2 instructions, so the driver only accepts it in clusters of two even when the CTAs work
   // independently (pair == 0): the grid is kept even, a surplus CTA finds no work item and exits.
-  l->grid = p.pair ? std::min(2 * p.total_q, num_sms() & ~1) : std::min((p.total_tiles + 1) & ~1, num_sms() & ~1);
+  l->grid = p.pair ? std::min(2 * p.total_q, num_sms() & ~1)
+                   : std::min(((p.rowroll ? p.total_q : p.total_tiles) + 1) & ~1, num_sms() & ~1);
   l->smem_bytes = p.stg_off + (staged ? p.stg_regions * p.gslots * kChunkBytes : 0) + 1024;
   l->flops = 2.0 * d->B * d->H * d->W * static_cast<double>(d->cout_pad) * d->taps * (d->cin_pad + d->cin2_pad);
   if (!var->attr_done) {

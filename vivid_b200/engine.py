@@ -227,6 +227,8 @@ class Plan:
                 ns = [bn] if fullrow else [bn] + [n for n in (256, 192, 128, 64, 32, 16)
                                                   if n != bn and cout_pad % n == 0 and n % multiple == 0]
                 cands = [(n, t | (tap << 2)) for n in ns for tap in ((0, 1, 2) if taps == 9 else (0,)) for t in (0, 1, 2)]
+                if taps == 9 and R >= 128 and cin_pad == 64 and cin2_pad == 0 and cout_pad == 64 and not qkv and outs:
+                    cands.append((64, 1 << 4))         # row-rolling input-stationary layout (conv_gemm.cu, rowroll)
                 _TUNE_CACHE[key] = self._tune_conv(d, cands)
                 if os.environ.get("VB_TUNE_LOG"):
                     print("tune", key[:8], "heuristic bn", ns[0], "->", _TUNE_CACHE[key], flush=True)
