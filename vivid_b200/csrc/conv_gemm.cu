@@ -42,13 +42,14 @@ constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kChunkBytes = kBlockM * 128;            // one 64-column 16-bit sub-tile: 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kMaxBSlots = 12;
-constexpr int kThreads = 384;
-constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = kEpiWarps * 32;
+// Epilogue warps: PARTS per TMEM lane quadrant, each owning 64/PARTS columns of every 64-column chunk.  PARTS = 2 is the
+// default; PARTS = 4 (16 epilogue warps, four per scheduler, 16 columns per thread) is a plan-time tuning choice for the
+// epilogue-bound layers: the per-tile epilogue is a latency-bound instruction stream (IPC ~0.3 per scheduler with two
+// warps), so more, lighter warps hide it better.
 constexpr int kFirstEpiWarp = 4;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;                       // columns between the two accumulator buffers
-constexpr int kStaticSmem = 4096;                     // barriers + statistic exchange (static __shared__), rounded up
+constexpr int kStaticSmem = 5120;                     // barriers + statistic exchange (static __shared__), rounded up
 constexpr int kSmemMax = 227 * 1024 - 1024 - kStaticSmem;   // dynamic smem we allow ourselves (1 KiB alignment slack)
 constexpr int kMaxResSlots = 4;                       // residual TMA ring depth (16 KiB sub-tiles)
 constexpr int kEpiBarrier = 1;                        // named barrier of all epilogue warps
@@ -182,11 +183,12 @@ __device__ __forceinline__ uint32_t mp_silu_pk(uint32_t x2, float scale) {
 __device__ __forceinline__ int swz(int u, int row) { return (u ^ (row & 7)) << 4; }
 
 // Sum of squares of this row's 32 residual columns [half*32, half*32+32) (VB_RES_PIXNORM statistic).
-__device__ __forceinline__ float res_sumsq32(const uint8_t* rrow, int row, int half) {
+template <int U>
+__device__ __forceinline__ float res_sumsq32(const uint8_t* rrow, int row, int part) {
   float ss = 0.f;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint4 q = *reinterpret_cast<const uint4*>(rrow + swz(half * 4 + j, row));
+  for (int j = 0; j < U; ++j) {
+    const uint4 q = *reinterpret_cast<const uint4*>(rrow + swz(part * U + j, row));
     const float2 a = unpack_op2(q.x), b = unpack_op2(q.y), c = unpack_op2(q.z), d = unpack_op2(q.w);
     ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
   }
@@ -688,11 +690,15 @@ __device__ __forceinline__ bool kind_norm(int k) { return k == VB_OUT_NORM || k 
 
 // Template arguments >= 0 fix the epilogue variant at compile time; -1 reads it from the parameters (generic
 // fallback for combinations the plans never emit).  STAGED = 0 is the QKVNORM / narrow fp32 epilogue.
-template <int STAGED, int RES_T, int MOD_T, int K0_T, int K1_T, int K2_T>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int STAGED, int RES_T, int MOD_T, int K0_T, int K1_T, int K2_T, int PARTS>
+__global__ void __launch_bounds__(128 + 128 * PARTS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_res,
                  const __grid_constant__ OutMaps map_out, const __grid_constant__ ConvKernelParams p) {
+  constexpr int kEpiWarps = 4 * PARTS;
+  constexpr int kEpiThreads = kEpiWarps * 32;
+  constexpr int CW = 64 / PARTS;          // accumulator columns per thread per 64-column chunk
+  constexpr int U = CW / 8;               // 16-byte units per thread per chunk row
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -702,7 +708,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __shared__ __align__(8) uint64_t tmem_empty[8];
   __shared__ __align__(8) uint64_t res_full[kMaxResSlots];
   __shared__ __align__(8) uint64_t res_empty[kMaxResSlots];
-  __shared__ float xchg[2][2][kBlockM];     // [residual | result statistic][column half][row]
+  __shared__ float xchg[2][PARTS][kBlockM];     // [residual | result statistic][column part][row]
   __shared__ uint32_t tmem_slot;
 
   // SWIZZLE_128B tiles need 1024-byte alignment.
@@ -789,7 +795,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else if (warp >= kFirstEpiWarp) {
     // ------------------------------------------------------------------ epilogue
     const int quad = warp & 3;                                      // TMEM lane quadrant this warp may read
-    const int half = (warp - kFirstEpiWarp) >> 2;                   // which 32 columns of every 64-column chunk
+    const int half = (warp - kFirstEpiWarp) >> 2;                   // which CW columns of every 64-column chunk (part)
     const int row = quad * 32 + lane;
     const bool leader = elect_one_sync() && warp == kFirstEpiWarp;  // one thread issues the epilogue's TMA traffic
     const int rx = row % p.bw;
@@ -819,12 +825,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tc_fence_after();
         if (p.epi_mode == VB_EPI_QKVNORM) {
           if (p.head_dim == 64) {
-            for (int c = half * 64; c < p.block_n; c += 128) epi_group_qkv<64>(p, taddr + c, t.col0 + c, n, s_img, valid);
+            for (int c = half * 64; c < p.block_n; c += 64 * PARTS) epi_group_qkv<64>(p, taddr + c, t.col0 + c, n, s_img, valid);
           } else {
-            for (int c = half * 32; c < p.block_n; c += 64) epi_group_qkv<32>(p, taddr + c, t.col0 + c, n, s_img, valid);
+            for (int c = half * 32; c < p.block_n; c += 32 * PARTS) epi_group_qkv<32>(p, taddr + c, t.col0 + c, n, s_img, valid);
           }
         } else {
-          for (int c = half * 16; c < p.block_n; c += 32) epi_f32_16(p, taddr + c, t.col0 + c, pix, valid);
+          for (int c = half * 16; c < p.block_n; c += 16 * PARTS) epi_f32_16(p, taddr + c, t.col0 + c, pix, valid);
         }
         tc_fence_before();
         __syncwarp();
@@ -913,7 +919,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int nblk = p.rowroll ? p.strip_rows + 2 : 1;            // accumulator blocks per work item
       if (p.rowroll) {                                              // all eight slots start cleared and free
         for (int sl = 0; sl < 8; ++sl) {
-          slot_clear(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(sl * 64 + half * 32));
+          slot_clear(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(sl * 64 + half * CW));
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[sl]);
@@ -931,7 +937,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const bool valid = n < p.B;
         const size_t pix = static_cast<size_t>(n) * p.H * p.W + (t.y0 + ry) * p.W + t.x0 + rx;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                               static_cast<uint32_t>((p.rowroll ? buf * 64 : buf * kAccStride) + half * 32);
+                               static_cast<uint32_t>((p.rowroll ? buf * 64 : buf * kAccStride) + half * CW);
         if (p.rowroll && jb < 2) {                                  // partial sums of rows outside the strip: discard
           mbar_wait(&tmem_full[buf], bphase);
           tc_fence_after();
@@ -960,23 +966,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           float ss = 0.f;
           for (int c = 0; c < chunks; ++c) {
             const uint8_t* rrow = res_acquire();
-            ss += res_sumsq32(rrow, row, half);
+            ss += res_sumsq32<U>(rrow, row, half);
             res_release();
           }
           xchg[0][half][row] = ss;
-          named_bar_sync(kPairBarrier + quad, 64);
-          ss += xchg[0][half ^ 1][row];
+          named_bar_sync(kPairBarrier + quad, 32 * PARTS);
+#pragma unroll
+          for (int o = 1; o < PARTS; ++o) ss += xchg[0][(half + o) % PARTS][row];
           res_scale = p.res_a / (1e-4f + sqrtf(ss) * p.inv_sqrt_c);
         }
 
         // modulation row of this (image, column block): fetched ahead of the accumulator wait, the next chunk's while the
         // current one is packed and stored (L2 latency off the per-tile critical path)
-        float4 mreg[8];
+        float4 mreg[CW / 4];
         auto mod_fetch = [&](int c) {
           const float4* m = reinterpret_cast<const float4*>(p.mod + static_cast<size_t>(valid ? n : 0) * p.mod_stride + t.col0 +
-                                                            c * 64 + half * 32);
+                                                            c * 64 + half * CW);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) mreg[j] = __ldg(m + j);
+          for (int j = 0; j < CW / 4; ++j) mreg[j] = __ldg(m + j);
         };
         if (modsilu) mod_fetch(0);
 
@@ -986,14 +993,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
         // ---- pass M: accumulator -> modulation / mp_silu -> mp_sum with the residual -> clamp; RAW / SILU outputs leave
         // now, the clamped value stays packed in registers for the pixel-norm outputs.
-        uint32_t keep[4][16];
+        uint32_t keep[4][CW / 2];
         float ssv = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (c < chunks) {
             const uint8_t* rrow = has_res ? res_acquire() : nullptr;
-            float v[32];
-            tmem_ld32(taddr + c * 64, v);
+            float v[CW];
+            if (PARTS == 2) tmem_ld32(taddr + c * 64, v); else tmem_ld16(taddr + c * 64, v);
             tmem_ld_wait();
             if (c == chunks - 1) {                  // accumulator fully read: the MMA warp may start the tile after next
               if (p.rowroll) slot_clear(taddr);
@@ -1001,12 +1008,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               __syncwarp();
               if (lane == 0) acc_release(buf);
             }
-            const int col = t.col0 + c * 64 + half * 32;
+            const int col = t.col0 + c * 64 + half * CW;
             // conv_res0 (modulation + mp_silu, nothing else): the activation is applied to the packed 16-bit value
             const bool mod_pk = modsilu && !has_res && !needs_norm && p.out_f32 == nullptr && !(p.flags & VB_F_CLIP);
             if (modsilu) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < CW / 4; ++j) {
                 const float4 mm = mreg[j];
                 if (mod_pk) {
                   v[4 * j + 0] *= mm.x;
@@ -1024,8 +1031,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             if (has_res) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 q = *reinterpret_cast<const uint4*>(rrow + swz(half * 4 + j, row));
+              for (int j = 0; j < U; ++j) {
+                const uint4 q = *reinterpret_cast<const uint4*>(rrow + swz(half * U + j, row));
                 const float2 a = unpack_op2(q.x), b = unpack_op2(q.y), cc = unpack_op2(q.z), d = unpack_op2(q.w);
                 v[8 * j + 0] = fmaf(a.x, res_scale, v[8 * j + 0] * p.res_b);
                 v[8 * j + 1] = fmaf(a.y, res_scale, v[8 * j + 1] * p.res_b);
@@ -1039,32 +1046,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               res_release();
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -clampv), clampv);
+            for (int j = 0; j < CW; ++j) v[j] = fminf(fmaxf(v[j], -clampv), clampv);
             if (needs_norm) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) ssv = fmaf(v[j], v[j], ssv);
+              for (int j = 0; j < CW; ++j) ssv = fmaf(v[j], v[j], ssv);
             }
             if (p.out_f32 != nullptr && valid) {
               float4* o = reinterpret_cast<float4*>(p.out_f32 + pix * p.ld_f32 + col);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              for (int j = 0; j < CW / 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
-            uint32_t r16[16];
+            uint32_t r16[CW / 2];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) r16[j] = pack_op2_nosat(v[2 * j], v[2 * j + 1]);
+            for (int j = 0; j < CW / 2; ++j) r16[j] = pack_op2_nosat(v[2 * j], v[2 * j + 1]);
             if (mod_pk) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) r16[j] = mp_silu_pk(r16[j], 1.0f);
+              for (int j = 0; j < CW / 2; ++j) r16[j] = mp_silu_pk(r16[j], 1.0f);
             }
             if (needs_norm) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) keep[c][j] = r16[j];
+              for (int j = 0; j < CW / 2; ++j) keep[c][j] = r16[j];
             }
             if (any_direct) {
               uint8_t* srow = stg_region() + row * 128;
               auto put = [&](int kind, float scale) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < U; ++j) {
                   uint4 o;
                   if (kind == VB_OUT_RAW) {
                     o = make_uint4(r16[4 * j], r16[4 * j + 1], r16[4 * j + 2], r16[4 * j + 3]);
@@ -1074,7 +1081,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     o.z = mp_silu_pk(r16[4 * j + 2], scale);
                     o.w = mp_silu_pk(r16[4 * j + 3], scale);
                   }
-                  *reinterpret_cast<uint4*>(srow + swz(half * 4 + j, row)) = o;
+                  *reinterpret_cast<uint4*>(srow + swz(half * U + j, row)) = o;
                 }
                 srow += kChunkBytes;
               };
@@ -1089,8 +1096,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // ---- pass N: pixel-norm outputs from the packed registers
         if (needs_norm) {
           xchg[1][half][row] = ssv;
-          named_bar_sync(kPairBarrier + quad, 64);
-          ssv += xchg[1][half ^ 1][row];
+          named_bar_sync(kPairBarrier + quad, 32 * PARTS);
+#pragma unroll
+          for (int o = 1; o < PARTS; ++o) ssv += xchg[1][(half + o) % PARTS][row];
           const float inv_v = 1.0f / (1e-4f + sqrtf(ssv) * p.inv_sqrt_c);
           if (p.out_rnorm != nullptr && half == 0 && valid) p.out_rnorm[pix] = inv_v;
 #pragma unroll
@@ -1099,7 +1107,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               uint8_t* srow = stg_region() + row * 128;
               auto putn = [&](int kind) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < U; ++j) {
                   uint32_t o[4];
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
@@ -1110,7 +1118,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                       o[e] = mp_silu_pk(keep[c][4 * j + e], inv_v);
                     }
                   }
-                  *reinterpret_cast<uint4*>(srow + swz(half * 4 + j, row)) = make_uint4(o[0], o[1], o[2], o[3]);
+                  *reinterpret_cast<uint4*>(srow + swz(half * U + j, row)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
                 srow += kChunkBytes;
               };
@@ -1144,41 +1152,50 @@ typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtenso
 
 struct Variant {
   int staged, res, mod, k0, k1, k2;     // -1 = any (run-time switch inside the kernel)
+  int parts;                            // epilogue warps per TMEM lane quadrant (2, or 4 as a plan-time tuning choice)
   ConvKernelFn fn;
   bool attr_done;
 };
-#define VB_VARIANT(S, R, M, A, B, C) {S, R, M, A, B, C, conv_gemm_kernel<S, R, M, A, B, C>, false}
+#define VB_VARIANT(S, R, M, A, B, C, P) {S, R, M, A, B, C, P, conv_gemm_kernel<S, R, M, A, B, C, P>, false}
+// (the 16-warp form, PARTS = 4, is kept compilable — add VB_VARIANT(..., 4) here — but not instantiated: measured on B200 it
+//  was 1-5 % SLOWER on every epilogue-bound layer, profiles/r01_conv_epilogue_notes.txt, so the epilogue is not bound by
+//  per-warp latency)
+#define VB_VARIANT24(S, R, M, A, B, C) VB_VARIANT(S, R, M, A, B, C, 2)
 // The epilogue combinations the plans emit (engine.py) get straight-line code; anything else runs the generic one.
 static Variant g_variants[] = {
-    VB_VARIANT(0, -1, -1, -1, -1, -1),                                   // QKVNORM / narrow fp32
-    VB_VARIANT(1, 0, 1, VB_OUT_RAW, 0, 0),                               // conv_res0: modulation + mp_silu
-    VB_VARIANT(1, 0, 0, VB_OUT_RAW, 0, 0),                               // conv_skip, first conv
-    VB_VARIANT(1, 0, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, 0),
-    VB_VARIANT(1, 0, 0, VB_OUT_RAW, VB_OUT_SILU, 0),
-    VB_VARIANT(1, 0, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, VB_OUT_SILU),
-    VB_VARIANT(1, 0, 0, VB_OUT_NORM, VB_OUT_NORM_SILU, 0),               // enc conv_skip + pixel-norm
-    VB_VARIANT(1, 1, 0, VB_OUT_RAW, 0, 0),                               // conv_res1 / attn_proj: mp_sum (+clip)
-    VB_VARIANT(1, 1, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, 0),
-    VB_VARIANT(1, 1, 0, VB_OUT_RAW, VB_OUT_SILU, 0),
-    VB_VARIANT(1, 1, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, VB_OUT_SILU),
-    VB_VARIANT(1, 1, 0, VB_OUT_RAW, VB_OUT_SILU, VB_OUT_SILU),
-    VB_VARIANT(1, 3, 0, VB_OUT_RAW, 0, 0),                               // ... with the residual scaled per pixel (fused pixel-norm;
-    VB_VARIANT(1, 3, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, 0),                //     VB_RES_PIXNORM itself runs the generic epilogue)
-    VB_VARIANT(1, 3, 0, VB_OUT_RAW, VB_OUT_SILU, 0),
-    VB_VARIANT(1, 3, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, VB_OUT_SILU),
-    VB_VARIANT(1, 3, 0, VB_OUT_RAW, VB_OUT_SILU, VB_OUT_SILU),
-    VB_VARIANT(1, -1, -1, -1, -1, -1),                                   // generic staged epilogue (must stay last)
+    VB_VARIANT(0, -1, -1, -1, -1, -1, 2),                                  // QKVNORM / narrow fp32
+    VB_VARIANT24(1, 0, 1, VB_OUT_RAW, 0, 0),                               // conv_res0: modulation + mp_silu
+    VB_VARIANT24(1, 0, 0, VB_OUT_RAW, 0, 0),                               // conv_skip, first conv
+    VB_VARIANT24(1, 0, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, 0),
+    VB_VARIANT24(1, 0, 0, VB_OUT_RAW, VB_OUT_SILU, 0),
+    VB_VARIANT24(1, 0, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, VB_OUT_SILU),
+    VB_VARIANT24(1, 0, 0, VB_OUT_NORM, VB_OUT_NORM_SILU, 0),               // enc conv_skip + pixel-norm
+    VB_VARIANT24(1, 1, 0, VB_OUT_RAW, 0, 0),                               // conv_res1 / attn_proj: mp_sum (+clip)
+    VB_VARIANT24(1, 1, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, 0),
+    VB_VARIANT24(1, 1, 0, VB_OUT_RAW, VB_OUT_SILU, 0),
+    VB_VARIANT24(1, 1, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, VB_OUT_SILU),
+    VB_VARIANT24(1, 1, 0, VB_OUT_RAW, VB_OUT_SILU, VB_OUT_SILU),
+    VB_VARIANT24(1, 3, 0, VB_OUT_RAW, 0, 0),                               // ... with the residual scaled per pixel (fused pixel-norm;
+    VB_VARIANT24(1, 3, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, 0),                //     VB_RES_PIXNORM itself runs the generic epilogue)
+    VB_VARIANT24(1, 3, 0, VB_OUT_RAW, VB_OUT_SILU, 0),
+    VB_VARIANT24(1, 3, 0, VB_OUT_RAW, VB_OUT_NORM_SILU, VB_OUT_SILU),
+    VB_VARIANT24(1, 3, 0, VB_OUT_RAW, VB_OUT_SILU, VB_OUT_SILU),
+    VB_VARIANT(1, -1, -1, -1, -1, -1, 2),                                  // generic staged epilogue (must stay last)
 };
+#undef VB_VARIANT24
 #undef VB_VARIANT
 
-static Variant* find_variant(int staged, int res, int mod, const int* kinds) {
+static Variant* find_variant(int staged, int res, int mod, const int* kinds, int parts) {
   static const bool generic_only = getenv("VB_GENERIC_EPI") != nullptr;       // A/B testing
-  for (Variant& v : g_variants) {
-    if (v.staged != staged) continue;
-    if (!staged) return &v;
-    if (v.res < 0) return &v;
-    if (generic_only) continue;
-    if (v.res == res && v.mod == mod && v.k0 == kinds[0] && v.k1 == kinds[1] && v.k2 == kinds[2]) return &v;
+  for (int pass = 0; pass < 2; ++pass) {              // second pass: the 8-warp form of whatever was asked for
+    const int want = pass == 0 ? parts : 2;
+    for (Variant& v : g_variants) {
+      if (v.staged != staged || v.parts != want) continue;
+      if (!staged) return &v;
+      if (v.res < 0) return &v;
+      if (generic_only) continue;
+      if (v.res == res && v.mod == mod && v.k0 == kinds[0] && v.k1 == kinds[1] && v.k2 == kinds[2]) return &v;
+    }
   }
   return nullptr;
 }
@@ -1189,6 +1206,7 @@ struct ConvLaunch {
   ConvKernelParams p;
   ConvKernelFn fn;
   int grid;
+  int threads;
   int smem_bytes;
   double flops;
 };
@@ -1472,9 +1490,14 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
   p.res_off = main_bytes;
   p.stg_off = p.res_off + (p.res_mode != VB_RES_NONE ? p.res_slots * kChunkBytes : 0);
 
-  Variant* var = find_variant(staged ? 1 : 0, p.res_mode, (d->flags & VB_F_MODSILU) ? 1 : 0, kinds);
+  // tune bit 6: sixteen epilogue warps (the specialised staged variants only; the row-rolling layout keeps eight)
+  static const bool env_epi16 = getenv("VB_EPI16") != nullptr && atoi(getenv("VB_EPI16")) != 0;     // A/B testing: wherever available
+  const int want_parts = (((d->tune >> 6) & 1) || env_epi16) && staged && !p.rowroll ? 4 : 2;
+  Variant* var = find_variant(staged ? 1 : 0, p.res_mode, (d->flags & VB_F_MODSILU) ? 1 : 0, kinds, want_parts);
   VB_REQUIRE_L(var != nullptr, "vb_conv: no kernel variant");
+  VB_REQUIRE_L(var->parts == want_parts || !((d->tune >> 6) & 1), "vb_conv: no 16-warp epilogue variant for this output combination");
   l->fn = var->fn;
+  l->threads = 128 + 128 * var->parts;
 
   // Tensor maps.  Activations / residual / outputs: {C, W, H, N} with a {64, bw, bh, bn} box;
   // weights: {K, cout_pad} with a {64, block_n} box.
@@ -1530,7 +1553,7 @@ int conv_launch(const ConvLaunch* l, cudaStream_t s) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(l->grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(l->threads);
   cfg.dynamicSmemBytes = l->smem_bytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
