@@ -506,10 +506,8 @@ def test_generate_images_nvs_pipeline(env):
     b = list(vivid_b200.generate_images_nvs(net, seeds=[3, 4, 5, 6, 7], max_batch_size=2, **kw))
     assert len(a) == 1 and a[0].images.shape == (5, 3, 16, 16) and a[0].images.dtype == torch.uint8
     assert [len(r.seeds) for r in b] == [2, 2, 1]
-    # (the batch split changes the tiling the plan-time tuner picks, i.e. fp32 summation order: identical up to 16-bit
-    #  rounding of the activations, which four Heun steps can carry into the last uint8 level)
-    diff = (a[0].images.int() - torch.cat([r.images for r in b]).int()).abs()
-    assert diff.max() <= 2 and diff.float().mean() < 0.1
+    # (the plan-time tuner only varies bitwise-neutral tiling knobs, so the batch split does not change a single bit)
+    assert torch.equal(a[0].images, torch.cat([r.images for r in b]))
     # two-stage pipeline: base -> bilinear x4 -> SR model
     c = list(vivid_b200.generate_images_nvs(net, seeds=[3, 4, 5], max_batch_size=8, sr_model=sr, **kw))
     assert c[0].images.shape == (3, 3, 64, 64) and c[0].images.dtype == torch.uint8
