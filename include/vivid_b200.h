@@ -132,7 +132,7 @@ typedef struct vb_conv_desc {
   int32_t tune;        /* plan-time autotuning; 0 = the library decides.  bits 0-1: 1 single CTA, 2 CTA pair;
                         * bits 2-3: 1 per-tap operand boxes, 2 shared haloed boxes wherever they fit;
                         * bits 4-5: 1 row-rolling input-stationary layout (3x3, 64 -> 64 channels, rows >= 128 px);
-                        * bit 6: sixteen epilogue warps (16 columns per thread) instead of eight */
+                        * bit 6: ping-pong epilogue (two groups of four warps on alternate tiles; block_n == 64) */
 } vb_conv_desc;
 int vb_conv(const vb_conv_desc* d, void* stream);
 /* Diagnostics (micro-benchmarks only): with the environment variable VB_DBG & 16 set when an op is prepared, the conv

@@ -53,7 +53,7 @@ constexpr int kStaticSmem = 5120;                     // barriers + statistic ex
 constexpr int kSmemMax = 227 * 1024 - 1024 - kStaticSmem;   // dynamic smem we allow ourselves (1 KiB alignment slack)
 constexpr int kMaxResSlots = 4;                       // residual TMA ring depth (16 KiB sub-tiles)
 constexpr int kEpiBarrier = 1;                        // named barrier of all epilogue warps
-constexpr int kPairBarrier = 2;                       // +quadrant: the two warps sharing a TMEM lane quadrant
+constexpr int kPairBarrier = 3;                       // +quadrant: the warps sharing a TMEM lane quadrant (1, 2: kEpiBarrier + group)
 
 // VB_DBG & 16: longest CTA lifetime (SM cycles) of the launches since the last vb_debug_conv_cycles() call.
 __device__ unsigned long long g_conv_cycles;
@@ -75,6 +75,7 @@ struct ConvKernelParams {
   // when it has read them; every MMA accumulates.
   int rowroll, strip_rows, strip_shift, chunk_mask, chunk_shift;
   uint32_t idesc128, idesc64;
+  int eg;               // ping-pong epilogue (kernel variants with PARTS == 1)
   int tune_tap;         // plan-time tuning: 0 auto, 1 no shared haloed boxes, 2 haloed boxes wherever they fit
   int pair, total_q;    // CTA-pair mode (cluster of 2, cta_group::2 MMA); work items per CTA / per pair
   int taps, kc_a, kc_b;
@@ -691,14 +692,24 @@ __device__ __forceinline__ bool kind_norm(int k) { return k == VB_OUT_NORM || k 
 // Template arguments >= 0 fix the epilogue variant at compile time; -1 reads it from the parameters (generic
 // fallback for combinations the plans never emit).  STAGED = 0 is the QKVNORM / narrow fp32 epilogue.
 template <int STAGED, int RES_T, int MOD_T, int K0_T, int K1_T, int K2_T, int PARTS>
-__global__ void __launch_bounds__(128 + 128 * PARTS, 1)
+__global__ void __launch_bounds__(PARTS == 1 ? 384 : 128 + 128 * PARTS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_res,
                  const __grid_constant__ OutMaps map_out, const __grid_constant__ ConvKernelParams p) {
-  constexpr int kEpiWarps = 4 * PARTS;
-  constexpr int kEpiThreads = kEpiWarps * 32;
-  constexpr int CW = 64 / PARTS;          // accumulator columns per thread per 64-column chunk
-  constexpr int U = CW / 8;               // 16-byte units per thread per chunk row
+  // PARTS == 1 selects the ping-pong epilogue (EG): two groups of four warps take ALTERNATE tiles (group g <-> accumulator
+  // buffer g), a thread owns a whole 64-column row (two 32-column halves in sequence), each group has its own residual
+  // ring, staging ring, barrier and TMA-issuing thread — so the latency chain of one tile's epilogue (accumulator
+  // wake-up, tcgen05.ld, proxy fence, staging barrier, TMA issue: ~2 k cycles even for the plainest epilogue) overlaps
+  // the other group's.  Only for one-chunk tiles (block_n == 64).
+  constexpr bool EG = PARTS == 1;
+  constexpr int NP = EG ? 2 : PARTS;      // column parts of a chunk (EG: processed in sequence by one thread)
+  constexpr int HH = EG ? 2 : 1;
+  constexpr int MAXC = EG ? 1 : 4;        // chunks per tile
+  constexpr int kEpiWarps = EG ? 8 : 4 * PARTS;
+  constexpr int kTileWarps = EG ? 4 : kEpiWarps;      // warps working on one tile
+  constexpr int kEpiThreads = kTileWarps * 32;
+  constexpr int CW = 64 / NP;             // accumulator columns per thread per part
+  constexpr int U = CW / 8;               // 16-byte units per part per chunk row
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -708,7 +719,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __shared__ __align__(8) uint64_t tmem_empty[8];
   __shared__ __align__(8) uint64_t res_full[kMaxResSlots];
   __shared__ __align__(8) uint64_t res_empty[kMaxResSlots];
-  __shared__ float xchg[2][PARTS][kBlockM];     // [residual | result statistic][column part][row]
+  __shared__ float xchg[2][NP][kBlockM];     // [residual | result statistic][column part][row]
   __shared__ uint32_t tmem_slot;
 
   // SWIZZLE_128B tiles need 1024-byte alignment.
@@ -743,11 +754,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int b = 0; b < 8; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], p.pair ? 2 * kEpiWarps : kEpiWarps);   // pair: the epilogue warps of both CTAs
+      mbar_init(&tmem_empty[b], p.pair ? 2 * kTileWarps : kTileWarps);   // pair: the epilogue warps of both CTAs
     }
     for (int b = 0; b < kMaxResSlots; ++b) {
       mbar_init(&res_full[b], 1);
-      mbar_init(&res_empty[b], kEpiWarps);
+      mbar_init(&res_empty[b], kTileWarps);
     }
     fence_mbar_init();
   }
@@ -795,9 +806,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else if (warp >= kFirstEpiWarp) {
     // ------------------------------------------------------------------ epilogue
     const int quad = warp & 3;                                      // TMEM lane quadrant this warp may read
-    const int half = (warp - kFirstEpiWarp) >> 2;                   // which CW columns of every 64-column chunk (part)
+    const int wq = (warp - kFirstEpiWarp) >> 2;
+    const int group = EG ? wq : 0;                                  // EG: which of the two alternating tile streams
+    const int half = EG ? 0 : wq;                                   // which CW columns of every 64-column chunk (part)
     const int row = quad * 32 + lane;
-    const bool leader = elect_one_sync() && warp == kFirstEpiWarp;  // one thread issues the epilogue's TMA traffic
+    const bool leader = elect_one_sync() && warp == kFirstEpiWarp + 4 * group;  // one thread per group issues its TMA traffic
     const int rx = row % p.bw;
     const int r2 = row / p.bw;
     const int ry = r2 % p.bh;
@@ -846,8 +859,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const bool needs_norm = kind_norm(k0) || kind_norm(k1) || kind_norm(k2);
       const bool any_direct = kind_direct(k0) || kind_direct(k1) || kind_direct(k2);
       const int chunks = p.block_n >> 6;                            // 64-column sub-tiles
-      uint8_t* res_ring = smem + p.res_off;
-      uint8_t* stg_ring = smem + p.stg_off;
+      uint8_t* res_ring = smem + p.res_off + group * p.res_slots * kChunkBytes;
+      uint8_t* stg_ring = smem + p.stg_off + group * p.stg_regions * p.gslots * kChunkBytes;
+      uint64_t* res_full_g = res_full + group * 2;            // EG: two slots per group
+      uint64_t* res_empty_g = res_empty + group * 2;
       const uint32_t rmask = static_cast<uint32_t>(p.res_slots - 1);
       const uint32_t rshift = p.res_slots == 4 ? 2u : 1u;
       const int items = chunks * (res_mode == VB_RES_PIXNORM ? 2 : 1);   // residual (pass, chunk) items per tile
@@ -861,16 +876,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       auto res_topup = [&]() {
         if (has_res && leader) {
           while (res_issued < res_q + static_cast<uint32_t>(p.res_slots)) {
-            const uint32_t ti = res_issued / items;                  // CTA-local index of the tile owning the item
+            const uint32_t tg = res_issued / items;                  // this group's tile number ...
+            const uint32_t ti = EG ? 2 * tg + group : tg;            // ... and its CTA-local index
             const int wl = p.rowroll ? static_cast<int>(ti >> p.strip_shift) : static_cast<int>(ti);
             const int ql = q0 + wl * qstride;
             if (ql >= p.total_q) break;
             const TileCoord tt = p.rowroll ? strip_tile(p, ql, static_cast<int>(ti) & (p.strip_rows - 1))
                                            : decode_tile(p, tile_of(p, ql, rank));
             const uint32_t slot = res_issued & rmask;
-            mbar_wait(&res_empty[slot], ((res_issued >> rshift) & 1u) ^ 1u);
-            mbar_expect_tx(&res_full[slot], kChunkBytes);
-            tma_load_4d(&map_res, &res_full[slot], res_ring + slot * kChunkBytes,
+            mbar_wait(&res_empty_g[slot], ((res_issued >> rshift) & 1u) ^ 1u);
+            mbar_expect_tx(&res_full_g[slot], kChunkBytes);
+            tma_load_4d(&map_res, &res_full_g[slot], res_ring + slot * kChunkBytes,
                         tt.col0 + static_cast<int>((res_issued % items) % chunks) * 64, tt.x0, tt.y0, tt.n0);
             ++res_issued;
           }
@@ -879,12 +895,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // Makes the next residual item readable; returns this row's 128-byte slot of it.
       auto res_acquire = [&]() -> const uint8_t* {
         res_topup();
-        mbar_wait(&res_full[res_q & rmask], (res_q >> rshift) & 1u);
+        mbar_wait(&res_full_g[res_q & rmask], (res_q >> rshift) & 1u);
         return res_ring + (res_q & rmask) * kChunkBytes + row * 128;
       };
       auto res_release = [&]() {
         __syncwarp();
-        if (lane == 0) mbar_arrive(&res_empty[res_q & rmask]);
+        if (lane == 0) mbar_arrive(&res_empty_g[res_q & rmask]);
         ++res_q;
       };
       // Region of the staging ring the next group of sub-tiles goes to.  With three regions the leader only has to know
@@ -893,18 +909,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // a wait for ALL stores, 14 % of the kernel's stall samples sat on this barrier: profiles/r01_conv_stage_ring.txt.)
       auto stg_region = [&]() -> uint8_t* { return stg_ring + greg * p.gslots * kChunkBytes; };
       // All 256 threads wrote their part of the region: publish it to the async proxy and let the leader store it.
-      auto stg_commit = [&](const TileCoord& t, int c, bool norm_pass) {
+      auto stg_commit = [&](const TileCoord& t, int c, bool norm_pass, int only = -1) {
         fence_proxy_async();
         if (leader) {
           if (p.stg_regions == 3) bulk_wait_read<1>(); else bulk_wait_read<0>();
         }
-        named_bar_sync(kEpiBarrier, kEpiThreads);
+        named_bar_sync(kEpiBarrier + group, kEpiThreads);
         if (leader && !(p.dbg & 2)) {
           const uint8_t* reg = stg_region();
           int di = 0;
-          if (norm_pass ? kind_norm(k0) : kind_direct(k0)) tma_store_4d(&map_out.m[0], reg + (di++) * kChunkBytes, t.col0 + c * 64, t.x0, t.y0, t.n0);
-          if (norm_pass ? kind_norm(k1) : kind_direct(k1)) tma_store_4d(&map_out.m[1], reg + (di++) * kChunkBytes, t.col0 + c * 64, t.x0, t.y0, t.n0);
-          if (norm_pass ? kind_norm(k2) : kind_direct(k2)) tma_store_4d(&map_out.m[2], reg + (di++) * kChunkBytes, t.col0 + c * 64, t.x0, t.y0, t.n0);
+          if ((only < 0 || only == 0) && (norm_pass ? kind_norm(k0) : kind_direct(k0))) tma_store_4d(&map_out.m[0], reg + (di++) * kChunkBytes, t.col0 + c * 64, t.x0, t.y0, t.n0);
+          if ((only < 0 || only == 1) && (norm_pass ? kind_norm(k1) : kind_direct(k1))) tma_store_4d(&map_out.m[1], reg + (di++) * kChunkBytes, t.col0 + c * 64, t.x0, t.y0, t.n0);
+          if ((only < 0 || only == 2) && (norm_pass ? kind_norm(k2) : kind_direct(k2))) tma_store_4d(&map_out.m[2], reg + (di++) * kChunkBytes, t.col0 + c * 64, t.x0, t.y0, t.n0);
           bulk_commit();
         }
         if (++greg == static_cast<uint32_t>(p.stg_regions)) greg = 0;
@@ -930,6 +946,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int jb = p.rowroll ? it - wi * nblk : 0;              // block within the strip: 0,1 carry no output row
         const int q = q0 + wi * qstride;
         if (q >= p.total_q) break;
+        if (EG && (it & 1) != group) continue;
         const int buf = p.rowroll ? (it & 7) : (it & 1);
         const uint32_t bphase = static_cast<uint32_t>(p.rowroll ? it >> 3 : it >> 1) & 1u;
         const TileCoord t = p.rowroll ? strip_tile(p, q, jb - 2) : decode_tile(p, tile_of(p, q, rank));
@@ -970,22 +987,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             res_release();
           }
           xchg[0][half][row] = ss;
-          named_bar_sync(kPairBarrier + quad, 32 * PARTS);
+          named_bar_sync(kPairBarrier + quad, 32 * NP);       // (never reached by the ping-pong variants)
 #pragma unroll
-          for (int o = 1; o < PARTS; ++o) ss += xchg[0][(half + o) % PARTS][row];
+          for (int o = 1; o < NP; ++o) ss += xchg[0][(half + o) % NP][row];
           res_scale = p.res_a / (1e-4f + sqrtf(ss) * p.inv_sqrt_c);
         }
 
         // modulation row of this (image, column block): fetched ahead of the accumulator wait, the next chunk's while the
         // current one is packed and stored (L2 latency off the per-tile critical path)
         float4 mreg[CW / 4];
-        auto mod_fetch = [&](int c) {
+        auto mod_fetch = [&](int c, int part) {
           const float4* m = reinterpret_cast<const float4*>(p.mod + static_cast<size_t>(valid ? n : 0) * p.mod_stride + t.col0 +
-                                                            c * 64 + half * CW);
+                                                            c * 64 + part * CW);
 #pragma unroll
           for (int j = 0; j < CW / 4; ++j) mreg[j] = __ldg(m + j);
         };
-        if (modsilu) mod_fetch(0);
+        if (modsilu) mod_fetch(0, half);
 
         mbar_wait(&tmem_full[buf], bphase);
         if (leader && it == 0) VB_TS(4);
@@ -993,139 +1010,173 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
         // ---- pass M: accumulator -> modulation / mp_silu -> mp_sum with the residual -> clamp; RAW / SILU outputs leave
         // now, the clamped value stays packed in registers for the pixel-norm outputs.
-        uint32_t keep[4][CW / 2];
-        float ssv = 0.f;
+        uint32_t keep[MAXC][HH][CW / 2];
+        float ssp[HH];                              // sum of squares per column part (summed in the same order in every layout)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int hh = 0; hh < HH; ++hh) ssp[hh] = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
           if (c < chunks) {
             const uint8_t* rrow = has_res ? res_acquire() : nullptr;
-            float v[CW];
-            if (PARTS == 2) tmem_ld32(taddr + c * 64, v); else tmem_ld16(taddr + c * 64, v);
-            tmem_ld_wait();
-            if (c == chunks - 1) {                  // accumulator fully read: the MMA warp may start the tile after next
-              if (p.rowroll) slot_clear(taddr);
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) acc_release(buf);
-            }
-            const int col = t.col0 + c * 64 + half * CW;
-            // conv_res0 (modulation + mp_silu, nothing else): the activation is applied to the packed 16-bit value
-            const bool mod_pk = modsilu && !has_res && !needs_norm && p.out_f32 == nullptr && !(p.flags & VB_F_CLIP);
-            if (modsilu) {
+            uint32_t r16h[HH][CW / 2];
 #pragma unroll
-              for (int j = 0; j < CW / 4; ++j) {
-                const float4 mm = mreg[j];
-                if (mod_pk) {
-                  v[4 * j + 0] *= mm.x;
-                  v[4 * j + 1] *= mm.y;
-                  v[4 * j + 2] *= mm.z;
-                  v[4 * j + 3] *= mm.w;
-                } else {
-                  v[4 * j + 0] = mp_silu_fast(v[4 * j + 0] * mm.x);
-                  v[4 * j + 1] = mp_silu_fast(v[4 * j + 1] * mm.y);
-                  v[4 * j + 2] = mp_silu_fast(v[4 * j + 2] * mm.z);
-                  v[4 * j + 3] = mp_silu_fast(v[4 * j + 3] * mm.w);
+            for (int hh = 0; hh < HH; ++hh) {
+              const int part = EG ? hh : half;
+              const uint32_t ta = taddr + static_cast<uint32_t>(c * 64 + (EG ? hh * CW : 0));
+              if (EG && modsilu && hh > 0) mod_fetch(c, part);
+              float v[CW];
+              if (CW == 32) tmem_ld32(ta, v); else tmem_ld16(ta, v);
+              tmem_ld_wait();
+              if (c == chunks - 1 && hh == HH - 1) {   // accumulator fully read: the MMA warp may start the tile after next
+                if (p.rowroll) slot_clear(taddr);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) acc_release(buf);
+              }
+              const int col = t.col0 + c * 64 + part * CW;
+              // conv_res0 (modulation + mp_silu, nothing else): the activation is applied to the packed 16-bit value
+              const bool mod_pk = modsilu && !has_res && !needs_norm && p.out_f32 == nullptr && !(p.flags & VB_F_CLIP);
+              if (modsilu) {
+#pragma unroll
+                for (int j = 0; j < CW / 4; ++j) {
+                  const float4 mm = mreg[j];
+                  if (mod_pk) {
+                    v[4 * j + 0] *= mm.x;
+                    v[4 * j + 1] *= mm.y;
+                    v[4 * j + 2] *= mm.z;
+                    v[4 * j + 3] *= mm.w;
+                  } else {
+                    v[4 * j + 0] = mp_silu_fast(v[4 * j + 0] * mm.x);
+                    v[4 * j + 1] = mp_silu_fast(v[4 * j + 1] * mm.y);
+                    v[4 * j + 2] = mp_silu_fast(v[4 * j + 2] * mm.z);
+                    v[4 * j + 3] = mp_silu_fast(v[4 * j + 3] * mm.w);
+                  }
                 }
+                if (!EG && c + 1 < chunks) mod_fetch(c + 1, half);
               }
-              if (c + 1 < chunks) mod_fetch(c + 1);
-            }
-            if (has_res) {
-#pragma unroll
-              for (int j = 0; j < U; ++j) {
-                const uint4 q = *reinterpret_cast<const uint4*>(rrow + swz(half * U + j, row));
-                const float2 a = unpack_op2(q.x), b = unpack_op2(q.y), cc = unpack_op2(q.z), d = unpack_op2(q.w);
-                v[8 * j + 0] = fmaf(a.x, res_scale, v[8 * j + 0] * p.res_b);
-                v[8 * j + 1] = fmaf(a.y, res_scale, v[8 * j + 1] * p.res_b);
-                v[8 * j + 2] = fmaf(b.x, res_scale, v[8 * j + 2] * p.res_b);
-                v[8 * j + 3] = fmaf(b.y, res_scale, v[8 * j + 3] * p.res_b);
-                v[8 * j + 4] = fmaf(cc.x, res_scale, v[8 * j + 4] * p.res_b);
-                v[8 * j + 5] = fmaf(cc.y, res_scale, v[8 * j + 5] * p.res_b);
-                v[8 * j + 6] = fmaf(d.x, res_scale, v[8 * j + 6] * p.res_b);
-                v[8 * j + 7] = fmaf(d.y, res_scale, v[8 * j + 7] * p.res_b);
-              }
-              res_release();
-            }
-#pragma unroll
-            for (int j = 0; j < CW; ++j) v[j] = fminf(fmaxf(v[j], -clampv), clampv);
-            if (needs_norm) {
-#pragma unroll
-              for (int j = 0; j < CW; ++j) ssv = fmaf(v[j], v[j], ssv);
-            }
-            if (p.out_f32 != nullptr && valid) {
-              float4* o = reinterpret_cast<float4*>(p.out_f32 + pix * p.ld_f32 + col);
-#pragma unroll
-              for (int j = 0; j < CW / 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            uint32_t r16[CW / 2];
-#pragma unroll
-            for (int j = 0; j < CW / 2; ++j) r16[j] = pack_op2_nosat(v[2 * j], v[2 * j + 1]);
-            if (mod_pk) {
-#pragma unroll
-              for (int j = 0; j < CW / 2; ++j) r16[j] = mp_silu_pk(r16[j], 1.0f);
-            }
-            if (needs_norm) {
-#pragma unroll
-              for (int j = 0; j < CW / 2; ++j) keep[c][j] = r16[j];
-            }
-            if (any_direct) {
-              uint8_t* srow = stg_region() + row * 128;
-              auto put = [&](int kind, float scale) {
+              if (has_res) {
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
-                  uint4 o;
-                  if (kind == VB_OUT_RAW) {
-                    o = make_uint4(r16[4 * j], r16[4 * j + 1], r16[4 * j + 2], r16[4 * j + 3]);
-                  } else {
-                    o.x = mp_silu_pk(r16[4 * j + 0], scale);
-                    o.y = mp_silu_pk(r16[4 * j + 1], scale);
-                    o.z = mp_silu_pk(r16[4 * j + 2], scale);
-                    o.w = mp_silu_pk(r16[4 * j + 3], scale);
-                  }
-                  *reinterpret_cast<uint4*>(srow + swz(half * U + j, row)) = o;
+                  const uint4 q = *reinterpret_cast<const uint4*>(rrow + swz(part * U + j, row));
+                  const float2 a = unpack_op2(q.x), b = unpack_op2(q.y), cc = unpack_op2(q.z), d = unpack_op2(q.w);
+                  v[8 * j + 0] = fmaf(a.x, res_scale, v[8 * j + 0] * p.res_b);
+                  v[8 * j + 1] = fmaf(a.y, res_scale, v[8 * j + 1] * p.res_b);
+                  v[8 * j + 2] = fmaf(b.x, res_scale, v[8 * j + 2] * p.res_b);
+                  v[8 * j + 3] = fmaf(b.y, res_scale, v[8 * j + 3] * p.res_b);
+                  v[8 * j + 4] = fmaf(cc.x, res_scale, v[8 * j + 4] * p.res_b);
+                  v[8 * j + 5] = fmaf(cc.y, res_scale, v[8 * j + 5] * p.res_b);
+                  v[8 * j + 6] = fmaf(d.x, res_scale, v[8 * j + 6] * p.res_b);
+                  v[8 * j + 7] = fmaf(d.y, res_scale, v[8 * j + 7] * p.res_b);
                 }
-                srow += kChunkBytes;
+              }
+#pragma unroll
+              for (int j = 0; j < CW; ++j) v[j] = fminf(fmaxf(v[j], -clampv), clampv);
+              if (needs_norm) {
+#pragma unroll
+                for (int j = 0; j < CW; ++j) ssp[hh] = fmaf(v[j], v[j], ssp[hh]);
+              }
+              if (p.out_f32 != nullptr && valid) {
+                float4* o = reinterpret_cast<float4*>(p.out_f32 + pix * p.ld_f32 + col);
+#pragma unroll
+                for (int j = 0; j < CW / 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              }
+#pragma unroll
+              for (int j = 0; j < CW / 2; ++j) r16h[hh][j] = pack_op2_nosat(v[2 * j], v[2 * j + 1]);
+              if (mod_pk) {
+#pragma unroll
+                for (int j = 0; j < CW / 2; ++j) r16h[hh][j] = mp_silu_pk(r16h[hh][j], 1.0f);
+              }
+              if (needs_norm) {
+#pragma unroll
+                for (int j = 0; j < CW / 2; ++j) keep[c][hh][j] = r16h[hh][j];
+              }
+            }
+            if (has_res) res_release();
+            if (any_direct) {
+              // one output after the other through a single staging slot (ping-pong epilogue: its two rings must fit), or
+              // all outputs of the chunk side by side and one commit
+              auto put = [&](int kind, float scale, uint8_t* srow) {
+#pragma unroll
+                for (int hh = 0; hh < HH; ++hh) {
+                  const int part = EG ? hh : half;
+#pragma unroll
+                  for (int j = 0; j < U; ++j) {
+                    uint4 o;
+                    if (kind == VB_OUT_RAW) {
+                      o = make_uint4(r16h[hh][4 * j], r16h[hh][4 * j + 1], r16h[hh][4 * j + 2], r16h[hh][4 * j + 3]);
+                    } else {
+                      o.x = mp_silu_pk(r16h[hh][4 * j + 0], scale);
+                      o.y = mp_silu_pk(r16h[hh][4 * j + 1], scale);
+                      o.z = mp_silu_pk(r16h[hh][4 * j + 2], scale);
+                      o.w = mp_silu_pk(r16h[hh][4 * j + 3], scale);
+                    }
+                    *reinterpret_cast<uint4*>(srow + swz(part * U + j, row)) = o;
+                  }
+                }
               };
-              if (kind_direct(k0)) put(k0, p.out_scale[0]);
-              if (kind_direct(k1)) put(k1, p.out_scale[1]);
-              if (kind_direct(k2)) put(k2, p.out_scale[2]);
-              stg_commit(t, c, false);
+              if (EG) {
+                if (kind_direct(k0)) { put(k0, p.out_scale[0], stg_region() + row * 128); stg_commit(t, c, false, 0); }
+                if (kind_direct(k1)) { put(k1, p.out_scale[1], stg_region() + row * 128); stg_commit(t, c, false, 1); }
+                if (kind_direct(k2)) { put(k2, p.out_scale[2], stg_region() + row * 128); stg_commit(t, c, false, 2); }
+              } else {
+                uint8_t* srow = stg_region() + row * 128;
+                if (kind_direct(k0)) { put(k0, p.out_scale[0], srow); srow += kChunkBytes; }
+                if (kind_direct(k1)) { put(k1, p.out_scale[1], srow); srow += kChunkBytes; }
+                if (kind_direct(k2)) { put(k2, p.out_scale[2], srow); srow += kChunkBytes; }
+                stg_commit(t, c, false);
+              }
             }
           }
         }
 
         // ---- pass N: pixel-norm outputs from the packed registers
         if (needs_norm) {
-          xchg[1][half][row] = ssv;
-          named_bar_sync(kPairBarrier + quad, 32 * PARTS);
+          float ssv;
+          if (EG) {
+            ssv = ssp[0] + ssp[HH - 1];
+          } else {
+            ssv = ssp[0];
+            xchg[1][half][row] = ssv;
+            named_bar_sync(kPairBarrier + quad, 32 * NP);
 #pragma unroll
-          for (int o = 1; o < PARTS; ++o) ssv += xchg[1][(half + o) % PARTS][row];
+            for (int o = 1; o < NP; ++o) ssv += xchg[1][(half + o) % NP][row];
+          }
           const float inv_v = 1.0f / (1e-4f + sqrtf(ssv) * p.inv_sqrt_c);
           if (p.out_rnorm != nullptr && half == 0 && valid) p.out_rnorm[pix] = inv_v;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < MAXC; ++c) {
             if (c < chunks) {
-              uint8_t* srow = stg_region() + row * 128;
-              auto putn = [&](int kind) {
+              auto putn = [&](int kind, uint8_t* srow) {
 #pragma unroll
-                for (int j = 0; j < U; ++j) {
-                  uint32_t o[4];
+                for (int hh = 0; hh < HH; ++hh) {
+                  const int part = EG ? hh : half;
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    if (kind == VB_OUT_NORM) {
-                      const float2 x = unpack_op2(keep[c][4 * j + e]);
-                      o[e] = pack_sat2(x.x * inv_v, x.y * inv_v);
-                    } else {
-                      o[e] = mp_silu_pk(keep[c][4 * j + e], inv_v);
+                  for (int j = 0; j < U; ++j) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      if (kind == VB_OUT_NORM) {
+                        const float2 x = unpack_op2(keep[c][hh][4 * j + e]);
+                        o[e] = pack_sat2(x.x * inv_v, x.y * inv_v);
+                      } else {
+                        o[e] = mp_silu_pk(keep[c][hh][4 * j + e], inv_v);
+                      }
                     }
+                    *reinterpret_cast<uint4*>(srow + swz(part * U + j, row)) = make_uint4(o[0], o[1], o[2], o[3]);
                   }
-                  *reinterpret_cast<uint4*>(srow + swz(half * U + j, row)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
-                srow += kChunkBytes;
               };
-              if (kind_norm(k0)) putn(k0);
-              if (kind_norm(k1)) putn(k1);
-              if (kind_norm(k2)) putn(k2);
-              stg_commit(t, c, true);
+              if (EG) {
+                if (kind_norm(k0)) { putn(k0, stg_region() + row * 128); stg_commit(t, c, true, 0); }
+                if (kind_norm(k1)) { putn(k1, stg_region() + row * 128); stg_commit(t, c, true, 1); }
+                if (kind_norm(k2)) { putn(k2, stg_region() + row * 128); stg_commit(t, c, true, 2); }
+              } else {
+                uint8_t* srow = stg_region() + row * 128;
+                if (kind_norm(k0)) { putn(k0, srow); srow += kChunkBytes; }
+                if (kind_norm(k1)) { putn(k1, srow); srow += kChunkBytes; }
+                if (kind_norm(k2)) { putn(k2, srow); srow += kChunkBytes; }
+                stg_commit(t, c, true);
+              }
             }
           }
         }
@@ -1160,7 +1211,7 @@ struct Variant {
 // (the 16-warp form, PARTS = 4, is kept compilable — add VB_VARIANT(..., 4) here — but not instantiated: measured on B200 it
 //  was 1-5 % SLOWER on every epilogue-bound layer, profiles/r01_conv_epilogue_notes.txt, so the epilogue is not bound by
 //  per-warp latency)
-#define VB_VARIANT24(S, R, M, A, B, C) VB_VARIANT(S, R, M, A, B, C, 2)
+#define VB_VARIANT24(S, R, M, A, B, C) VB_VARIANT(S, R, M, A, B, C, 2), VB_VARIANT(S, R, M, A, B, C, 1)
 // The epilogue combinations the plans emit (engine.py) get straight-line code; anything else runs the generic one.
 static Variant g_variants[] = {
     VB_VARIANT(0, -1, -1, -1, -1, -1, 2),                                  // QKVNORM / narrow fp32
@@ -1314,6 +1365,7 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
   p.block_n = d->block_n;
   static const int env_pair = getenv("VB_PAIR") ? atoi(getenv("VB_PAIR")) : -1;      // -1 auto, 0 off, 1 on (A/B testing)
   static const int env_rowroll = getenv("VB_ROWROLL") ? atoi(getenv("VB_ROWROLL")) : 0;          // A/B testing
+  static const bool env_epi_pp = getenv("VB_EPI_PP") != nullptr && atoi(getenv("VB_EPI_PP")) != 0;
   const bool want_rowroll = ((d->tune >> 4) & 3) == 1 || (env_rowroll && ((d->tune >> 4) & 3) == 0 && d->taps == 9 && p.bh == 1 &&
                             p.bw == kBlockM && d->cin_pad == 64 && d->cin2_pad == 0 && d->block_n == 64 && d->cout_pad == 64 &&
                             d->H % 16 == 0 && d->epi_mode == VB_EPI_PLAIN);
@@ -1413,16 +1465,32 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
       // a CTA pair is taken when it upgrades the main loop (its half-size weight tiles fit resident) or for narrow 3x3
       // tiles, where the single-CTA MMA is shared-memory bound.
       const int opts[4][2] = {{4, 3}, {4, 2}, {2, 3}, {2, 2}};      // {residual ring slots, staging regions}
+      // tune bit 6: ping-pong epilogue (two groups, each with its own rings): one-chunk tiles only, two residual slots each
+      Variant* egv = find_variant(1, d->res_mode, (d->flags & VB_F_MODSILU) ? 1 : 0, kinds, 1);
+      const bool eg_ok = egv != nullptr && egv->parts == 1 && d->block_n == 64 && !want_rowroll && d->res_mode != VB_RES_PIXNORM;
+      VB_REQUIRE_L(eg_ok || !((d->tune >> 6) & 1), "vb_conv: no ping-pong epilogue for this layer (needs block_n == 64 and a specialised variant)");
+      const int gslots_all = p.gslots;
+      bool want_eg = (((d->tune >> 6) & 1) || env_epi_pp) && eg_ok;
+      int best_score = -1;
+      for (int attempt = 0; attempt < 2 && best_score < 0; ++attempt) {
+      if (attempt == 1) {
+        if (!want_eg || ((d->tune >> 6) & 1)) break;      // an environment-forced ping-pong epilogue that does not fit: plain one
+        want_eg = false;
+        p.gslots = gslots_all;
+      }
+      const int eg_mul = want_eg ? 2 : 1;
+      if (want_eg) p.gslots = 1;            // one output per staging slot and commit
       int best[2] = {-1, -1};
       ConvKernelParams best_p[2] = {p, p};
       for (int pair = 0; pair <= (pair_possible ? 1 : 0); ++pair) {
         for (int o = 0; o < 4; ++o) {
           if (forced_regions == 2 && opts[o][1] != 2) continue;
           if (!has_res && opts[o][0] != 4) continue;               // no residual: the ring size is moot
+          if (want_eg && has_res && opts[o][0] != 2) continue;
           set_pair(pair);
           p.res_slots = has_res ? opts[o][0] : 2;
           p.stg_regions = opts[o][1];
-          if (!plan_mainloop(p, kSmemMax - (has_res ? p.res_slots * kChunkBytes : 0) - p.stg_regions * p.gslots * kChunkBytes,
+          if (!plan_mainloop(p, kSmemMax - eg_mul * ((has_res ? p.res_slots * kChunkBytes : 0) + p.stg_regions * p.gslots * kChunkBytes),
                              false))
             continue;
           const int score = 100 * mainloop_score(p) + (has_res && p.res_slots == 4 ? 40 : 0) + (p.stg_regions == 3 ? 10 : 0);
@@ -1441,8 +1509,10 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
         use_pair = forced_pair >= 0 ? forced_pair : ((upgrade || narrow) ? 1 : 0);
         if (best[0] < 0) use_pair = 1;
       }
-      const int best_score = best[use_pair];
+      best_score = best[use_pair];
       p = best_p[use_pair];
+      p.eg = want_eg ? 1 : 0;
+      }
       VB_REQUIRE_L(best_score >= 0, "vb_conv: shared memory budget exceeded");
     } else {
       if (forced_pair == 1 && pair_possible) set_pair(1);
@@ -1488,16 +1558,17 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
   const int main_bytes = p.tap_mode != 0 ? p.b_off + (p.b_resident ? 9 * (p.kc_a + p.kc_b) : p.b_slots) * p.b_bytes
                                          : p.num_stages * p.stage_bytes;
   p.res_off = main_bytes;
-  p.stg_off = p.res_off + (p.res_mode != VB_RES_NONE ? p.res_slots * kChunkBytes : 0);
+  const int eg_mul2 = p.eg ? 2 : 1;
+  p.stg_off = p.res_off + eg_mul2 * (p.res_mode != VB_RES_NONE ? p.res_slots * kChunkBytes : 0);
 
   // tune bit 6: sixteen epilogue warps (the specialised staged variants only; the row-rolling layout keeps eight)
-  static const bool env_epi16 = getenv("VB_EPI16") != nullptr && atoi(getenv("VB_EPI16")) != 0;     // A/B testing: wherever available
-  const int want_parts = (((d->tune >> 6) & 1) || env_epi16) && staged && !p.rowroll ? 4 : 2;
+  const int want_parts = p.eg ? 1 : 2;
   Variant* var = find_variant(staged ? 1 : 0, p.res_mode, (d->flags & VB_F_MODSILU) ? 1 : 0, kinds, want_parts);
   VB_REQUIRE_L(var != nullptr, "vb_conv: no kernel variant");
-  VB_REQUIRE_L(var->parts == want_parts || !((d->tune >> 6) & 1), "vb_conv: no 16-warp epilogue variant for this output combination");
+  VB_REQUIRE_L(var->parts == want_parts || !((d->tune >> 6) & 1), "vb_conv: no ping-pong epilogue variant for this output combination");
+  VB_REQUIRE_L(var->parts == want_parts, "vb_conv: ping-pong epilogue unavailable for this output combination");
   l->fn = var->fn;
-  l->threads = 128 + 128 * var->parts;
+  l->threads = var->parts == 1 ? 384 : 128 + 128 * var->parts;
 
   // Tensor maps.  Activations / residual / outputs: {C, W, H, N} with a {64, bw, bh, bn} box;
   // weights: {K, cout_pad} with a {64, block_n} box.
@@ -1535,7 +1606,7 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
   // independently (pair == 0): the grid is kept even, a surplus CTA finds no work item and exits.
   l->grid = p.pair ? std::min(2 * p.total_q, num_sms() & ~1)
                    : std::min(((p.rowroll ? p.total_q : p.total_tiles) + 1) & ~1, num_sms() & ~1);
-  l->smem_bytes = p.stg_off + (staged ? p.stg_regions * p.gslots * kChunkBytes : 0) + 1024;
+  l->smem_bytes = p.stg_off + eg_mul2 * (staged ? p.stg_regions * p.gslots * kChunkBytes : 0) + 1024;
   l->flops = 2.0 * d->B * d->H * d->W * static_cast<double>(d->cout_pad) * d->taps * (d->cin_pad + d->cin2_pad);
   if (!var->attr_done) {
     cudaError_t e = cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax + 1024);
