@@ -99,9 +99,16 @@ CONV_CASES = [
 ]
 
 
+# vb_conv_desc.tune: library default | single CTA | CTA pair | per-tap boxes | shared haloed boxes | row-rolling layout |
+# ping-pong epilogue | ping-pong + pair.  Layouts a layer cannot take (shared-memory budget, shape) are skipped.
+TUNES = [0, 1, 2, 4, 8, 16, 64, 66]
+
+
+@pytest.mark.parametrize("tune", TUNES)
 @pytest.mark.parametrize("B,R,cin,cout,taps,bn,modsilu,res_mode,clip,kinds", CONV_CASES)
-def test_conv_gemm_vs_conv2d(env, B, R, cin, cout, taps, bn, modsilu, res_mode, clip, kinds):
-    """vb_conv (+vb_weight_prep) vs MPConv semantics (models.py:115-126) with the fused epilogues."""
+def test_conv_gemm_vs_conv2d(env, B, R, cin, cout, taps, bn, modsilu, res_mode, clip, kinds, tune):
+    """vb_conv (+vb_weight_prep) vs MPConv semantics (models.py:115-126) with the fused epilogues, in every layout the
+    plan-time tuner (or a maintainer) can ask for."""
     L, lib, dev = env
     dt = L.operand_torch_dtype()
     g = torch.Generator().manual_seed(B * 1000 + R + cin + cout)
@@ -140,12 +147,17 @@ def test_conv_gemm_vs_conv2d(env, B, R, cin, cout, taps, bn, modsilu, res_mode, 
                    out_rnorm=L.ptr(rn_out), res_rnorm=L.ptr(rn_in), B=B, H=R, W=R,
                    cin_pad=cin_pad, cin2_pad=0, cout_pad=cout, taps=taps, block_n=bn, epi_mode=L.VB_EPI_PLAIN,
                    flags=(L.VB_F_MODSILU if modsilu else 0) | (L.VB_F_CLIP if clip else 0), mod_stride=cout, ld_f32=cout,
-                   res_mode=res_mode, res_t=0.3, clip=1.5)
+                   res_mode=res_mode, res_t=0.3, clip=1.5, tune=tune)
     for i, kd in enumerate(kinds):
         d.out[i], d.out_kind[i], d.out_scale[i] = outs[i].data_ptr(), kd, 0.8
     if any(kd >= 3 for kd in kinds) or res_mode == 2:
         assert bn == cout
-    L.check(lib.vb_conv(C.byref(d), stream()), "vb_conv")
+    rc = lib.vb_conv(C.byref(d), stream())
+    if rc != 0 and tune != 0:
+        msg = lib.vb_last_error().decode()
+        assert any(k in msg for k in ("ping-pong", "row-rolling", "budget")), msg
+        pytest.skip(f"layout not available for this layer: {msg}")
+    L.check(rc, "vb_conv")
     torch.cuda.synchronize()
     tol = 2e-3 if dt == torch.float16 else 8e-3
     assert rel(o32.permute(0, 3, 1, 2), y) < (2e-3 if (modsilu or res_mode >= 2) else 2e-5)   # tanh-based silu / rsqrt

@@ -700,11 +700,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // buffer g), a thread owns a whole 64-column row (two 32-column halves in sequence), each group has its own residual
   // ring, staging ring, barrier and TMA-issuing thread — so the latency chain of one tile's epilogue (accumulator
   // wake-up, tcgen05.ld, proxy fence, staging barrier, TMA issue: ~2 k cycles even for the plainest epilogue) overlaps
-  // the other group's.  Only for one-chunk tiles (block_n == 64).
+  // the other group's.  For tiles of one or two chunks (block_n <= 128).
   constexpr bool EG = PARTS == 1;
   constexpr int NP = EG ? 2 : PARTS;      // column parts of a chunk (EG: processed in sequence by one thread)
   constexpr int HH = EG ? 2 : 1;
-  constexpr int MAXC = EG ? 1 : 4;        // chunks per tile
+  constexpr int MAXC = EG ? 2 : 4;        // chunks per tile
   constexpr int kEpiWarps = EG ? 8 : 4 * PARTS;
   constexpr int kTileWarps = EG ? 4 : kEpiWarps;      // warps working on one tile
   constexpr int kEpiThreads = kTileWarps * 32;
@@ -1023,7 +1023,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int hh = 0; hh < HH; ++hh) {
               const int part = EG ? hh : half;
               const uint32_t ta = taddr + static_cast<uint32_t>(c * 64 + (EG ? hh * CW : 0));
-              if (EG && modsilu && hh > 0) mod_fetch(c, part);
+              if (EG && modsilu && (c > 0 || hh > 0)) mod_fetch(c, part);
               float v[CW];
               if (CW == 32) tmem_ld32(ta, v); else tmem_ld16(ta, v);
               tmem_ld_wait();
@@ -1467,7 +1467,7 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
       const int opts[4][2] = {{4, 3}, {4, 2}, {2, 3}, {2, 2}};      // {residual ring slots, staging regions}
       // tune bit 6: ping-pong epilogue (two groups, each with its own rings): one-chunk tiles only, two residual slots each
       Variant* egv = find_variant(1, d->res_mode, (d->flags & VB_F_MODSILU) ? 1 : 0, kinds, 1);
-      const bool eg_ok = egv != nullptr && egv->parts == 1 && d->block_n == 64 && !want_rowroll && d->res_mode != VB_RES_PIXNORM;
+      const bool eg_ok = egv != nullptr && egv->parts == 1 && d->block_n <= 128 && !want_rowroll && d->res_mode != VB_RES_PIXNORM;
       VB_REQUIRE_L(eg_ok || !((d->tune >> 6) & 1), "vb_conv: no ping-pong epilogue for this layer (needs block_n == 64 and a specialised variant)");
       const int gslots_all = p.gslots;
       bool want_eg = (((d->tune >> 6) & 1) || env_epi_pp) && eg_ok;

@@ -232,8 +232,8 @@ class Plan:
                 # row-rolling layout (bits 4-5) reorder the K sum (1-ulp flips on ~0.3 % of the elements) and bought
                 # nothing measurable, so they stay with the library's deterministic defaults.
                 cands = [(n, t) for n in ns for t in (0, 1, 2)]
-                if outs and cout_pad == 64:      # ping-pong epilogue (tune bit 6): same arithmetic per element, other schedule
-                    cands += [(64, t | 64) for t in (0, 1, 2)]
+                # ping-pong epilogue (tune bit 6, block_n <= 128): same arithmetic per element, other schedule
+                cands += [(n, t | 64) for n in ns if n <= 128 and outs for t in (0, 1, 2)]
                 _TUNE_CACHE[key] = self._tune_conv(d, cands)
                 if os.environ.get("VB_TUNE_LOG"):
                     print("tune", key[:8], "heuristic bn", ns[0], "->", _TUNE_CACHE[key], flush=True)
