@@ -87,9 +87,13 @@ class NVPrecond(torch.nn.Module):
     def invalidate_plans(self):
         """Call after mutating weights (plans bake the normalised bf16 weights)."""
         self._plans.clear()
+        self._sig_tensors = None
 
     def _weight_signature(self):
-        return sum(p._version for p in self.parameters()) + sum(b._version for b in self.buffers())
+        ps = getattr(self, "_sig_tensors", None)
+        if ps is None:          # the parameter/buffer set of an inference net does not change: walk the module tree once
+            ps = self._sig_tensors = list(self.parameters()) + list(self.buffers())
+        return sum(t._version for t in ps)
 
     def plan(self, batch, device):
         key = (int(batch), str(device))
@@ -103,8 +107,15 @@ class NVPrecond(torch.nn.Module):
         return p
 
     def _apply(self, fn, *a, **k):
-        self._plans = {}
-        return super()._apply(fn, *a, **k)
+        # .to()/.cuda()/.half() re-home the parameters the plans point at; a no-op call (generate_images_nvs does
+        # net.to(device) on every invocation, generate_images.py:164-174) must not throw the plans, their tuning and
+        # their captured graphs away
+        before = [(q.data_ptr(), q.dtype, q.device) for q in self.parameters()]
+        out = super()._apply(fn, *a, **k)
+        if before != [(q.data_ptr(), q.dtype, q.device) for q in self.parameters()]:
+            self._plans = {}
+            self._sig_tensors = None
+        return out
 
     # ------------------------------------------------------------------ forward
     def forward(self, src, dst, sigma, geometry=None, conditioning_image=None, force_fp32=False, return_logvar=False,
