@@ -261,6 +261,12 @@ typedef struct vb_heun_desc {
 } vb_heun_desc;
 int vb_heun(const vb_heun_desc* d, void* stream);
 
+/* Uncertainty head u(sigma) = logvar_linear(logvar_fourier(ln(sigma)/4)) (training/models.py:746-747; dual-source mode
+ * :686-688 passes sigma_stride = 2 for c_noise[::2]).  weight is the RAW [channels] fp32 parameter of logvar_linear (the
+ * forced weight normalisation is applied inside), freqs/phases the MPFourier buffers; out is [n] fp32. */
+int vb_logvar(const float* sigma, int32_t n, int32_t sigma_stride, const float* weight, const float* freqs,
+              const float* phases, int32_t channels, float* out, void* stream);
+
 /* Pixel codec (training/encoders.py:58-62). */
 int vb_encode_u8(const uint8_t* src, float* dst, int64_t n, void* stream); /* x/127.5 - 1 */
 int vb_decode_u8(const float* src, uint8_t* dst, int64_t n, void* stream); /* clip(x*127.5+128) */
@@ -285,6 +291,9 @@ int vb_plan_num_ops(const vb_plan* p);
 int vb_plan_run(vb_plan* p, int first, int last, void* stream);
 /* Capture the whole plan into a CUDA graph (once), then launch it. */
 int vb_plan_launch_graph(vb_plan* p, void* stream);
+/* Same for ops [first, last) only; one graph is kept per distinct range.  Used for no_time_enc feature caching
+ * (generate_images.py:52-57): the source-view encoder runs once per batch, the denoising UNet once per sampler step. */
+int vb_plan_launch_graph_range(vb_plan* p, int first, int last, void* stream);
 /* Algorithmic work of one plan run: kind 0 = GEMM+attention FLOPs, 1 = kernel launches. */
 double vb_plan_query(const vb_plan* p, int kind);
 

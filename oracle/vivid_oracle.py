@@ -261,11 +261,24 @@ class OracleNet:
         return out
 
     def __call__(self, src, dst, sigma, geometry=None, conditioning_image=None, return_features=False,
-                 inject_features=None, sr_noise=None):
+                 inject_features=None, sr_noise=None, return_logvar=False):
         if self.dual:
-            return self._forward_dual(src, dst, sigma, geometry, conditioning_image, return_features, inject_features)
-        return self._forward_vanilla(src, dst, sigma, geometry, conditioning_image, return_features, inject_features,
-                                     sr_noise)
+            d = self._forward_dual(src, dst, sigma, geometry, conditioning_image, return_features, inject_features)
+        else:
+            d = self._forward_vanilla(src, dst, sigma, geometry, conditioning_image, return_features, inject_features,
+                                      sr_noise)
+        if return_logvar and not return_features:
+            return d, self.logvar(sigma)
+        return d
+
+    def logvar(self, sigma):
+        """Uncertainty head: snapshot training/models.py:746-747; current tree :686-688 reads c_noise[::2]."""
+        sigma = torch.as_tensor(sigma, dtype=torch.float32, device=self.p["logvar_linear.weight"].device).reshape(-1)
+        c_noise = self._coeffs(sigma)[3]
+        if self.dual:
+            c_noise = c_noise[::2]
+        feat = mp_fourier(c_noise, self.p["logvar_fourier.freqs"], self.p["logvar_fourier.phases"])
+        return mp_conv(feat, self.p["logvar_linear.weight"]).reshape(-1, 1, 1, 1)
 
     def _coeffs(self, sigma):
         sd = self.sigma_data

@@ -398,6 +398,76 @@ def test_denoiser_vs_reference_golden(env, golden, case):
         assert torch.equal(d0, d)
 
 
+def _extra(key):
+    import os
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "extra.pt"), weights_only=False)[key]
+
+
+def _product_cfg(cfg, dev):
+    import vivid_b200
+    net = vivid_b200.NVPrecond(**cfg)
+    shapes = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+    net.load_state_dict(cases.synth_state_dict(shapes))
+    return net.to(dev).eval()
+
+
+@pytest.mark.parametrize("case", ["v_cond", "d_cond"])
+def test_logvar_head_vs_reference_golden(env, case):
+    """return_logvar=True: u(sigma) is all-fp32 in the reference as well, so it agrees to rounding (1e-4 abs: the
+    Fourier phase c_noise*freq reaches ~30 rad, one fp32 ulp of which is 2e-6)."""
+    L, lib, dev = env
+    rec = _extra(f"logvar_{case}")
+    net = _product(case, dev)
+    inp = {k: v.to(dev) for k, v in cases.synth_inputs(case, rec["B"]).items()}
+    sigma = rec["sigma"].to(dev)
+    x = inp["tgt"] + sigma.reshape(-1, 1, 1, 1) * inp["noise"]
+    d, lv = net(inp["src"], x, sigma, inp["geometry"], return_logvar=True)
+    assert lv.dtype == torch.float32 and lv.shape == (rec["B"], 1, 1, 1)
+    assert (lv.cpu() - rec["logvar"]).abs().max() < 1e-4
+    assert rel(d.cpu(), rec["D"]) <= 1e-2
+    d2 = net(inp["src"], x, sigma, inp["geometry"])
+    assert torch.equal(d, d2)
+
+
+@pytest.mark.parametrize("case", ["v_cond", "d_cond"])
+def test_cached_source_features_vs_reference_golden(env, case):
+    """no_time_enc nets (generate_images.py:52-57): return_features runs the source-view encoder alone, inject_features
+    the denoising UNet alone, and edm_sampler uses the pair so that the encoder runs once per batch."""
+    import vivid_b200
+    L, lib, dev = env
+    rec = _extra(f"features_{case}")
+    net = _product_cfg(rec["cfg"], dev)
+    assert net.no_time_enc
+    inp = {k: v.to(dev) for k, v in cases.synth_inputs(case, rec["B"]).items()}
+    n_in = inp["src"].shape[0]
+    for graph in (False, True):
+        net.use_graph = graph
+        feats = net(inp["src"], torch.zeros_like(inp["src"]), torch.ones(n_in, device=dev), inp["geometry"], None,
+                    return_features=True)
+        assert len(feats) == len(rec["features"])
+        for f, ref in zip(feats, rec["features"]):
+            assert f.shape == ref.shape and rel(f.float().cpu(), ref) <= 1e-2
+        sg = rec["sigma"]
+        x = inp["tgt"] + sg * inp["noise"]
+        sigma = torch.full((n_in,), sg, device=dev)
+        d_full = net(inp["src"], x, sigma, inp["geometry"])
+        # the encoder must NOT run on the inject path: poison src, and clobber the plan's feature buffers in between
+        net(torch.full_like(inp["src"], 0.5), x, sigma, inp["geometry"])
+        d_inj = net(torch.full_like(inp["src"], float("nan")), x, sigma, inp["geometry"], inject_features=feats)
+        assert torch.equal(d_inj, d_full), graph
+        c_skip = 0.25 / (sg ** 2 + 0.25)
+        xs = (x[::2] if case == "d_cond" else x).cpu()
+        assert rel(d_inj.cpu(), rec["D"]) <= 1e-2
+        assert rel(d_inj.cpu() - c_skip * xs, rec["D"] - c_skip * xs) <= 1.5e-2
+        # the reference's own feature maps (fp32) are accepted as well
+        d_ref = net(inp["src"], x, sigma, inp["geometry"], inject_features=[f.to(dev) for f in rec["features"]])
+        assert rel(d_ref.cpu(), rec["D"]) <= 1e-2
+    lat = vivid_b200.edm_sampler(net, inp["src"], inp["noise"], labels=inp["geometry"], num_steps=rec["num_steps"])
+    assert rel(lat.cpu(), rec["latents"]) <= 1e-2
+    with pytest.raises(ValueError):
+        net(inp["src"], x, sigma, inp["geometry"], inject_features=feats[:-1])
+
+
 def test_guided_sampler_vs_reference_golden(env, golden):
     """edm_sampler(net + uncond gnet, w=1.5): final image PSNR >= 40 dB against the reference's sample."""
     L, lib, dev = env

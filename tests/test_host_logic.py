@@ -121,9 +121,15 @@ def test_interface_attributes_and_unsupported_flags():
     with pytest.raises(ValueError):
         vivid_b200.NVPrecond(48, 3, 20)
     x = torch.zeros(1, 3, 64, 64)
-    for kw in (dict(return_logvar=True), dict(force_fp32=True), dict(return_features=True), dict(inject_features=[x])):
-        with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):
+        net(x, x, torch.ones(1), None, force_fp32=True)
+    # the optional outputs are served by the CUDA path like everything else
+    for kw in (dict(return_logvar=True), dict(return_features=True), dict(inject_features=[x])):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
             net(x, x, torch.ones(1), None, **kw)
+    unc = vivid_b200.NVPrecond(64, 3, 20, model_channels=64, uncond=True)
+    with pytest.raises(NotImplementedError):                       # no source-view encoder -> no features to hand out
+        unc(x, x, torch.ones(1), None, return_features=True)
 
 
 def test_seed_sharding_matches_reference_formula():

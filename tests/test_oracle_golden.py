@@ -79,6 +79,45 @@ def test_denoiser_against_reference(golden, case):
             assert rel(d, rec["D_nogeom"]) < TOL
 
 
+def _extra(key):
+    import os
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "extra.pt"), weights_only=False)[key]
+
+
+@pytest.mark.parametrize("case", ["v_cond", "d_cond"])
+def test_logvar_head_against_reference(case):
+    """Uncertainty head (return_logvar=True); fixture from tests/golden/make_golden_extra.py."""
+    rec = _extra(f"logvar_{case}")
+    net = O.OracleNet(cases.synth_state_dict(rec["shapes"]), dict(rec["cfg"], dual=case == "d_cond"))
+    inp = cases.synth_inputs(case, rec["B"])
+    x = inp["tgt"] + rec["sigma"].reshape(-1, 1, 1, 1) * inp["noise"]
+    with torch.no_grad():
+        d, lv = net(inp["src"], x, rec["sigma"], inp["geometry"], return_logvar=True)
+    assert lv.shape == rec["logvar"].shape == (rec["B"], 1, 1, 1)
+    assert (lv - rec["logvar"]).abs().max() < 1e-5
+    assert rel(d, rec["D"]) < TOL
+
+
+@pytest.mark.parametrize("case", ["v_cond", "d_cond"])
+def test_cached_source_features_against_reference(case):
+    """no_time_enc nets: return_features / inject_features and the sampler that caches the encoder output."""
+    rec = _extra(f"features_{case}")
+    net = O.OracleNet(cases.synth_state_dict(rec["shapes"]), dict(rec["cfg"], dual=case == "d_cond"))
+    assert net.no_time_enc
+    inp = cases.synth_inputs(case, rec["B"])
+    n_in = inp["src"].shape[0]
+    with torch.no_grad():
+        feats = net(inp["src"], torch.zeros_like(inp["src"]), torch.ones(n_in), inp["geometry"], None, return_features=True)
+        assert len(feats) == len(rec["features"])
+        for f, ref in zip(feats, rec["features"]):
+            assert f.shape == ref.shape and rel(f, ref) < TOL
+        x = inp["tgt"] + rec["sigma"] * inp["noise"]
+        d = net(torch.zeros_like(inp["src"]), x, torch.full((n_in,), rec["sigma"]), inp["geometry"], inject_features=feats)
+        assert rel(d, rec["D"]) < TOL
+        lat = O.edm_sampler(net, inp["src"], inp["noise"], labels=inp["geometry"], num_steps=rec["num_steps"])
+    assert rel(lat, rec["latents"]) < 5 * TOL
+
+
 def test_guided_sampler_against_reference(golden):
     nets = golden["vanilla"]["nets"]
     net = _oracle(nets["v_cond"], "v_cond")

@@ -83,6 +83,7 @@ SIGNATURES = {
     "vb_precond_in": (C.c_int, [C.POINTER(PrecondInDesc), vp]),
     "vb_precond_out": (C.c_int, [C.POINTER(PrecondOutDesc), vp]),
     "vb_heun": (C.c_int, [C.POINTER(HeunDesc), vp]),
+    "vb_logvar": (C.c_int, [vp, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, vp, vp]),
     "vb_encode_u8": (C.c_int, [vp, vp, i64, vp]),
     "vb_decode_u8": (C.c_int, [vp, vp, i64, vp]),
     "vb_plan_create": (C.c_int, [C.POINTER(vp)]),
@@ -100,6 +101,7 @@ SIGNATURES = {
     "vb_plan_num_ops": (C.c_int, [vp]),
     "vb_plan_run": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "vb_plan_launch_graph": (C.c_int, [vp, vp]),
+    "vb_plan_launch_graph_range": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "vb_plan_query": (C.c_double, [vp, C.c_int]),
 }
 

@@ -513,6 +513,34 @@ int precond_out_launch(const vb_precond_out_desc* d, cudaStream_t s) {
   return VB_OK;
 }
 
+// Uncertainty head u(sigma) (training/models.py:746-747, dual :686-688): a 1-output magnitude-preserving linear over the
+// Fourier features of c_noise = ln(sigma)/4.  One block per sample; the weight normalisation (||w||, fp32) is folded in.
+__global__ void __launch_bounds__(128) logvar_kernel(const float* __restrict__ sigma, int sigma_stride, const float* __restrict__ w,
+                                                     const float* __restrict__ freqs, const float* __restrict__ phases, int C,
+                                                     float* __restrict__ out) {
+  __shared__ float red[2][4];
+  const float c_noise = logf(sigma[static_cast<long long>(blockIdx.x) * sigma_stride]) * 0.25f;
+  float dot = 0.f, sq = 0.f;
+  for (int c = threadIdx.x; c < C; c += 128) {
+    const float wc = w[c];
+    dot = fmaf(wc, cosf(fmaf(c_noise, freqs[c], phases[c])) * 1.4142135623730951f, dot);
+    sq = fmaf(wc, wc, sq);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = dot; red[1][threadIdx.x >> 5] = sq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    dot = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    sq = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    const float rc = rsqrtf(static_cast<float>(C));
+    out[blockIdx.x] = dot * rc / (1e-4f + sqrtf(sq) * rc);
+  }
+}
+
 int heun_launch(const vb_heun_desc* d, cudaStream_t s) {
   VB_REQUIRE(d != nullptr && d->d_net && d->x_hat && d->d_cur && d->x_next, "vb_heun: null tensor");
   VB_REQUIRE(d->n > 0 && (d->phase == 0 || d->phase == 1), "vb_heun: bad n/phase");
@@ -542,6 +570,15 @@ extern "C" int vb_encode_u8(const uint8_t* src, float* dst, int64_t n, void* str
 extern "C" int vb_decode_u8(const float* src, uint8_t* dst, int64_t n, void* stream) {
   VB_REQUIRE(src && dst && n > 0, "vb_decode_u8: bad argument");
   vb::decode_u8_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, n);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB_OK;
+}
+extern "C" int vb_logvar(const float* sigma, int32_t n, int32_t sigma_stride, const float* weight, const float* freqs,
+                         const float* phases, int32_t channels, float* out, void* stream) {
+  VB_REQUIRE(sigma && weight && freqs && phases && out, "vb_logvar: null tensor");
+  VB_REQUIRE(n > 0 && channels > 0 && sigma_stride >= 0, "vb_logvar: bad n/channels/stride");
+  vb::logvar_kernel<<<static_cast<unsigned>(n), 128, 0, static_cast<cudaStream_t>(stream)>>>(sigma, sigma_stride, weight, freqs,
+                                                                                             phases, channels, out);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }

@@ -30,8 +30,14 @@ struct vb_plan {
   std::vector<Op> ops;
   double flops = 0.0;
   int launches = 0;
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t exec = nullptr;
+  // one instantiated graph per replayed op range: the whole plan, and -- for no_time_enc feature caching
+  // (generate_images.py:52-57) -- the source-view encoder and the denoising UNet on their own
+  struct Range {
+    int first, last;
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+  };
+  std::vector<Range> graphs;
 };
 
 static int run_op(const Op& op, cudaStream_t s) {
@@ -48,10 +54,11 @@ static int run_op(const Op& op, cudaStream_t s) {
 }
 
 static void drop_graph(vb_plan* p) {
-  if (p->exec) cudaGraphExecDestroy(p->exec);
-  if (p->graph) cudaGraphDestroy(p->graph);
-  p->exec = nullptr;
-  p->graph = nullptr;
+  for (auto& r : p->graphs) {
+    if (r.exec) cudaGraphExecDestroy(r.exec);
+    if (r.graph) cudaGraphDestroy(r.graph);
+  }
+  p->graphs.clear();
 }
 
 extern "C" int vb_plan_create(vb_plan** out) {
@@ -126,10 +133,16 @@ extern "C" int vb_plan_run(vb_plan* p, int first, int last, void* stream) {
   return VB_OK;
 }
 
-extern "C" int vb_plan_launch_graph(vb_plan* p, void* stream) {
+extern "C" int vb_plan_launch_graph_range(vb_plan* p, int first, int last, void* stream) {
   VB_REQUIRE(p != nullptr, "vb_plan_launch_graph: null plan");
+  const int n = static_cast<int>(p->ops.size());
+  if (last < 0 || last > n) last = n;
+  VB_REQUIRE(first >= 0 && first < last, "vb_plan_launch_graph: bad range [%d,%d)", first, last);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (p->exec == nullptr) {
+  cudaGraphExec_t exec = nullptr;
+  for (const auto& r : p->graphs)
+    if (r.first == first && r.last == last) exec = r.exec;
+  if (exec == nullptr) {
     // Capture on a private stream: the caller's stream may be the legacy default stream, which cannot capture.
     cudaStream_t cap = nullptr;
     VB_CHECK_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
@@ -140,10 +153,7 @@ extern "C" int vb_plan_launch_graph(vb_plan* p, void* stream) {
       return VB_ERR_CUDA;
     }
     int rc = VB_OK;
-    for (const Op& op : p->ops) {
-      rc = run_op(op, cap);
-      if (rc != VB_OK) break;
-    }
+    for (int i = first; i < last && rc == VB_OK; ++i) rc = run_op(p->ops[i], cap);
     cudaGraph_t g = nullptr;
     e = cudaStreamEndCapture(cap, &g);
     cudaStreamDestroy(cap);
@@ -155,12 +165,19 @@ extern "C" int vb_plan_launch_graph(vb_plan* p, void* stream) {
       vb::set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
       return VB_ERR_CUDA;
     }
-    p->graph = g;
-    VB_CHECK_CUDA(cudaGraphInstantiate(&p->exec, p->graph, 0));
+    e = cudaGraphInstantiate(&exec, g, 0);
+    if (e != cudaSuccess) {
+      cudaGraphDestroy(g);
+      vb::set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+      return VB_ERR_CUDA;
+    }
+    p->graphs.push_back({first, last, g, exec});
   }
-  VB_CHECK_CUDA(cudaGraphLaunch(p->exec, s));
+  VB_CHECK_CUDA(cudaGraphLaunch(exec, s));
   return VB_OK;
 }
+
+extern "C" int vb_plan_launch_graph(vb_plan* p, void* stream) { return vb_plan_launch_graph_range(p, 0, -1, stream); }
 
 extern "C" double vb_plan_query(const vb_plan* p, int kind) {
   if (p == nullptr) return 0.0;

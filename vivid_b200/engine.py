@@ -462,7 +462,7 @@ class Plan:
                     wkv = self.prep_weight(mod_.x_attn_kv.weight, perm=(2, D))
                     self.conv(f.raw, wkv, f.B, R, Cc, 2 * Cc, 1,
                               qkv=dict(D=D, parts=2, out=[k, v], seq=[sk, sk], off=[S, S], seg_div=feat_seg))
-                    temps.append(f.raw)                        # each feature map feeds exactly one block
+                    # f.raw stays allocated for the life of the plan: return_features / inject_features read and write it
                 y = self.a16(B, R, Cc)
                 temps += [q, k, v, y]
                 # unconditional model: x_attn_kv(0) == 0 -> the S*nseg zero keys are accounted for analytically
@@ -521,6 +521,10 @@ class Plan:
                                           0.0 if net.no_time_enc else 1.0, geom_scale)
             _, features = self.run_unet(enc, src16, Bx, mod, offs, total, collect_features=True)
             feat_seg = 2 if self.dual else 1
+        # ops [0, enc_ops) are the source-view encoder; its outputs (self.features) are what the reference's
+        # return_features / inject_features hand around (training/models.py:664-672, snapshot :612-626)
+        self.enc_ops = self.lib.vb_plan_num_ops(self.handle)
+        self.features = list(features or [])
 
         unet = net.unet
         x16 = self.buf((B * R * R, 64), self.op_dtype)
@@ -565,9 +569,15 @@ class Plan:
                 best[i] = min(best[i], ev[i].elapsed_time(ev[i + 1]))
         return [(k, lab, fl, by, ms) for (k, lab, fl, by), ms in zip(self.op_info, best)]
 
-    def run(self, graph=True):
+    def run(self, graph=True, section="all"):
+        """Replay the plan: everything, the source-view encoder alone ('enc') or the denoising UNet alone ('unet')."""
+        first, last = {"all": (0, -1), "enc": (0, self.enc_ops), "unet": (self.enc_ops, -1)}[section]
         stream = torch.cuda.current_stream(self.device).cuda_stream
         if graph:
-            L.check(self.lib.vb_plan_launch_graph(self.handle, stream), "vb_plan_launch_graph")
+            L.check(self.lib.vb_plan_launch_graph_range(self.handle, first, last, stream), "vb_plan_launch_graph_range")
         else:
-            L.check(self.lib.vb_plan_run(self.handle, 0, -1, stream), "vb_plan_run")
+            L.check(self.lib.vb_plan_run(self.handle, first, last, stream), "vb_plan_run")
+
+    def feature_views(self):
+        """The encoder's cross-attention feature maps as logical NCHW [Bx, C, R, R] views of the 16-bit NHWC buffers."""
+        return [f.raw.view(f.B, f.R, f.R, -1)[..., :f.C].permute(0, 3, 1, 2) for f in self.features]

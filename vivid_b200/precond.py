@@ -13,6 +13,7 @@ the reference's module-level VANILLA_MODE global:
 """
 import torch
 
+from . import _lib as L
 from . import engine
 from .networks import MPConv, MPFourier, SRXAttnUNet, UNetEncoder, XAttnUNet
 
@@ -117,13 +118,22 @@ class NVPrecond(torch.nn.Module):
             self._sig_tensors = None
         return out
 
+    def _logvar(self, sigma, B):
+        """u(sigma) = logvar_linear(logvar_fourier(ln(sigma)/4)) as [B,1,1,1] fp32 (reference models.py:746-747; dual
+        mode reads c_noise[::2], :686-688).  One small CUDA pass (vb_logvar), outside the replayed plan."""
+        lv = torch.empty(B, dtype=torch.float32, device=sigma.device)
+        w = self.logvar_linear.weight.detach().to(torch.float32).reshape(-1).contiguous()
+        f = self.logvar_fourier.freqs.to(torch.float32).contiguous()
+        ph = self.logvar_fourier.phases.to(torch.float32).contiguous()
+        L.check(L.lib().vb_logvar(sigma.data_ptr(), B, 2 if self.dual else 1, w.data_ptr(), f.data_ptr(), ph.data_ptr(),
+                                  w.numel(), lv.data_ptr(), torch.cuda.current_stream(sigma.device).cuda_stream), "vb_logvar")
+        return lv.reshape(-1, 1, 1, 1)
+
     # ------------------------------------------------------------------ forward
     def forward(self, src, dst, sigma, geometry=None, conditioning_image=None, force_fp32=False, return_logvar=False,
                 return_features=False, inject_features=None, **unet_kwargs):
-        if return_features or inject_features is not None:
-            raise NotImplementedError(f"return_features / inject_features (no_time_enc caching) {_UNSUPPORTED}")
-        if return_logvar:
-            raise NotImplementedError(f"return_logvar (training-only uncertainty head) {_UNSUPPORTED}")
+        if (return_features or inject_features is not None) and (self.encoder is None or self.super_res):
+            raise NotImplementedError(f"return_features / inject_features on a net without source-view encoder {_UNSUPPORTED}")
         if force_fp32:
             raise NotImplementedError(f"force_fp32 {_UNSUPPORTED}: the GEMMs run in bf16 with fp32 accumulation")
         if unet_kwargs:
@@ -143,7 +153,17 @@ class NVPrecond(torch.nn.Module):
         with torch.no_grad():
             p = self.plan(B, dst.device)
             p.in_x.copy_(dst)
-            if p.in_src is not None:
+            if inject_features is not None:
+                # no_time_enc caching (edm_sampler, generate_images.py:52-57): the encoder is skipped and the cached maps
+                # feed the cross-attention blocks; src is not read (reference: training/models.py:664-665)
+                views = p.feature_views()
+                if len(inject_features) != len(views):
+                    raise ValueError(f"inject_features must hold {len(views)} feature maps, got {len(inject_features)}")
+                for v, f in zip(views, inject_features):
+                    if f.shape != v.shape:
+                        raise ValueError(f"feature map must be {tuple(v.shape)}, got {tuple(f.shape)}")
+                    v.copy_(f)
+            elif p.in_src is not None:
                 if src.shape != p.in_src.shape:
                     raise ValueError(f"src must be {tuple(p.in_src.shape)}, got {tuple(src.shape)}")
                 p.in_src.copy_(src)
@@ -161,5 +181,11 @@ class NVPrecond(torch.nn.Module):
                 # the reference draws this from the GLOBAL torch RNG on every call;
                 # same call, same device/dtype/shape, so identical noise for identical generator state
                 p.in_noise.copy_(torch.randn_like(conditioning_image))
-            p.run(graph=self.use_graph)
+            if return_features:
+                # the reference returns before the denoising UNet runs (training/models.py:671-672)
+                p.run(graph=self.use_graph, section="enc")
+                return [v.clone(memory_format=torch.channels_last) for v in p.feature_views()]
+            p.run(graph=self.use_graph, section="all" if inject_features is None else "unet")
+            if return_logvar:
+                return p.out_d.clone(), self._logvar(p.in_sigma, B)
             return p.out_d.clone()

@@ -34,16 +34,20 @@ def edm_sampler(net, src, noise, labels=None, gnet=None, conditioning_image=None
         raise NotImplementedError("the sampler state is fp32 (the reference default); other dtypes are not implemented")
     if noise.device.type != "cuda":
         raise RuntimeError("vivid_b200.edm_sampler runs on CUDA only; there is no CPU fallback")
-    if getattr(net, "no_time_enc", None):
-        raise NotImplementedError("no_time_enc feature caching is outside the B200 hot path (no preset enables it)")
     lib = L.lib()
     dual = bool(getattr(net, "dual", False))
     t_dev = sigma_steps(num_steps, sigma_min, sigma_max, rho, noise.device, dtype)
     t_steps = t_dev.tolist()                       # one host sync per sampler call
 
+    # a net whose source-view encoder ignores the noise level runs it once per batch (generate_images.py:52-57)
+    features = None
+    if getattr(net, "no_time_enc", None):
+        features = net(src, torch.zeros_like(src), torch.ones(src.shape[0], dtype=dtype, device=noise.device), labels,
+                       conditioning_image, return_features=True)
+
     def denoise(x, t):
         tt = torch.full((x.shape[0],), t, dtype=dtype, device=x.device)
-        dn = net(src, x, tt, labels, conditioning_image)
+        dn = net(src, x, tt, labels, conditioning_image, inject_features=features)
         dg = gnet(src, x, tt) if guidance != 1 else None
         return dn, dg
 
