@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const op_t* __restri
   __shared__ __align__(128) op_t s_k[2][kBlockKV * D];
   __shared__ __align__(128) op_t s_v[2][kBlockKV * D];
 
+  pdl_grid_sync();
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kBlockQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t bh = static_cast<size_t>(b) * heads + h;
@@ -260,9 +261,9 @@ int attn_launch(const vb_attn_desc* d, cudaStream_t s) {
   const op_t* v = static_cast<const op_t*>(d->v);
   op_t* y = static_cast<op_t*>(d->y);
   if (d->head_dim == 64)
-    attn_kernel<64><<<grid, kAttnThreads, 0, s>>>(q, k, v, y, d->heads, d->sq, d->sk, d->zero_keys);
+    VB_CHECK_CUDA(launch_pdl(attn_kernel<64>, grid, dim3(kAttnThreads), 0, s, q, k, v, y, d->heads, d->sq, d->sk, d->zero_keys));
   else
-    attn_kernel<32><<<grid, kAttnThreads, 0, s>>>(q, k, v, y, d->heads, d->sq, d->sk, d->zero_keys);
+    VB_CHECK_CUDA(launch_pdl(attn_kernel<32>, grid, dim3(kAttnThreads), 0, s, q, k, v, y, d->heads, d->sq, d->sk, d->zero_keys));
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }

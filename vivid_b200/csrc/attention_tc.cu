@@ -159,6 +159,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_grid_sync();      // set-up above overlaps the previous kernel's tail (launch_pdl)
   const uint32_t tmem = tmem_slot;
   const uint32_t sm = pin(smem_u32(smem));
   const uint32_t q_full = pin(smem_u32(&b_q_full)), q_empty = pin(smem_u32(&b_q_empty));
@@ -419,8 +420,8 @@ int attn_tc_launch(const vb_attn_desc* d, cudaStream_t s) {
   static const int dbg = getenv("VB_ATTN_DBG") ? atoi(getenv("VB_ATTN_DBG")) : 0;
   p.dbg = dbg;
   const int grid = std::min(p.n_items, num_sms());
-  if (dbg & 1) attn_tc_kernel<false><<<grid, kAtThreads, kAtSmem, s>>>(mq, mk, mv, p);
-  else attn_tc_kernel<true><<<grid, kAtThreads, kAtSmem, s>>>(mq, mk, mv, p);
+  if (dbg & 1) VB_CHECK_CUDA(launch_pdl(attn_tc_kernel<false>, dim3(grid), dim3(kAtThreads), kAtSmem, s, mq, mk, mv, p));
+  else VB_CHECK_CUDA(launch_pdl(attn_tc_kernel<true>, dim3(grid), dim3(kAtThreads), kAtSmem, s, mq, mk, mv, p));
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }

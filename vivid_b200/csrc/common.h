@@ -31,6 +31,25 @@ void set_error(const char* fmt, ...);
 
 int num_sms();
 
+// Launch with programmatic stream serialisation (unless VB_PDL=0): the kernel's CTAs may start while the previous kernel
+// of the stream drains; the kernel MUST call pdl_grid_sync() (ptx.cuh) before its first global-memory access.
+bool pdl_enabled();
+template <typename... Exp, typename... Act>
+cudaError_t launch_pdl(void (*fn)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Act&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, fn, static_cast<Exp>(args)...);
+}
+
 // Encode a tiled 16-bit (operand format) tensor map with SWIZZLE_128B (inner box = 64 elements = 128 B).
 // dims/strides innermost first; strides in BYTES for dims 1..rank-1.
 int encode_tmap_16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

@@ -775,6 +775,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (p.pair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_grid_sync();      // everything above overlapped the previous kernel's tail; global memory is touched from here on
   if (threadIdx.x == 0) VB_TS(1);
 
   if (warp < 2 || warp == 3) {
@@ -1627,13 +1628,15 @@ int conv_launch(const ConvLaunch* l, cudaStream_t s) {
   cfg.blockDim = dim3(l->threads);
   cfg.dynamicSmemBytes = l->smem_bytes;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, l->fn, l->map_a, l->map_a2, l->map_w, l->map_res, l->map_out, l->p));
   return VB_OK;
 }

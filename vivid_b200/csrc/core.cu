@@ -1,6 +1,8 @@
 // Library core: error reporting, device queries, TMA descriptor encoding.
 #include <mutex>
 
+#include <cstdlib>
+
 #include "common.h"
 
 namespace vb {
@@ -12,6 +14,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("VB_PDL");
+    cached = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return cached != 0;
 }
 
 int num_sms() {

@@ -52,6 +52,7 @@ template <bool DOWN>
 __global__ void __launch_bounds__(kEwThreads) pixnorm_kernel(const op_t* __restrict__ a, op_t* __restrict__ out,
                                                              op_t* __restrict__ out_silu, long long pixels, int H, int W,
                                                              int C, int lpp) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int ppw = 32 / lpp;                         // pixels per warp
   const long long warp_id = (static_cast<long long>(blockIdx.x) * kEwThreads + threadIdx.x) >> 5;
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(kEwThreads) pixnorm_kernel(const op_t* __restr
 __global__ void __launch_bounds__(kEwThreads) up_kernel(const op_t* __restrict__ a, op_t* __restrict__ out,
                                                         op_t* __restrict__ out_silu, long long in_pixels, int Hi, int Wi,
                                                         int C, int lpp) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int ppw = 32 / lpp;
   const long long warp_id = (static_cast<long long>(blockIdx.x) * kEwThreads + threadIdx.x) >> 5;
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(kEwThreads) up_kernel(const op_t* __restrict__
 __global__ void __launch_bounds__(kEwThreads) cat_kernel(const op_t* __restrict__ a, const op_t* __restrict__ b,
                                                          op_t* __restrict__ out, op_t* __restrict__ out_silu,
                                                          long long pixels, int ca, int cb, float wa, float wb, int lpp) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int ppw = 32 / lpp;
   const long long warp_id = (static_cast<long long>(blockIdx.x) * kEwThreads + threadIdx.x) >> 5;
@@ -167,6 +170,7 @@ __global__ void __launch_bounds__(kEwThreads) cat_kernel(const op_t* __restrict_
 // ---- embedding ------------------------------------------------------------------------
 // One block per batch row: Fourier features -> emb_noise (+ emb_label, mp_sum) -> mp_silu.
 __global__ void __launch_bounds__(256) emb_kernel(const vb_emb_desc d) {
+  pdl_grid_sync();
   extern __shared__ float s_in[];   // [cnoise] fourier, then [label_dim] geometry
   const int b = blockIdx.x;
   const float sigma = d.sigma[d.sigma_n == 1 ? 0 : static_cast<size_t>(b) * d.sigma_stride];
@@ -221,6 +225,7 @@ __global__ void __launch_bounds__(256) emb_kernel(const vb_emb_desc d) {
 // reduction per batch row — took ~85 us for 11 904 channels; the modulation must stay fp32, so no tensor cores here.)
 constexpr int kModBM = 64, kModBK = 32;
 __global__ void __launch_bounds__(256) mod_kernel(const vb_emb_desc d) {
+  pdl_grid_sync();
   __shared__ float s_w[kModBM][kModBK + 1];
   __shared__ __align__(16) float s_e[kModBK][32];
   const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
@@ -268,6 +273,7 @@ __global__ void __launch_bounds__(256) mod_kernel(const vb_emb_desc d) {
 
 // ---- preconditioning ------------------------------------------------------------------
 __global__ void __launch_bounds__(256) precond_in_kernel(const vb_precond_in_desc d) {
+  pdl_grid_sync();
   const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long hw = static_cast<long long>(d.R) * d.R;
   if (pix >= hw * d.B) return;
@@ -354,6 +360,7 @@ __global__ void __launch_bounds__(256) precond_in_kernel(const vb_precond_in_des
 }
 
 __global__ void __launch_bounds__(256) precond_out_kernel(const vb_precond_out_desc d) {
+  pdl_grid_sync();
   const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long hw = static_cast<long long>(d.R) * d.R;
   if (pix >= hw * d.B) return;
@@ -448,9 +455,9 @@ int eltwise_launch(const vb_ew_desc* d, cudaStream_t s) {
       const int lpp = lanes_per_pixel(d->ca);
       const long long warps = (pixels + 32 / lpp - 1) / (32 / lpp);
       if (d->kind == VB_EW_PIXNORM)
-        pixnorm_kernel<false><<<warp_grid(warps), kEwThreads, 0, s>>>(a, o, os, pixels, d->H, d->W, d->ca, lpp);
+        VB_CHECK_CUDA(launch_pdl(pixnorm_kernel<false>, dim3(warp_grid(warps)), dim3(kEwThreads), 0, s, a, o, os, pixels, d->H, d->W, d->ca, lpp));
       else
-        pixnorm_kernel<true><<<warp_grid(warps), kEwThreads, 0, s>>>(a, o, os, pixels, d->H, d->W, d->ca, lpp);
+        VB_CHECK_CUDA(launch_pdl(pixnorm_kernel<true>, dim3(warp_grid(warps)), dim3(kEwThreads), 0, s, a, o, os, pixels, d->H, d->W, d->ca, lpp));
       break;
     }
     case VB_EW_UP: {
@@ -458,7 +465,7 @@ int eltwise_launch(const vb_ew_desc* d, cudaStream_t s) {
       const long long in_pixels = pixels / 4;
       const int lpp = lanes_per_pixel(d->ca);
       const long long warps = (in_pixels + 32 / lpp - 1) / (32 / lpp);
-      up_kernel<<<warp_grid(warps), kEwThreads, 0, s>>>(a, o, os, in_pixels, d->H / 2, d->W / 2, d->ca, lpp);
+      VB_CHECK_CUDA(launch_pdl(up_kernel, dim3(warp_grid(warps)), dim3(kEwThreads), 0, s, a, o, os, in_pixels, d->H / 2, d->W / 2, d->ca, lpp));
       break;
     }
     case VB_EW_CAT:
@@ -467,9 +474,9 @@ int eltwise_launch(const vb_ew_desc* d, cudaStream_t s) {
       if (cat) VB_REQUIRE(d->b != nullptr && d->cb > 0 && d->cb % 8 == 0, "vb_eltwise: CAT needs b with cb %% 8 == 0");
       const int lpp = lanes_per_pixel(d->ca + (cat ? d->cb : 0));
       const long long warps = (pixels + 32 / lpp - 1) / (32 / lpp);
-      cat_kernel<<<warp_grid(warps), kEwThreads, 0, s>>>(a, cat ? static_cast<const op_t*>(d->b) : nullptr, o, os, pixels,
-                                                         d->ca, cat ? d->cb : 0, cat ? d->wa : (d->wa != 0.f ? d->wa : 1.0f),
-                                                         cat ? d->wb : 1.0f, lpp);
+      VB_CHECK_CUDA(launch_pdl(cat_kernel, dim3(warp_grid(warps)), dim3(kEwThreads), 0, s, a,
+                               cat ? static_cast<const op_t*>(d->b) : nullptr, o, os, pixels, d->ca, cat ? d->cb : 0,
+                               cat ? d->wa : (d->wa != 0.f ? d->wa : 1.0f), cat ? d->wb : 1.0f, lpp));
       break;
     }
     default:
@@ -484,11 +491,11 @@ int embed_launch(const vb_emb_desc* d, cudaStream_t s) {
   VB_REQUIRE(d->B > 0 && d->cnoise > 0 && d->cemb > 0, "vb_embed: empty problem");
   VB_REQUIRE(d->mod_total == 0 || (d->w_mod && d->mod), "vb_embed: w_mod/mod missing");
   const size_t smem = sizeof(float) * (d->cnoise + (d->w_label ? d->label_dim : 0));
-  emb_kernel<<<dim3(d->B, 4), 256, smem, s>>>(*d);
+  VB_CHECK_CUDA(launch_pdl(emb_kernel, dim3(d->B, 4), dim3(256), smem, s, *d));
   VB_CHECK_CUDA(cudaGetLastError());
   if (d->mod_total > 0) {
     const dim3 grid((d->mod_total + kModBM - 1) / kModBM, (d->B + 31) / 32);
-    mod_kernel<<<grid, 256, 0, s>>>(*d);
+    VB_CHECK_CUDA(launch_pdl(mod_kernel, grid, dim3(256), 0, s, *d));
     VB_CHECK_CUDA(cudaGetLastError());
   }
   return VB_OK;
@@ -499,7 +506,7 @@ int precond_in_launch(const vb_precond_in_desc* d, cudaStream_t s) {
   VB_REQUIRE(d->B > 0 && d->R > 0 && d->cpad >= 8 && d->cpad % 8 == 0, "vb_precond_in: bad extent");
   VB_REQUIRE(!d->im2col || d->cpad >= 9 * (d->cond ? 7 : 4), "vb_precond_in: im2col needs cpad >= 9 * channels");
   const long long pixels = static_cast<long long>(d->B) * d->R * d->R;
-  precond_in_kernel<<<static_cast<unsigned>((pixels + 255) / 256), 256, 0, s>>>(*d);
+  VB_CHECK_CUDA(launch_pdl(precond_in_kernel, dim3(static_cast<unsigned>((pixels + 255) / 256)), dim3(256), 0, s, *d));
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }
@@ -508,7 +515,7 @@ int precond_out_launch(const vb_precond_out_desc* d, cudaStream_t s) {
   VB_REQUIRE(d != nullptr && d->x && d->f && d->sigma && d->d_out, "vb_precond_out: null tensor");
   VB_REQUIRE(d->B > 0 && d->R > 0 && d->ldf >= 4 && d->ldf % 4 == 0, "vb_precond_out: bad extent");
   const long long pixels = static_cast<long long>(d->B) * d->R * d->R;
-  precond_out_kernel<<<static_cast<unsigned>((pixels + 255) / 256), 256, 0, s>>>(*d);
+  VB_CHECK_CUDA(launch_pdl(precond_out_kernel, dim3(static_cast<unsigned>((pixels + 255) / 256)), dim3(256), 0, s, *d));
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }

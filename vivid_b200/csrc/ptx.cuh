@@ -96,6 +96,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the library starts with pdl_grid_sync(): when launched with the programmatic-serialisation attribute
+// (common.h launch_pdl) its CTAs may become resident, and run their set-up (barrier init, TMEM allocation, descriptor
+// prefetch), while the previous kernel of the stream is still draining; the wait returns once that kernel has completed
+// and its writes are visible.  No global memory may be touched before it.  Launched normally both are no-ops.
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------- cluster / CTA pair
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
