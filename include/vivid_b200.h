@@ -39,7 +39,7 @@ typedef enum vb_status {
   VB_ERR_NO_DEVICE = -3 /* no sm_100 device is current */
 } vb_status;
 
-typedef enum vb_dtype { VB_F32 = 0, VB_F16 = 1, VB_BF16 = 2 } vb_dtype;
+typedef enum vb_dtype { VB_F32 = 0, VB_F16 = 1, VB_BF16 = 2, VB_F64 = 3, VB_U8 = 4 } vb_dtype;
 
 const char* vb_last_error(void);
 int vb_abi_version(void);
@@ -48,7 +48,7 @@ int vb_device_check(void);
 /* Measurement plumbing: occupies `stream` for the given time (one spinning thread) so that work enqueued behind it
  * executes back to back, independent of the host's launch rate. */
 int vb_spin(int microseconds, void* stream);
-/* sizeof() of the descriptor structs below, in declaration order (0 = vb_weight_prep_desc ... 7 = vb_heun_desc);
+/* sizeof() of the descriptor structs below, in declaration order (0 = vb_weight_prep_desc ... 7 = vb_heun_desc, 8 = vb_stats_desc);
  * lets a foreign-language binding verify its mirror of the layout.  -1 for an unknown index. */
 int vb_struct_size(int which);
 /* vb_dtype of GEMM operands / stream in this build (VB_F16 unless built with -DVB_OP_BF16). */
@@ -266,6 +266,33 @@ int vb_heun(const vb_heun_desc* d, void* stream);
  * forced weight normalisation is applied inside), freqs/phases the MPFourier buffers; out is [n] fp32. */
 int vb_logvar(const float* sigma, int32_t n, int32_t sigma_stride, const float* weight, const float* freqs,
               const float* phases, int32_t channels, float* out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Metric statistics of `calculate_metrics.py gen` (calculate_stats_for_iterable_nvs, :158-172, :148):
+ *   vb_stats_update: cum_mu[F] += sum_n f[n,:], cum_sigma[F][F] += f^T f, fp64, for a batch of detector features
+ *     f = [feat | feat2] (F = f1 + f2; feat2/f2 = 0 for the plain statistics, the src-view features for the joint_* ones,
+ *     replacing torch.cat + .to(float64) + .sum(0) + features.T @ features).  Deterministic (no atomics).
+ *   vb_psnr_u8: psnr_out[i] = 10 log10(255^2 / mean((images[i] - tgt[i])^2)) per image (fp64 statistics); when cum_sum is
+ *     not NULL, cum_sum[0] += sum_i psnr_out[i] (image order).  tgt is uint8 or fp32 in [0, 255], images uint8.
+ * ------------------------------------------------------------------------ */
+typedef struct vb_stats_desc {
+  const void* feat;  /* [n][ld1] detector features */
+  const void* feat2; /* [n][ld2] or NULL */
+  double* cum_mu;    /* [f1 + f2] */
+  double* cum_sigma; /* [f1 + f2][f1 + f2] */
+  int64_t ld1, ld2;
+  int32_t dtype; /* vb_dtype of feat and feat2: VB_F32 / VB_F16 / VB_BF16 / VB_F64 */
+  int32_t n, f1, f2;
+} vb_stats_desc;
+int vb_stats_update(const vb_stats_desc* d, void* stream);
+int vb_psnr_u8(const uint8_t* images, const void* tgt, int32_t tgt_dtype, int32_t n, int64_t per_image,
+               int64_t tgt_image_stride, double* psnr_out, double* cum_sum, void* stream);
+
+/* Image resize, fp32 NCHW planes [planes][h_in][w_in] -> [planes][h_out][w_out]: the arithmetic of
+ * torch.nn.functional.interpolate(mode="bilinear", align_corners=False, antialias=<0|1>) — the x4 inter-stage upscale
+ * (generate_images.py:322) and the anti-aliased x1/4 low-res conditioning of the SR-only path (:282-283). */
+int vb_resize(const float* src, float* dst, int32_t planes, int32_t h_in, int32_t w_in, int32_t h_out, int32_t w_out,
+              int32_t antialias, void* stream);
 
 /* Pixel codec (training/encoders.py:58-62). */
 int vb_encode_u8(const uint8_t* src, float* dst, int64_t n, void* stream); /* x/127.5 - 1 */

@@ -438,3 +438,45 @@ def compose_geometry(tgt2src, src_k4, tgt_k4, imsize=64):
     std[12:] *= (imsize / 64) ** 2
     g = torch.cat((tgt2src.reshape(*tgt2src.shape[:-2], 12), src_k4, tgt_k4), -1)
     return torch.where(std > 0, (g - mean) / std, torch.zeros_like(g))
+
+
+# ----------------------------------------------------------------------------- metric statistics (calculate_metrics.py)
+
+
+class StatsOracle:
+    """fp64 feature statistics of calculate_stats_for_iterable_nvs: update_mu_sigma (:158-172) and reduce (:174-183)."""
+
+    def __init__(self, dim):
+        self.cum_mu = np.zeros([dim], dtype=np.float64)
+        self.cum_sigma = np.zeros([dim, dim], dtype=np.float64)
+        self.n = 0
+
+    def update(self, features, features2=None):
+        f = np.asarray(features, dtype=np.float64)
+        if features2 is not None:
+            f = np.concatenate([f, np.asarray(features2, dtype=np.float64)], axis=-1)
+        self.cum_mu += f.sum(0)
+        self.cum_sigma += f.T @ f
+        self.n += f.shape[0]
+
+    def finalize(self, num_images=None):
+        n = self.n if num_images is None else num_images
+        mu = self.cum_mu / n
+        sigma = (self.cum_sigma - np.outer(mu, mu) * n) / (n - 1)
+        return dict(mu=mu, sigma=sigma)
+
+
+def psnr_u8(images, tgt):
+    """calculate_metrics.py:148 — 10 log10(255^2 / mean((x - y)^2)) per image, evaluated in fp64."""
+    x = np.asarray(images, dtype=np.float64)
+    y = np.asarray(tgt, dtype=np.float64)
+    return 10 * np.log10(255.0 ** 2 / ((x - y) ** 2).mean(axis=(1, 2, 3)))
+
+
+def frechet_distance(mu, sigma, mu_ref, sigma_ref):
+    """calculate_metrics.py:309-311."""
+    import scipy.linalg
+    m = np.square(mu - mu_ref).sum()
+    s = scipy.linalg.sqrtm(np.dot(sigma, sigma_ref))     # (scipy >= 1.16 has no `disp`; older ones return the same matrix)
+    s = s[0] if isinstance(s, tuple) else s
+    return float(np.real(m + np.trace(sigma + sigma_ref - s * 2)))

@@ -60,3 +60,29 @@ def synth_inputs(case, B, seed=0):
     if dual:
         noise = noise.repeat_interleave(2, dim=0)
     return dict(src=src, tgt=tgt, geometry=geom, noise=noise)
+
+
+# ----------------------------------------------------------------------------- metric statistics (calculate_metrics.py gen)
+class FakeDetector:
+    """Deterministic stand-in for the downloaded detector networks (calculate_metrics.py:29-83): uint8/float NCHW
+    images -> [N, 48] features (4x4 average pooling of a 16x16 image, scaled), so that the statistics code of the
+    reference can run offline.  Injected through the reference's own `_detector_cache`."""
+    feature_dim = 48
+
+    def __call__(self, x):
+        x = torch.as_tensor(x).to(torch.float32)
+        f = torch.nn.functional.adaptive_avg_pool2d(x, 4).flatten(1) / 64.0
+        return f + 0.25 * torch.sin(f * 3.0)
+
+
+def synth_metric_batches(num_batches=3, batch=5, res=16, seed=0):
+    """[(src, tgt, images)] batches: float src/tgt in [0,255] (as the dataset yields them), uint8 generated images."""
+    g = torch.Generator().manual_seed(4242 + seed)
+    out = []
+    for b in range(num_batches):
+        n = batch - (b == num_batches - 1)          # ragged last batch
+        src = torch.rand(n, 3, res, res, generator=g) * 255
+        tgt = torch.rand(n, 3, res, res, generator=g) * 255
+        img = (tgt + 12 * torch.randn(n, 3, res, res, generator=g)).clip(0, 255).to(torch.uint8)
+        out.append((src, tgt, img))
+    return out

@@ -596,3 +596,88 @@ def test_generate_images_nvs_pipeline(env):
     assert c[0].tgt.shape == (3, 3, 64, 64) and c[0].noise.shape == (3, 3, 64, 64)
     m = vivid_b200.get_metrics(iter(c), device=dev)
     assert m["num_images"] == 3 and 3.0 < m["psnr"] < 60.0
+
+
+# ------------------------------------------------------------------------------- metric statistics + resize (§8(f) N2, N3)
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,f1,f2,dtype", [(37, 96, 0, torch.float32), (1, 64, 0, torch.float32), (64, 2048, 0, torch.float32),
+                                           (25, 1024, 1024, torch.float32), (33, 200, 56, torch.float16),
+                                           (16, 48, 48, torch.float64), (70, 130, 0, torch.bfloat16)])
+def test_stats_update_vs_oracle(env, n, f1, f2, dtype):
+    """vb_stats_update against the oracle (fp64 numpy restatement of calculate_metrics.py:158-172), two batches."""
+    import numpy as np
+    from oracle import vivid_oracle as O
+    from vivid_b200 import metrics as M
+    L, lib, dev = env
+    g = torch.Generator().manual_seed(n + f1)
+    F = f1 + f2
+    mu = torch.zeros(F, dtype=torch.float64, device=dev)
+    sg = torch.zeros(F, F, dtype=torch.float64, device=dev)
+    acc = O.StatsOracle(F)
+    for b in range(2):
+        x1 = (torch.randn(n + b, f1, generator=g) * 3 + 1).to(dtype)
+        x2 = (torch.randn(n + b, f2, generator=g) - 2).to(dtype) if f2 else None
+        wide = torch.randn(n + b, f1 + 8, generator=g).to(dtype)          # a strided view: ld > f
+        wide[:, :f1] = x1
+        M.stats_update(mu, sg, wide.to(dev)[:, :f1], None if x2 is None else x2.to(dev))
+        acc.update(x1.double().numpy(), None if x2 is None else x2.double().numpy())
+    assert np.allclose(mu.cpu().numpy(), acc.cum_mu, rtol=1e-13, atol=1e-11)
+    assert np.allclose(sg.cpu().numpy(), acc.cum_sigma, rtol=1e-13, atol=1e-10)
+    assert torch.equal(sg, sg.T)                                           # mirrored blocks: exactly symmetric
+
+
+@pytest.mark.gpu
+def test_psnr_and_stats_iterable_vs_reference_golden(env):
+    """calculate_stats_for_iterable_nvs (CUDA accumulation) against the reference's own outputs for the same batches and
+    the same fake detector (tests/golden/make_golden_metrics.py)."""
+    import os
+    import numpy as np
+    import vivid_b200
+    from oracle import vivid_oracle as O
+    from vivid_b200 import metrics as M
+    L, lib, dev = env
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "metrics.pt"), weights_only=False)
+    batches = cases.synth_metric_batches()
+    it = [dict(src=s, tgt=t, images=i) for s, t, i in batches]
+    last = None
+    for r, ref in vivid_b200.calculate_stats_for_iterable_nvs(it, metrics=g["metrics"], verbose=False, device=dev,
+                                                               detectors={"fid": cases.FakeDetector()}):
+        last = (r, ref)
+    r, ref = last
+    assert r.stats["num_images"] == g["stats"]["num_images"] and ref.stats["num_images"] == g["ref"]["num_images"]
+    for side, got in (("stats", r.stats), ("ref", ref.stats)):
+        for name in ("fid", "joint_fid"):
+            # the detector ran on the GPU here (fp32 features differ in the last bit from the CPU golden's)
+            assert np.allclose(got[name]["mu"], g[side][name]["mu"], rtol=1e-5, atol=1e-6)
+            assert np.allclose(got[name]["sigma"], g[side][name]["sigma"], rtol=1e-4, atol=1e-5)
+    assert abs(float(r.stats["psnr"]["val"][0]) - float(np.asarray(g["stats"]["psnr"]["val"]).reshape(-1)[0])) < 1e-4
+    res = vivid_b200.calculate_metrics_from_stats_nvs(r.stats, ref.stats, metrics=g["metrics"], verbose=False)
+    for k, v in g["results"].items():
+        assert abs(res[k] - v) < 1e-3 * max(1.0, abs(v)), (k, res[k], v)
+    # PSNR kernel alone: uint8 and float targets, bit-for-bit repeatable, against the fp64 oracle
+    src, tgt, img = batches[0]
+    for t in (tgt, tgt.clip(0, 255).to(torch.uint8)):
+        cum = torch.zeros(1, dtype=torch.float64, device=dev)
+        p1 = M.psnr_u8(img.to(dev), t.to(dev), cum)
+        p2 = M.psnr_u8(img.to(dev), t.to(dev))
+        want = O.psnr_u8(img.numpy(), t.to(torch.float32).numpy())
+        assert torch.equal(p1, p2) and np.allclose(p1.cpu().numpy(), want, rtol=1e-12, atol=0)
+        assert abs(cum.item() - want.sum()) < 1e-10
+    same = M.psnr_u8(img.to(dev), img.to(dev))
+    assert torch.isinf(same).all()                                         # identical images: mse 0 -> +inf, as in torch
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,size,aa", [((3, 3, 64, 64), 256, False), ((2, 3, 16, 16), 64, False), ((2, 3, 256, 256), 64, True),
+                                           ((1, 3, 64, 64), 16, True), ((2, 3, 24, 40), (96, 100), False),
+                                           ((2, 1, 40, 24), (10, 7), True), ((1, 3, 16, 16), 16, False)])
+def test_resize_vs_torch_interpolate(env, shape, size, aa):
+    """vb_resize against torch.nn.functional.interpolate(mode='bilinear', antialias=aa) — the library op the reference
+    calls at generate_images.py:282-283,322 — on the same device."""
+    from vivid_b200 import metrics as M
+    L, lib, dev = env
+    x = (torch.rand(shape, generator=torch.Generator().manual_seed(shape[-1])) * 2 - 1).to(dev)
+    want = torch.nn.functional.interpolate(x, size=size, mode="bilinear", antialias=aa)
+    got = M.resize_bilinear(x, size, antialias=aa)
+    assert got.shape == want.shape and got.dtype == torch.float32
+    assert (got - want).abs().max().item() <= 2e-6

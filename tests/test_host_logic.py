@@ -176,19 +176,25 @@ def test_compose_geometry_and_schedule_match_reference(golden):
 _WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
-from vivid_b200.generate import split_seeds, get_metrics, EasyDict
+from vivid_b200.generate import split_seeds, reduce_psnr
+from vivid_b200.metrics import finalize_stats
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
 rank = dist.get_rank()
 batches = split_seeds(10, 3, rank, 2)
-def it():
-    for b in batches:
-        img = torch.stack([torch.full((3, 4, 4), float(10 * i), dtype=torch.uint8) for i in b])
-        tgt = torch.stack([torch.full((3, 4, 4), float(10 * i + 2)) for i in b])
-        yield EasyDict(images=img, tgt=tgt)
-m = get_metrics(it(), device=torch.device("cpu"))
-assert m["num_images"] == 10, m
+# the per-batch accumulation is CUDA-only (vb_psnr_u8 / vb_stats_update); here: the cross-rank reduction of the
+# accumulators each rank would hold after its shard (calculate_metrics.py:174-183,221-236)
 import math
-assert abs(m["psnr"] - 10 * math.log10(255 ** 2 / 4.0)) < 1e-9, m
+val = 10 * math.log10(255 ** 2 / 4.0)
+n_local = sum(len(b) for b in batches)
+m = reduce_psnr(torch.full([1], val * n_local, dtype=torch.float64), torch.tensor(n_local))
+assert m["num_images"] == 10, m
+assert abs(m["psnr"] - val) < 1e-9, m
+g = torch.Generator().manual_seed(5)
+x = torch.randn(10, 6, generator=g, dtype=torch.float64)
+mine = x[[i for b in batches for i in b]]
+st = finalize_stats(mine.sum(0), mine.T @ mine, 10)
+import numpy as np
+assert np.allclose(st["mu"], x.mean(0).numpy()) and np.allclose(st["sigma"], np.cov(x.numpy(), rowvar=False))
 print("rank", rank, "ok")
 """
 
@@ -204,3 +210,22 @@ def test_world_size_2_sharding_and_metric_reduction(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"rank {r} ok" in o
+
+
+def test_metrics_host_logic_and_cpu_refusal():
+    """calculate_metrics_from_stats_nvs (host numpy/scipy) against the reference's results; CUDA-only accumulation."""
+    import vivid_b200
+    from vivid_b200 import metrics as M
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "metrics.pt"), weights_only=False)
+    res = vivid_b200.calculate_metrics_from_stats_nvs(g["stats"], g["ref"], metrics=g["metrics"], verbose=False)
+    assert set(res) == set(g["results"])
+    for k, v in g["results"].items():
+        assert abs(res[k] - v) < 1e-8 * max(1.0, abs(v)), k
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        M.stats_update(torch.zeros(4, dtype=torch.float64), torch.zeros(4, 4, dtype=torch.float64), torch.zeros(2, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        M.psnr_u8(torch.zeros(1, 3, 2, 2, dtype=torch.uint8), torch.zeros(1, 3, 2, 2))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        vivid_b200.get_metrics(iter([]), device=torch.device("cpu"))
+    with pytest.raises(NotImplementedError):
+        vivid_b200.calculate_stats_for_iterable_nvs([], metrics=["fid"])

@@ -164,3 +164,45 @@ def test_tiny_config_sampler_against_reference(golden):
     with torch.no_grad():
         lat = O.edm_sampler(net, inp["src"], inp["noise"], labels=inp["geometry"], num_steps=8)
     assert rel(lat, nets["sampler_tiny"]["latents"]) < 1e-4
+
+
+# ----------------------------------------------------------------------------- metric statistics (calculate_metrics.py gen)
+def _metrics_golden():
+    import os
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "metrics.pt"), weights_only=False)
+
+
+def test_metric_statistics_against_reference():
+    """Oracle restatement of update_mu_sigma / reduce / psnr / Frechet distance vs the reference's own outputs
+    (tests/golden/make_golden_metrics.py: real calculate_stats_for_iterable_nvs with a fake detector)."""
+    import numpy as np
+    g = _metrics_golden()
+    det = cases.FakeDetector()
+    st, rf, jst, jrf = O.StatsOracle(48), O.StatsOracle(48), O.StatsOracle(96), O.StatsOracle(96)
+    ps = []
+    for src, tgt, img in cases.synth_metric_batches():
+        f_img, f_tgt, f_src = det(img).numpy(), det(tgt).numpy(), det(src).numpy()
+        st.update(f_img)
+        rf.update(f_tgt)
+        jst.update(f_img, f_src)
+        jrf.update(f_tgt, f_src)
+        ps.append(O.psnr_u8(img.numpy(), tgt.numpy()))
+    assert st.n == g["stats"]["num_images"] == 14
+    for name, acc, side in (("fid", st, "stats"), ("fid", rf, "ref"), ("joint_fid", jst, "stats"), ("joint_fid", jrf, "ref")):
+        got = acc.finalize()
+        assert np.allclose(got["mu"], g[side][name]["mu"], rtol=1e-12, atol=1e-13)
+        assert np.allclose(got["sigma"], g[side][name]["sigma"], rtol=1e-9, atol=1e-12)
+    # the reference evaluates PSNR in fp32 (:148): agreement to fp32 rounding
+    assert abs(np.concatenate(ps).mean() - float(np.asarray(g["stats"]["psnr"]["val"]).reshape(-1)[0])) < 1e-4
+    fid = O.frechet_distance(st.finalize()["mu"], st.finalize()["sigma"], rf.finalize()["mu"], rf.finalize()["sigma"])
+    assert abs(fid - g["results"]["fid"]) < 1e-8 * max(1.0, abs(g["results"]["fid"]))
+    jfid = O.frechet_distance(jst.finalize()["mu"], jst.finalize()["sigma"], jrf.finalize()["mu"], jrf.finalize()["sigma"])
+    assert abs(jfid - g["results"]["joint_fid"]) < 1e-8 * max(1.0, abs(g["results"]["joint_fid"]))
+    # known answers: unbiased covariance, identical statistics -> distance 0
+    x = np.random.default_rng(0).normal(size=(40, 7))
+    acc = O.StatsOracle(7)
+    acc.update(x[:25])
+    acc.update(x[25:])
+    assert np.allclose(acc.finalize()["sigma"], np.cov(x, rowvar=False), atol=1e-12)
+    s = acc.finalize()
+    assert abs(O.frechet_distance(s["mu"], s["sigma"], s["mu"], s["sigma"])) < 1e-6

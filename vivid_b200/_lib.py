@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvividb200.so")
 
-VB_F32, VB_F16, VB_BF16 = 0, 1, 2
+VB_F32, VB_F16, VB_BF16, VB_F64, VB_U8 = 0, 1, 2, 3, 4
 VB_EPI_PLAIN, VB_EPI_QKVNORM = 0, 1
 VB_F_MODSILU, VB_F_CLIP = 1, 4
 VB_RES_NONE, VB_RES_PLAIN, VB_RES_PIXNORM, VB_RES_SCALED = 0, 1, 2, 3
@@ -68,6 +68,11 @@ class HeunDesc(C.Structure):
                 ("phase", i32), ("guidance", f32), ("t_hat", f32), ("t_next", f32)]
 
 
+class StatsDesc(C.Structure):
+    _fields_ = [("feat", vp), ("feat2", vp), ("cum_mu", vp), ("cum_sigma", vp), ("ld1", i64), ("ld2", i64),
+                ("dtype", i32), ("n", i32), ("f1", i32), ("f2", i32)]
+
+
 # name -> (restype, argtypes); the smoke/CPU tests check that every one of these is exported.
 SIGNATURES = {
     "vb_last_error": (C.c_char_p, []),
@@ -84,6 +89,9 @@ SIGNATURES = {
     "vb_precond_out": (C.c_int, [C.POINTER(PrecondOutDesc), vp]),
     "vb_heun": (C.c_int, [C.POINTER(HeunDesc), vp]),
     "vb_logvar": (C.c_int, [vp, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, vp, vp]),
+    "vb_stats_update": (C.c_int, [C.POINTER(StatsDesc), vp]),
+    "vb_psnr_u8": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int64, C.c_int64, vp, vp, vp]),
+    "vb_resize": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "vb_encode_u8": (C.c_int, [vp, vp, i64, vp]),
     "vb_decode_u8": (C.c_int, [vp, vp, i64, vp]),
     "vb_plan_create": (C.c_int, [C.POINTER(vp)]),
@@ -105,7 +113,7 @@ SIGNATURES = {
     "vb_plan_query": (C.c_double, [vp, C.c_int]),
 }
 
-STRUCTS = [WeightPrepDesc, ConvDesc, AttnDesc, EwDesc, EmbDesc, PrecondInDesc, PrecondOutDesc, HeunDesc]
+STRUCTS = [WeightPrepDesc, ConvDesc, AttnDesc, EwDesc, EmbDesc, PrecondInDesc, PrecondOutDesc, HeunDesc, StatsDesc]
 
 _lib = None
 

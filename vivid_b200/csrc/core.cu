@@ -145,6 +145,7 @@ extern "C" int vb_struct_size(int which) {
     case 5: return static_cast<int>(sizeof(vb_precond_in_desc));
     case 6: return static_cast<int>(sizeof(vb_precond_out_desc));
     case 7: return static_cast<int>(sizeof(vb_heun_desc));
+    case 8: return static_cast<int>(sizeof(vb_stats_desc));
     default: return -1;
   }
 }

@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from .encoders import StandardRGBEncoder
+from .imageops import resize_bilinear
 from .precond import NVPrecond
 from .sampler import StackedRandomGenerator, edm_sampler
 from . import synthetic
@@ -136,8 +137,9 @@ def generate_images_nvs(
                     kwargs = dict(sampler_kwargs)
                     if super_res:
                         tgt = encoder.encode_latents(r.tgt.to(device))
-                        small = torch.nn.functional.interpolate(tgt, size=tgt.shape[-1] // 4, mode="bilinear", antialias=True)
-                        kwargs["conditioning_image"] = torch.nn.functional.interpolate(small, size=tgt.shape[-1], mode="bilinear")
+                        # low-res conditioning of the SR-only path (generate_images.py:282-283), vb_resize
+                        small = resize_bilinear(tgt, tgt.shape[-1] // 4, antialias=True)
+                        kwargs["conditioning_image"] = resize_bilinear(small, tgt.shape[-1])
                         torch.manual_seed(int(r.seeds[0]) % (1 << 32))
                     with torch.no_grad():
                         latents = sampler_fn(net=net, src=src, noise=r.noise, labels=r.labels, gnet=gnet,
@@ -150,8 +152,8 @@ def generate_images_nvs(
                         r.noise = rnd.randn([len(r.seeds), sr_model.img_channels, sr_model.img_resolution,
                                              sr_model.img_resolution], device=device)
                         r.labels = sr_geometry.to(device, non_blocking=True)
-                        # inter-stage bilinear upscale (generate_images.py:322; torch library op, once per batch)
-                        low_res = torch.nn.functional.interpolate(latents, size=sr_src.shape[-1], mode="bilinear")
+                        # inter-stage bilinear upscale (generate_images.py:322), vb_resize
+                        low_res = resize_bilinear(latents, sr_src.shape[-1])
                         torch.manual_seed(int(r.seeds[0]) % (1 << 32))
                         with torch.no_grad():
                             sr_latents = sampler_fn(net=sr_model, src=sr_src, noise=r.noise, labels=r.labels, gnet=sr_model,
@@ -177,23 +179,31 @@ def generate_images_nvs(
 
 def get_metrics(image_iter, device=torch.device("cuda")):
     """PSNR leg of calculate_metrics.get_metrics / calculate_stats_for_iterable_nvs
-    (calculate_metrics.py:148,221-236): per-image PSNR of uint8 images against tgt, fp64 sum,
-    two int64 counters and one fp64 scalar all_reduced.  The Inception/DINOv2 detectors need
-    network downloads and are out of scope."""
-    psnr_sum = torch.zeros([], dtype=torch.float64, device=device)
+    (calculate_metrics.py:148,221-236): per-image PSNR of the uint8 images against tgt (vb_psnr_u8, fp64 statistics),
+    one int64 counter and one fp64 sum all_reduced.  The feature-statistics metrics take user-supplied detectors:
+    vivid_b200.metrics.calculate_stats_for_iterable_nvs."""
+    from . import metrics as M
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("vivid_b200.get_metrics runs on CUDA only; there is no CPU fallback")
+    psnr_sum = torch.zeros([1], dtype=torch.float64, device=device)
     count = torch.zeros([], dtype=torch.int64, device=device)
     for r in image_iter:
         if r.images is None:
             continue
-        img = r.images.to(device).to(torch.float64)
-        tgt = r.tgt.to(device).clip(0, 255).to(torch.uint8).to(torch.float64)
+        img = r.images.to(device)
+        tgt = r.tgt.to(device)
         if tgt.shape[0] != img.shape[0]:        # dual-source: targets are duplicated per source
             tgt = tgt[::2]
-        mse = ((img - tgt) ** 2).mean(dim=(1, 2, 3))
-        psnr_sum += (10 * torch.log10(255.0 ** 2 / mse.clamp_min(1e-12))).sum()
+        M.psnr_u8(img, tgt, psnr_sum)
         count += img.shape[0]
+    return reduce_psnr(psnr_sum, count)
+
+
+def reduce_psnr(psnr_sum, count):
+    """Cross-rank reduction of the PSNR accumulators (calculate_metrics.py:221-236). Host logic, any device."""
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         torch.distributed.all_reduce(psnr_sum)
         torch.distributed.all_reduce(count)
     n = int(count.item())
-    return dict(psnr=float(psnr_sum.item() / max(n, 1)), num_images=n)
+    return dict(psnr=float(psnr_sum.sum().item() / max(n, 1)), num_images=n)
