@@ -340,7 +340,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step (the reference's --batch option; its default is 32)")
+    ap.add_argument("--batch", type=int, default=128, help="images per GPU per step (the reference's --batch option; its default is 32)")
     ap.add_argument("--num-steps", type=int, default=32, help="Heun steps per stage (reference default)")
     ap.add_argument("--guidance", type=float, default=1.5)
     ap.add_argument("--no-e2e", action="store_true")
