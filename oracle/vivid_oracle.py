@@ -354,8 +354,9 @@ def sigma_schedule(num_steps, sigma_min, sigma_max, rho, device, dtype=torch.flo
 
 
 def edm_sampler(net, src, noise, labels=None, gnet=None, conditioning_image=None, num_steps=32, sigma_min=0.002,
-                sigma_max=80, rho=7, guidance=1, dtype=torch.float32, trace=None):
-    """EDM Heun sampler with autoguidance, S_churn = 0.
+                sigma_max=80, rho=7, guidance=1, S_churn=0, S_min=0, S_max=float("inf"), S_noise=1,
+                dtype=torch.float32, randn_like=torch.randn_like, trace=None):
+    """EDM Heun sampler with autoguidance and the stochastic churn branch (generate_images.py:77-84).
     vanilla: snapshot generate_images.py:41-91; dual-source fold: current generate_images.py:43-118."""
     features = None
     if getattr(net, "no_time_enc", None):
@@ -375,7 +376,13 @@ def edm_sampler(net, src, noise, labels=None, gnet=None, conditioning_image=None
     x_next = noise.to(dtype) * t_steps[0]
     dual = False
     for i, (t_cur, t_next) in enumerate(zip(t_steps[:-1], t_steps[1:])):
-        x_hat, t_hat = x_next, t_cur
+        x_cur = x_next
+        if S_churn > 0 and S_min <= t_cur <= S_max:
+            gamma = min(S_churn / num_steps, math.sqrt(2) - 1)
+            t_hat = t_cur + gamma * t_cur
+            x_hat = x_cur + (t_hat ** 2 - t_cur ** 2).sqrt() * S_noise * randn_like(x_cur)
+        else:
+            x_hat, t_hat = x_cur, t_cur
         d0 = denoise(x_hat, t_hat)
         if trace is not None:
             trace.append(d0.clone())

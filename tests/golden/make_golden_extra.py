@@ -65,5 +65,15 @@ with torch.no_grad():
     out[f"features_{case}"] = dict(B=B, shapes=shapes, cfg=cfg, features=[f.clone() for f in feats], sigma=sg, D=d_full.clone(),
                                    latents=lat.clone(), num_steps=3)
     print(case, "features", [tuple(f.shape) for f in feats], "latents", tuple(lat.shape))
+with torch.no_grad():
+    # ---- stochastic sampler branch (S_churn > 0, generate_images.py:77-84)
+    net, shapes, cfg = build()
+    B = 2
+    inp = cases.synth_inputs(case, B)
+    kw = dict(num_steps=4, S_churn=8, S_min=0.05, S_max=50, S_noise=1.003)
+    torch.manual_seed(77)                         # randn_like is the default torch.randn_like: global CPU generator
+    lat = G.edm_sampler(net, inp["src"], inp["noise"], labels=inp["geometry"], **kw)
+    out[f"churn_{case}"] = dict(B=B, shapes=shapes, cfg=cfg, latents=lat.clone(), seed=77, kwargs=kw)
+    print(case, "churn latents", tuple(lat.shape), float(lat.abs().mean()))
 torch.save(out, path)
 print("wrote", path, os.path.getsize(path) // 1024, "KiB")

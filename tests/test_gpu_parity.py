@@ -468,6 +468,27 @@ def test_cached_source_features_vs_reference_golden(env, case):
         net(inp["src"], x, sigma, inp["geometry"], inject_features=feats[:-1])
 
 
+@pytest.mark.parametrize("case", ["v_cond", "d_cond"])
+def test_stochastic_sampler_vs_reference_golden(env, case):
+    """S_churn > 0 (generate_images.py:77-84): the reference's noise came from the CPU generator (seed 77), so the same
+    draws are fed through randn_like; the churn coefficients are evaluated in fp32 like the reference's 0-dim tensors."""
+    import vivid_b200
+    L, lib, dev = env
+    rec = _extra(f"churn_{case}")
+    net = _product_cfg(rec["cfg"], dev)
+    inp = {k: v.to(dev) for k, v in cases.synth_inputs(case, rec["B"]).items()}
+    torch.manual_seed(rec["seed"])
+    draws = []
+
+    def cpu_randn_like(x):
+        draws.append(tuple(x.shape))
+        return torch.randn(x.shape, dtype=x.dtype).to(x.device)
+
+    lat = vivid_b200.edm_sampler(net, inp["src"], inp["noise"], labels=inp["geometry"], randn_like=cpu_randn_like, **rec["kwargs"])
+    assert len(draws) >= 2 and draws[0][0] == inp["noise"].shape[0]        # dual: drawn for the 2B interleaved state
+    assert lat.shape == rec["latents"].shape and rel(lat.cpu(), rec["latents"]) <= 1e-2
+
+
 def test_guided_sampler_vs_reference_golden(env, golden):
     """edm_sampler(net + uncond gnet, w=1.5): final image PSNR >= 40 dB against the reference's sample."""
     L, lib, dev = env

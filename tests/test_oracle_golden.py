@@ -118,6 +118,18 @@ def test_cached_source_features_against_reference(case):
     assert rel(lat, rec["latents"]) < 5 * TOL
 
 
+@pytest.mark.parametrize("case", ["v_cond", "d_cond"])
+def test_stochastic_sampler_against_reference(case):
+    """S_churn > 0 branch (generate_images.py:77-84) with the default torch.randn_like and a seeded global generator."""
+    rec = _extra(f"churn_{case}")
+    net = O.OracleNet(cases.synth_state_dict(rec["shapes"]), dict(rec["cfg"], dual=case == "d_cond"))
+    inp = cases.synth_inputs(case, rec["B"])
+    torch.manual_seed(rec["seed"])
+    with torch.no_grad():
+        lat = O.edm_sampler(net, inp["src"], inp["noise"], labels=inp["geometry"], **rec["kwargs"])
+    assert lat.shape == rec["latents"].shape and rel(lat, rec["latents"]) < 5 * TOL
+
+
 def test_guided_sampler_against_reference(golden):
     nets = golden["vanilla"]["nets"]
     net = _oracle(nets["v_cond"], "v_cond")

@@ -65,7 +65,10 @@ def edm_sampler(net, src, noise, labels=None, gnet=None, conditioning_image=None
         if S_churn > 0 and S_min <= t_cur <= S_max:
             gamma = min(S_churn / num_steps, np.sqrt(2) - 1)
             t_hat = float(np.float32(t_cur) + np.float32(gamma) * np.float32(t_cur))
-            x_hat = x_cur + float(np.sqrt(np.float32(t_hat) ** 2 - np.float32(t_cur) ** 2)) * S_noise * randn_like(x_cur)
+            # (dual-source: the reference draws for the 2B interleaved state and keeps the even rows, :80,:92)
+            eps = randn_like(widen(x_cur))[::2] if dual else randn_like(x_cur)
+            coef = np.sqrt(np.float32(t_hat) ** 2 - np.float32(t_cur) ** 2) * np.float32(S_noise)     # fp32 like the reference
+            x_hat = x_cur + float(coef) * eps
         else:
             t_hat, x_hat = t_cur, x_cur
         dn, dg = denoise(widen(x_hat), t_hat)
