@@ -48,7 +48,7 @@ int vb_device_check(void);
 /* Measurement plumbing: occupies `stream` for the given time (one spinning thread) so that work enqueued behind it
  * executes back to back, independent of the host's launch rate. */
 int vb_spin(int microseconds, void* stream);
-/* sizeof() of the descriptor structs below, in declaration order (0 = vb_weight_prep_desc ... 7 = vb_heun_desc, 8 = vb_stats_desc);
+/* sizeof() of the descriptor structs below, in declaration order (0 = vb_weight_prep_desc ... 7 = vb_heun_desc, 8 = vb_stats_desc, 9 = vb_f32_conv_desc, 10 = vb_f32_op_desc);
  * lets a foreign-language binding verify its mirror of the layout.  -1 for an unknown index. */
 int vb_struct_size(int which);
 /* vb_dtype of GEMM operands / stream in this build (VB_F16 unless built with -DVB_OP_BF16). */
@@ -293,6 +293,44 @@ int vb_psnr_u8(const uint8_t* images, const void* tgt, int32_t tgt_dtype, int32_
  * (generate_images.py:322) and the anti-aliased x1/4 low-res conditioning of the SR-only path (:282-283). */
 int vb_resize(const float* src, float* dst, int32_t planes, int32_t h_in, int32_t w_in, int32_t h_out, int32_t w_out,
               int32_t antialias, void* stream);
+
+/* ------------------------------------------------------------------------
+ * fp32 validation path — NVPrecond(use_fp16=False) / forward(force_fp32=True) (training/models.py:632,697).
+ * CUDA-core kernels on NHWC fp32 activations [B*H*W][C], one per reference op, unfused; meets the north star's
+ * "fp32 mode" parity bound (rel-L2 <= 1e-4), which the tensor cores cannot (tf32 keeps 10 mantissa bits).
+ * For validation, not speed.  Weights come from vb_weight_prep with dst_dtype VB_F32 ([cout][cin*taps], OIHW order).
+ * ------------------------------------------------------------------------ */
+typedef struct vb_f32_conv_desc {
+  const float* x; /* [B*H*W][cin] */
+  const float* w; /* [cout][cin*taps], k = ci*taps + tap (MPConv's F.conv2d, models.py:126) */
+  float* out;     /* [B*H*W][ldo], cout columns written */
+  int32_t B, H, W, cin, cout, taps, ldo;
+} vb_f32_conv_desc;
+int vb_f32_conv(const vb_f32_conv_desc* d, void* stream);
+
+enum { VB_F32_ACT = 0, VB_F32_SUM = 1, VB_F32_CAT = 2, VB_F32_DOWN = 3, VB_F32_UP = 4, VB_F32_QKV = 5, VB_F32_PRECOND_IN = 6 };
+enum { VB_F32_NORM = 1, VB_F32_MOD = 2, VB_F32_SILU = 4 };
+typedef struct vb_f32_op_desc {
+  const float* a;
+  const float* b;   /* SUM: second operand or NULL; CAT: second source; PRECOND_IN: conditioning image (NCHW) or NULL */
+  const float* b2;  /* PRECOND_IN: noise added to the conditioning image as wb * noise, or NULL */
+  const float* mod; /* ACT+MOD: [B][mod_stride] per-channel gains; PRECOND_IN: sigma [B*mod_stride] or NULL */
+  float* out;
+  float* out2;      /* QKV: destination of part 1 / 2 */
+  float* out3;
+  int64_t img_stride; /* PRECOND_IN: floats between consecutive images of a */
+  int32_t kind, flags; /* VB_F32_* ; ACT: VB_F32_NORM | VB_F32_MOD | VB_F32_SILU */
+  int32_t B, H, W;     /* extents of OUT */
+  int32_t ca, cb;      /* channels of a (and of out, except CAT: ca + cb) and of b */
+  int32_t mod_stride;
+  int32_t heads, parts, head_dim, seg_div; /* QKV */
+  int32_t part_seq[3], part_off[3];
+  float wa, wb, clip;  /* SUM/CAT weights; clip <= 0: none; PRECOND_IN: wa = sigma_data, wb = noisy_sr */
+} vb_f32_op_desc;
+int vb_f32_op(const vb_f32_op_desc* d, void* stream);
+/* y[b][s][h*D + d] = softmax(q k^T / sqrt(D)) v, q [B*heads][sq][D], k/v [B*heads][sk][D], plus zero_keys all-zero keys. */
+int vb_f32_attn(const float* q, const float* k, const float* v, float* y, int32_t B, int32_t heads, int32_t sq, int32_t sk,
+                int32_t head_dim, int32_t zero_keys, void* stream);
 
 /* Pixel codec (training/encoders.py:58-62). */
 int vb_encode_u8(const uint8_t* src, float* dst, int64_t n, void* stream); /* x/127.5 - 1 */

@@ -564,6 +564,10 @@ def test_full_size_presets_vs_oracle(env, preset, B):
         with torch.no_grad():
             ref = onet(src, x, sigma, geom, **kw)
         assert rel(d, ref) <= 1e-2, (preset, sg)
+        torch.manual_seed(77)
+        d32 = net(src, x, sigma, geom, force_fp32=True, **kw)          # fp32 validation mode: the north star's 1e-4 bound
+        assert rel(d32, ref) <= 1e-4, (preset, sg, rel(d32, ref))
+        print(f"{preset} sigma={sg}: rel-L2 fp16 path {rel(d, ref):.2e}, fp32 path {rel(d32, ref):.2e}")
     # size-independent properties at the bench batch size: batch-composition independence + graph == eager
     Bb = 8 if preset != "vivid-sr" else 2
     batch = synth_batch(range(Bb), R)
@@ -702,3 +706,82 @@ def test_resize_vs_torch_interpolate(env, shape, size, aa):
     got = M.resize_bilinear(x, size, antialias=aa)
     assert got.shape == want.shape and got.dtype == torch.float32
     assert (got - want).abs().max().item() <= 2e-6
+
+
+# ------------------------------------------------------------------------------- fp32 validation mode
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["v_cond", "v_uncond", "v_sr", "d_cond", "v_tiny"])
+def test_fp32_mode_vs_reference_golden(env, golden, case):
+    """force_fp32=True / use_fp16=False (models.py:632,697): the north star's fp32-mode bound, rel-L2 <= 1e-4 against
+    the reference's fp32 path on identical weights and inputs."""
+    import vivid_b200
+    L, lib, dev = env
+    mode = cases.CASES[case]["mode"]
+    rec = golden[mode]["nets"][case]
+    net = _product(case, dev)
+    inp = {k: v.to(dev) for k, v in cases.synth_inputs(case, rec["B"]).items()}
+    n_in = inp["src"].shape[0]
+    worst = 0.0
+    for sg, ref in rec["D"].items():
+        x = inp["tgt"] + sg * inp["noise"]
+        sigma = torch.full((n_in,), sg, device=dev)
+        if rec["cfg"].get("super_res"):
+            torch.manual_seed(123)
+            net_noise = torch.randn_like(inp["tgt"].cpu()).to(dev)
+            orig = torch.randn_like
+            torch.randn_like = lambda t, *a, **k: net_noise if t.shape == net_noise.shape else orig(t, *a, **k)
+            try:
+                d = net(inp["src"], x, sigma, inp["geometry"], conditioning_image=inp["tgt"], force_fp32=True)
+            finally:
+                torch.randn_like = orig
+        else:
+            d = net(inp["src"], x, sigma, inp["geometry"], force_fp32=True)
+        assert d.dtype == torch.float32 and d.shape == ref.shape
+        c_skip = 0.25 / (sg ** 2 + 0.25)
+        xs = (x[::2] if mode == "dual" else x).cpu()
+        worst = max(worst, rel(d.cpu(), ref), rel(d.cpu() - c_skip * xs, ref - c_skip * xs))
+    assert worst <= 1e-4, (case, worst)
+    if "D_nogeom" in rec:
+        x = inp["tgt"] + 5.0 * inp["noise"]
+        d = net(inp["src"], x, torch.full((n_in,), 5.0, device=dev), force_fp32=True)
+        assert rel(d.cpu(), rec["D_nogeom"]) <= 1e-4
+    # use_fp16=False selects the same path
+    net32 = _product_cfg(dict(cases.CASES[case]["cfg"], use_fp16=False), dev)
+    if not rec["cfg"].get("super_res"):
+        sg = 5.0 if 5.0 in rec["D"] else next(iter(rec["D"]))
+        x = inp["tgt"] + sg * inp["noise"]
+        d2 = net32(inp["src"], x, torch.full((n_in,), sg, device=dev), inp["geometry"])
+        assert rel(d2.cpu(), rec["D"][sg]) <= 1e-4
+
+
+@pytest.mark.gpu
+def test_fp32_kernels_vs_torch(env):
+    """vb_f32_conv / vb_f32_attn against torch fp32 ops on ragged shapes (odd channel counts, partial tiles)."""
+    L, lib, dev = env
+    g = torch.Generator().manual_seed(11)
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for B, R, cin, cout, taps in [(2, 8, 7, 70, 9), (1, 16, 64, 3, 9), (3, 4, 130, 200, 1), (2, 5, 20, 33, 9)]:
+            x = torch.randn(B, cin, R, R, generator=g).to(dev)
+            k = 3 if taps == 9 else 1
+            w = torch.randn(cout, cin, k, k, generator=g).to(dev) * 0.1
+            want = torch.nn.functional.conv2d(x, w, padding=k // 2).permute(0, 2, 3, 1).reshape(-1, cout)
+            xn = x.permute(0, 2, 3, 1).contiguous()
+            out = torch.full((B * R * R, cout + 1), 7.0, device=dev)
+            d = L.F32ConvDesc(x=xn.data_ptr(), w=w.reshape(cout, -1).contiguous().data_ptr(), out=out.data_ptr(), B=B, H=R, W=R,
+                              cin=cin, cout=cout, taps=taps, ldo=cout + 1)
+            L.check(lib.vb_f32_conv(C.byref(d), stream()), "vb_f32_conv")
+            assert rel(out[:, :cout], want) < 2e-6 and (out[:, cout] == 7.0).all()
+        for B, h, sq, sk, D, zk in [(2, 3, 37, 50, 64, 0), (1, 2, 16, 16, 32, 16), (2, 1, 64, 192, 64, 0)]:
+            q, k_, v = (torch.randn(B * h, n, D, generator=g).to(dev) for n in (sq, sk, sk))
+            y = torch.empty(B * sq, h * D, device=dev)
+            L.check(lib.vb_f32_attn(q.data_ptr(), k_.data_ptr(), v.data_ptr(), y.data_ptr(), B, h, sq, sk, D, zk, stream()),
+                    "vb_f32_attn")
+            kz = torch.cat([k_, torch.zeros(B * h, zk, D, device=dev)], 1)
+            vz = torch.cat([v, torch.zeros(B * h, zk, D, device=dev)], 1)
+            w = torch.softmax(q.double() @ kz.double().transpose(1, 2) / math.sqrt(D), dim=-1)
+            want = (w @ vz.double()).reshape(B, h, sq, D).permute(0, 2, 1, 3).reshape(B * sq, h * D)
+            assert rel(y, want.float()) < 2e-6
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev

@@ -121,10 +121,8 @@ def test_interface_attributes_and_unsupported_flags():
     with pytest.raises(ValueError):
         vivid_b200.NVPrecond(48, 3, 20)
     x = torch.zeros(1, 3, 64, 64)
-    with pytest.raises(NotImplementedError):
-        net(x, x, torch.ones(1), None, force_fp32=True)
-    # the optional outputs are served by the CUDA path like everything else
-    for kw in (dict(return_logvar=True), dict(return_features=True), dict(inject_features=[x])):
+    # the optional outputs / modes are served by the CUDA path like everything else
+    for kw in (dict(force_fp32=True), dict(return_logvar=True), dict(return_features=True), dict(inject_features=[x])):
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             net(x, x, torch.ones(1), None, **kw)
     unc = vivid_b200.NVPrecond(64, 3, 20, model_channels=64, uncond=True)

@@ -68,6 +68,22 @@ class HeunDesc(C.Structure):
                 ("phase", i32), ("guidance", f32), ("t_hat", f32), ("t_next", f32)]
 
 
+class F32ConvDesc(C.Structure):
+    _fields_ = [("x", vp), ("w", vp), ("out", vp), ("B", i32), ("H", i32), ("W", i32), ("cin", i32), ("cout", i32),
+                ("taps", i32), ("ldo", i32)]
+
+
+class F32OpDesc(C.Structure):
+    _fields_ = [("a", vp), ("b", vp), ("b2", vp), ("mod", vp), ("out", vp), ("out2", vp), ("out3", vp), ("img_stride", i64),
+                ("kind", i32), ("flags", i32), ("B", i32), ("H", i32), ("W", i32), ("ca", i32), ("cb", i32),
+                ("mod_stride", i32), ("heads", i32), ("parts", i32), ("head_dim", i32), ("seg_div", i32),
+                ("part_seq", i32 * 3), ("part_off", i32 * 3), ("wa", f32), ("wb", f32), ("clip", f32)]
+
+
+VB_F32_ACT, VB_F32_SUM, VB_F32_CAT, VB_F32_DOWN, VB_F32_UP, VB_F32_QKV, VB_F32_PRECOND_IN = range(7)
+VB_F32_NORM, VB_F32_MOD, VB_F32_SILU = 1, 2, 4
+
+
 class StatsDesc(C.Structure):
     _fields_ = [("feat", vp), ("feat2", vp), ("cum_mu", vp), ("cum_sigma", vp), ("ld1", i64), ("ld2", i64),
                 ("dtype", i32), ("n", i32), ("f1", i32), ("f2", i32)]
@@ -89,6 +105,9 @@ SIGNATURES = {
     "vb_precond_out": (C.c_int, [C.POINTER(PrecondOutDesc), vp]),
     "vb_heun": (C.c_int, [C.POINTER(HeunDesc), vp]),
     "vb_logvar": (C.c_int, [vp, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, vp, vp]),
+    "vb_f32_conv": (C.c_int, [C.POINTER(F32ConvDesc), vp]),
+    "vb_f32_op": (C.c_int, [C.POINTER(F32OpDesc), vp]),
+    "vb_f32_attn": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "vb_stats_update": (C.c_int, [C.POINTER(StatsDesc), vp]),
     "vb_psnr_u8": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int64, C.c_int64, vp, vp, vp]),
     "vb_resize": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
@@ -113,7 +132,7 @@ SIGNATURES = {
     "vb_plan_query": (C.c_double, [vp, C.c_int]),
 }
 
-STRUCTS = [WeightPrepDesc, ConvDesc, AttnDesc, EwDesc, EmbDesc, PrecondInDesc, PrecondOutDesc, HeunDesc, StatsDesc]
+STRUCTS = [WeightPrepDesc, ConvDesc, AttnDesc, EwDesc, EmbDesc, PrecondInDesc, PrecondOutDesc, HeunDesc, StatsDesc, F32ConvDesc, F32OpDesc]
 
 _lib = None
 

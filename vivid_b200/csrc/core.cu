@@ -146,6 +146,8 @@ extern "C" int vb_struct_size(int which) {
     case 6: return static_cast<int>(sizeof(vb_precond_out_desc));
     case 7: return static_cast<int>(sizeof(vb_heun_desc));
     case 8: return static_cast<int>(sizeof(vb_stats_desc));
+    case 9: return static_cast<int>(sizeof(vb_f32_conv_desc));
+    case 10: return static_cast<int>(sizeof(vb_f32_op_desc));
     default: return -1;
   }
 }

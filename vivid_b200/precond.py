@@ -4,7 +4,8 @@ Same constructor arguments, attributes and call signature as the reference
 (training/models.py:589-749; vanilla semantics: experiments/code/training/models.py:547-638),
 so it can be passed as net / gnet / sr_model to generate_images_nvs and called as
 `net(src, x, sigma, labels, conditioning_image)` by edm_sampler.  The forward runs entirely in
-libvividb200.so (bf16 tensor-core GEMMs, fp32 accumulation / statistics / residual stream).
+libvividb200.so: fp16 operands and residual stream on the tcgen05 path (fp32 accumulation and statistics), or — with
+use_fp16=False / force_fp32=True, as in the reference (models.py:632,697) — the all-fp32 validation path (engine_f32.py).
 
 Two semantics behind one class, chosen by the constructor arguments instead of
 the reference's module-level VANILLA_MODE global:
@@ -96,13 +97,19 @@ class NVPrecond(torch.nn.Module):
             ps = self._sig_tensors = list(self.parameters()) + list(self.buffers())
         return sum(t._version for t in ps)
 
-    def plan(self, batch, device):
-        key = (int(batch), str(device))
+    def plan(self, batch, device, fp32=False):
+        """The recorded denoiser call for this batch size: the tcgen05 production plan, or — `fp32=True`, i.e.
+        use_fp16=False / force_fp32=True in the reference's terms (models.py:632,697) — the fp32 validation plan."""
+        key = (int(batch), str(device), bool(fp32))
         sig = self._weight_signature()
         hit = self._plans.get(key)
         if hit is not None and hit.weight_versions == sig:
             return hit
-        p = engine.Plan(self, int(batch), device)
+        if fp32:
+            from .engine_f32 import PlanF32
+            p = PlanF32(self, int(batch), device)
+        else:
+            p = engine.Plan(self, int(batch), device)
         p.weight_versions = sig
         self._plans[key] = p
         return p
@@ -134,8 +141,9 @@ class NVPrecond(torch.nn.Module):
                 return_features=False, inject_features=None, **unet_kwargs):
         if (return_features or inject_features is not None) and (self.encoder is None or self.super_res):
             raise NotImplementedError(f"return_features / inject_features on a net without source-view encoder {_UNSUPPORTED}")
-        if force_fp32:
-            raise NotImplementedError(f"force_fp32 {_UNSUPPORTED}: the GEMMs run in bf16 with fp32 accumulation")
+        fp32 = bool(force_fp32) or not self.use_fp16
+        if fp32 and (return_features or inject_features is not None):
+            raise NotImplementedError("return_features / inject_features are not offered by the fp32 validation path")
         if unet_kwargs:
             raise TypeError(f"unexpected arguments {sorted(unet_kwargs)}")
         if dst.device.type != "cuda":
@@ -151,7 +159,7 @@ class NVPrecond(torch.nn.Module):
                 raise TypeError("dual-source mode requires geometry")   # reference: NoneType * int (models.py:631)
         B = n_in // 2 if self.dual else n_in
         with torch.no_grad():
-            p = self.plan(B, dst.device)
+            p = self.plan(B, dst.device, fp32=fp32)
             p.in_x.copy_(dst)
             if inject_features is not None:
                 # no_time_enc caching (edm_sampler, generate_images.py:52-57): the encoder is skipped and the cached maps
