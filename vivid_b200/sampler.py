@@ -6,6 +6,7 @@ schedule is computed with the reference's exact fp32 torch expression; the guida
 Heun updates run in one fused CUDA pass each (vb_heun) instead of ~10 eager pointwise launches.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -18,6 +19,16 @@ def _heun(lib, d_net, d_gnet, x_hat, d_cur, x_next, phase, guidance, t_hat, t_ne
                       x_next=x_next.data_ptr(), n=x_hat.numel(), phase=phase, guidance=float(guidance),
                       t_hat=float(t_hat), t_next=float(t_next))
     L.check(lib.vb_heun(C.byref(desc), torch.cuda.current_stream(x_hat.device).cuda_stream), "vb_heun")
+
+
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device)
+    return _SIDE[key]
 
 
 def sigma_steps(num_steps, sigma_min, sigma_max, rho, device, dtype=torch.float32):
@@ -45,10 +56,27 @@ def edm_sampler(net, src, noise, labels=None, gnet=None, conditioning_image=None
         features = net(src, torch.zeros_like(src), torch.ones(src.shape[0], dtype=dtype, device=noise.device), labels,
                        conditioning_image, return_features=True)
 
+    # The guiding net's call is independent of the main net's (generate_images.py:57-62): replay the two plans on two
+    # streams so that the tail, set-up and single-wave layers of one overlap the other (VB_DUAL_STREAM=0: one stream).
+    side = None
+    if guidance != 1 and gnet is not net and os.environ.get("VB_DUAL_STREAM", "1") != "0":
+        side = _side_stream(noise.device)
+
     def denoise(x, t):
         tt = torch.full((x.shape[0],), t, dtype=dtype, device=x.device)
+        if side is None:
+            dn = net(src, x, tt, labels, conditioning_image, inject_features=features)
+            dg = gnet(src, x, tt) if guidance != 1 else None
+            return dn, dg
+        cur = torch.cuda.current_stream(x.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            dg = gnet(src, x, tt)
         dn = net(src, x, tt, labels, conditioning_image, inject_features=features)
-        dg = gnet(src, x, tt) if guidance != 1 else None
+        cur.wait_stream(side)
+        dg.record_stream(cur)
+        for t_in in (src, x, tt):                 # read on the side stream: keep the allocator from recycling them early
+            t_in.record_stream(side)
         return dn, dg
 
     def widen(xh):                                 # dual-source: every target appears twice (generate_images.py:96-98)
