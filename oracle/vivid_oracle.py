@@ -12,8 +12,10 @@ Each function cites the reference lines it restates.  Two semantics are covered:
 
 Parity pinning: the reference has no tests or golden vectors, so this oracle is
 pinned against OUTPUTS OF THE REFERENCE ITSELF, generated in the build container by
-tests/golden/make_golden.py (imports /root/reference) and committed under tests/golden/.
-tests/test_oracle_golden.py replays them.
+tests/golden/make_golden.py (denoiser / sampler vectors of both trees), make_golden_extra.py (return_logvar,
+return_features / inject_features with no_time_enc, S_churn > 0) and make_golden_metrics.py (the statistics leg of
+calculate_metrics.py gen, run through the reference's own code with a fake detector) — all import /root/reference —
+and committed under tests/golden/.  tests/test_oracle_golden.py replays them.
 """
 import math
 
