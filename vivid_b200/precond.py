@@ -87,7 +87,7 @@ class NVPrecond(torch.nn.Module):
         return net.to(dev).eval()
 
     def invalidate_plans(self):
-        """Call after mutating weights (plans bake the normalised bf16 weights)."""
+        """Call after mutating weights (plans bake the normalised 16-bit weights)."""
         self._plans.clear()
         self._sig_tensors = None
 
