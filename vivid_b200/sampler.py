@@ -69,10 +69,10 @@ def edm_sampler(net, src, noise, labels=None, gnet=None, conditioning_image=None
             dg = gnet(src, x, tt) if guidance != 1 else None
             return dn, dg
         cur = torch.cuda.current_stream(x.device)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            dg = gnet(src, x, tt)
+        side.wait_stream(cur)                     # the inputs are ready; recorded BEFORE net's launch, so gnet does not wait for it
         dn = net(src, x, tt, labels, conditioning_image, inject_features=features)
+        with torch.cuda.stream(side):             # host order net -> gnet as in the reference (global-RNG draws of SR nets, F7)
+            dg = gnet(src, x, tt)
         cur.wait_stream(side)
         dg.record_stream(cur)
         for t_in in (src, x, tt):                 # read on the side stream: keep the allocator from recycling them early
