@@ -274,9 +274,14 @@ __global__ void __launch_bounds__(256) mod_kernel(const vb_emb_desc d) {
 // ---- preconditioning ------------------------------------------------------------------
 __global__ void __launch_bounds__(256) precond_in_kernel(const vb_precond_in_desc d) {
   pdl_grid_sync();
-  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  __shared__ uint4 stage[8][32][8];     // im2col fast path: per-warp transpose so that the 128-byte rows leave coalesced
+  const long long pix_raw = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long hw = static_cast<long long>(d.R) * d.R;
-  if (pix >= hw * d.B) return;
+  const long long total = hw * d.B;
+  const bool fast = d.im2col && d.cpad == 64;
+  if (pix_raw >= total && !fast) return;
+  const bool valid = pix_raw < total;
+  const long long pix = valid ? pix_raw : total - 1;      // (fast path: out-of-range lanes compute a dummy pixel, store nothing)
   const long long n = pix / hw, s = pix - n * hw;
   float c_in = 1.f;
   if (d.sigma != nullptr) {
@@ -339,11 +344,23 @@ __global__ void __launch_bounds__(256) precond_in_kernel(const vb_precond_in_des
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) v[27 + tap] = ok[tap] ? 1.0f : 0.f;
     }
-    uint4* o4 = reinterpret_cast<uint4*>(o);
+    // A thread owns one pixel = one 128-byte output row; written directly, every store instruction of the warp would
+    // touch 32 different rows (16 B each).  Transpose through shared memory (XOR-swizzled 16-byte slots, conflict-free
+    // both ways) so that 8 lanes write one whole row and a store instruction covers 4 contiguous rows.
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      o4[i] = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
-                         pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
+      stage[wid][lane][i ^ (lane & 7)] = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
+                                                    pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
+    __syncwarp();
+    const long long pix0 = pix_raw - lane;                 // first pixel of this warp
+    uint4* out4 = reinterpret_cast<uint4*>(d.out);
+    const int c = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = 4 * i + (lane >> 3);
+      if (pix0 + row < total) out4[(pix0 + row) * 8 + c] = stage[wid][row][c ^ (row & 7)];
+    }
     return;
   }
   for (int base = 0; base < d.cpad; base += 8) {
