@@ -68,6 +68,19 @@ def test_argument_validation_returns_error_codes(lib):
     a = L.AttnDesc(q=1, k=1, v=1, y=1, B=1, heads=1, sq=16, sk=16, head_dim=48)
     assert lib.vb_attn(ctypes.byref(a), None) == -1 and b"head_dim" in lib.vb_last_error()
     assert lib.vb_plan_run(None, 0, -1, None) == -1
+    # the auxiliary entry points validate before they launch as well
+    assert lib.vb_logvar(1, 0, 1, 1, 1, 1, 128, 1, None) == -1 and b"vb_logvar" in lib.vb_last_error()
+    s = L.StatsDesc(feat=1, cum_mu=1, cum_sigma=1, n=4, f1=8, f2=4, ld1=8, dtype=L.VB_F32)
+    assert lib.vb_stats_update(ctypes.byref(s), None) == -1 and b"second feature block" in lib.vb_last_error()
+    s = L.StatsDesc(feat=1, cum_mu=1, cum_sigma=1, n=4, f1=8, ld1=8, dtype=L.VB_U8)
+    assert lib.vb_stats_update(ctypes.byref(s), None) == -1 and b"dtype" in lib.vb_last_error()
+    assert lib.vb_psnr_u8(1, 1, L.VB_F16, 2, 48, 48, 1, None, None) == -1 and b"uint8 or fp32" in lib.vb_last_error()
+    assert lib.vb_resize(1, 1, 3, 256, 256, 16, 16, 1, None) == -1 and b"factor of 8" in lib.vb_last_error()
+    c = L.F32ConvDesc(x=1, w=1, out=1, B=1, H=4, W=4, cin=4, cout=8, taps=4, ldo=8)
+    assert lib.vb_f32_conv(ctypes.byref(c), None) == -1 and b"taps" in lib.vb_last_error()
+    o = L.F32OpDesc(a=1, out=1, kind=L.VB_F32_QKV, B=1, H=4, W=4, ca=100, heads=2, parts=3, head_dim=16, seg_div=1)
+    assert lib.vb_f32_op(ctypes.byref(o), None) == -1 and b"channel count" in lib.vb_last_error()
+    assert lib.vb_f32_attn(1, 1, 1, 1, 1, 1, 16, 16, 48, 0, None) == -1 and b"head_dim" in lib.vb_last_error()
 
 
 @pytest.mark.parametrize("case", list(cases.CASES))
