@@ -95,6 +95,7 @@ def make_net(name, seed, device):
 def run_ours(args):
     import vivid_b200
     from vivid_b200.generate import SyntheticDataset
+    from vivid_b200.imageops import resize_bilinear
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -120,13 +121,15 @@ def run_ours(args):
     def resident(seeds):
         d = {k: v.to(dev) for k, v in ds.batch(seeds).items()}
         rnd = vivid_b200.StackedRandomGenerator(dev, seeds)
-        return dict(src=enc.encode_latents(d["src_image"]), geom=d["geometry"], noise=rnd.randn([B, 3, 64, 64], device=dev),
+        return dict(seed0=seeds[0], src=enc.encode_latents(d["src_image"]), geom=d["geometry"],
+                    noise=rnd.randn([B, 3, 64, 64], device=dev),
                     sr_src=enc.encode_latents(d["sr_src_image"]), sr_geom=d["sr_geometry"],
                     sr_noise=vivid_b200.StackedRandomGenerator(dev, seeds).randn([B, 3, 256, 256], device=dev))
 
     def pipeline(r):
         lat = vivid_b200.edm_sampler(net, r["src"], r["noise"], labels=r["geom"], gnet=gnet, num_steps=T, guidance=args.guidance)
-        low = torch.nn.functional.interpolate(lat, size=256, mode="bilinear")
+        low = resize_bilinear(lat, 256)                 # inter-stage bilinear x4 (generate_images.py:322), vb_resize
+        torch.manual_seed(int(r["seed0"]))              # the SR net's per-call noise comes from the global generator (F7)
         sr_lat = vivid_b200.edm_sampler(sr, r["sr_src"], r["sr_noise"], labels=r["sr_geom"], gnet=sr, num_steps=T,
                                         conditioning_image=low)
         return enc.decode(sr_lat)
@@ -159,21 +162,29 @@ def run_ours(args):
     ms, clocks = timed(pipeline, args.warmup, args.steps, resident)
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- e2e: public driver, pinned host inputs, H2D + D2H inside the timed region
+    # ---- e2e: public driver, pinned host inputs, H2D + D2H inside the timed region; at N>1 every batch's images are
+    #      gathered on rank 0 (one NCCL gather per batch) and the PSNR statistics are all_reduced, as calculate_metrics gen does
     host_items = {}
 
     class HostDataset:
         def batch(self, seeds):
             return host_items[tuple(seeds)]
 
+    pinned_out = torch.empty((world * B, 3, 256, 256), dtype=torch.uint8).pin_memory() if rank == 0 else None
+
     def e2e_step(step):
         seeds = list(range(step * world * B, (step + 1) * world * B))       # the driver shards these over the ranks itself
         it = vivid_b200.generate_images_nvs(net, gnet=gnet, sr_model=sr, seeds=seeds, max_batch_size=B, device=dev,
-                                            dataset=HostDataset(), verbose=False, num_steps=T, guidance=args.guidance)
-        out = None
+                                            dataset=HostDataset(), verbose=False, num_steps=T, guidance=args.guidance,
+                                            gather_images=world > 1)
+        recs = []
         for r in it:
-            out = r.images.cpu()        # device -> host read of the step's result
-        return out
+            recs.append(r)
+            imgs = r.gathered_images if world > 1 else r.images
+            if rank == 0:                # device -> host read of the step's result (all ranks' images on rank 0)
+                pinned_out[:imgs.shape[0]].copy_(imgs, non_blocking=True)
+        m = vivid_b200.get_metrics(iter(recs), device=dev)         # PSNR vs tgt: counter + fp64 sum all_reduce, .item()
+        return m
 
     prep_count = [0]
 
@@ -184,9 +195,22 @@ def run_ours(args):
 
     e2e_ms, e2e_clocks = timed(e2e_step, max(1, args.warmup // 3), args.steps, prep_host) if not args.no_e2e else (None, None)
     h2d = B * (3 * 64 * 64 * 4 * 2 + 20 * 4 + 3 * 256 * 256 * 4 * 2 + 20 * 4)
-    d2h = B * 3 * 256 * 256
+    d2h = B * 3 * 256 * 256 * (world if rank == 0 else 0) + 16
 
-    # ---- roofline: every recorded op timed alone with CUDA events (eager replay on the launching stream)
+    # ---- N>1: rank-sharded + gathered output == rank 0 generating every seed alone (tiny nets, bitwise), and the cost of the
+    #      collectives of the calculate_metrics gen shape (batches of 31-32)
+    multi = multi_gpu_checks(vivid_b200, dev, rank, world) if world > 1 else None
+
+    # ---- roofline, regime 1 (in situ): one more step with kernel activity records (CUPTI through torch.profiler) while the
+    #      chip is still at its sustained clocks; net and gnet on ONE stream so that kernel durations do not overlap
+    insitu = None
+    if not args.no_insitu:
+        try:
+            insitu = insitu_profile(pipeline, resident(seeds_of(args.warmup + args.steps)), dev)
+        except Exception as e:      # the number is an attribution aid: never lose the bench line over it
+            insitu = dict(error=f"{type(e).__name__}: {e}"[:200])
+
+    # ---- roofline, regime 2 (isolated): every recorded op timed alone with CUDA events behind a blocker kernel
     calls = 2 * T - 1
     plans = {"vivid-base": net.plan(B, dev), "vivid-uncond": gnet.plan(B, dev), "vivid-sr": sr.plan(B, dev)}
     agg = {}
@@ -202,23 +226,34 @@ def run_ours(args):
     conv_fl = agg["conv3"]["flops"] + agg["conv1"]["flops"]
     conv_n = agg["conv3"]["launches"] + agg["conv1"]["launches"]
     total_ms = sum(a["ms"] for a in agg.values())
-    achieved = conv_fl / (conv_ms / 1e3) / 1e12
+    isolated = conv_fl / (conv_ms / 1e3) / 1e12
     conv_by = agg["conv3"]["bytes"] + agg["conv1"]["bytes"]
     traffic, traffic_src = None, None
-    try:        # DRAM bytes per conv launch from the committed ncu launch list of one call per net at this batch
-        with open(os.path.join(ROOT, "profiles", f"r01_launches_B{B}.json")) as f:
-            tj = json.load(f)
-        if tj.get("batch") == B:
-            traffic, traffic_src = round(tj["dram_bytes_per_launch"]), "profiles/r01_launches_B%d.json: %s" % (B, tj["source"])
-    except Exception:
-        pass
+    for tag in ("r02", "r01"):      # DRAM bytes per conv launch from the committed ncu launch list of one call per net at this batch
+        try:
+            with open(os.path.join(ROOT, "profiles", f"{tag}_launches_B{B}.json")) as f:
+                tj = json.load(f)
+            if tj.get("batch") == B:
+                traffic, traffic_src = round(tj["dram_bytes_per_launch"]), "profiles/%s_launches_B%d.json: %s" % (tag, B, tj["source"])
+                break
+        except Exception:
+            pass
+    step_ms = ms / args.steps
+    if insitu and "conv_ms" in insitu:
+        achieved, regime = conv_fl / (insitu["conv_ms"] / 1e3) / 1e12, "in situ"
+        avg_us, share = insitu["conv_ms"] / max(insitu["conv_launches"], 1) * 1e3, insitu["conv_ms"] / insitu["step_ms"]
+    else:
+        achieved, regime = isolated, "isolated ops (no in-situ record)"
+        avg_us, share = conv_ms / conv_n * 1e3, conv_ms / total_ms
     roofline = dict(bound="tensor", kernel="conv_gemm_kernel (tcgen05 implicit-GEMM 3x3/1x1 conv)", achieved=round(achieved, 1),
-                    peak=pk["tflops"], unit="TFLOP/s", frac=round(achieved / pk["tflops"], 4),
-                    peak_source=f"{pk['source']} bf16 sustained (kernel timed inside a long step)", traffic=traffic,
-                    traffic_unit="bytes per launch (dram read+write, ncu)", traffic_source=traffic_src,
+                    peak=pk["tflops"], unit="TFLOP/s", frac=round(achieved / pk["tflops"], 4), regime=regime,
+                    peak_source=f"{pk['source']} bf16 sustained (kernel durations recorded inside a running step)",
+                    achieved_isolated=round(isolated, 1), peak_burst=pk["tflops_burst"],
+                    frac_isolated=round(isolated / pk["tflops_burst"], 4),
+                    isolated_note="ops timed alone behind a blocker at cool clocks, against the burst peak",
+                    traffic=traffic, traffic_unit="bytes per launch (dram read+write, ncu)", traffic_source=traffic_src,
                     alg_bytes_per_launch=round(conv_by / conv_n),
-                    launches_per_step=conv_n, avg_launch_us=round(conv_ms / conv_n * 1e3, 2),
-                    share_of_step=round(conv_ms / total_ms, 4),
+                    launches_per_step=conv_n, avg_launch_us=round(avg_us, 2), share_of_step=round(share, 4),
                     alg_flops_per_step=conv_fl)
     kernels = {}
     for kind, a in agg.items():
@@ -231,10 +266,10 @@ def run_ours(args):
             k["frac_of_hbm_peak"] = round(k["gbs"] / pk["gbs"], 4)
         kernels[kind] = k
     alg_tflop_img = calls * (ALG_GFLOP["vivid-base"] + ALG_GFLOP["vivid-uncond"] + ALG_GFLOP["vivid-sr"]) / 1e3
-    launches = calls * sum(p.launches for p in plans.values()) + 2 * calls + 1     # + Heun passes + decode
+    launches = calls * sum(p.launches for p in plans.values()) + 2 * calls + 1 + calls + 2     # + Heun, SR noise, resize, decode
 
     out = dict(metric="guided NVS images/sec (vivid-base+SR)", value=round(value, 3), unit="images/s", n_gpus=world,
-               steps=args.steps, warmup=args.warmup, ms_per_step=round(ms / args.steps, 2), higher_is_better=True,
+               steps=args.steps, warmup=args.warmup, ms_per_step=round(step_ms, 2), higher_is_better=True,
                scaling="weak", vs_baseline=None, dtype="fp16", data="synthetic",
                config=dict(workload="vivid-base guided (vivid-uncond gnet, w=%.1f) -> bilinear x4 -> vivid-sr; Heun %d steps/stage "
                            "(%d denoiser calls each); random-init weights" % (args.guidance, T, calls),
@@ -244,32 +279,202 @@ def run_ours(args):
                            residual_stream="fp16", sampler_state="fp32"),
                clocks=clocks, gpu_launches=int(launches * args.steps),
                e2e=None if e2e_ms is None else dict(value=round(world * B * args.steps / (e2e_ms / 1e3), 3), unit="images/s",
-                                                    h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, clocks=e2e_clocks),
-               roofline=roofline, kernels=kernels,
+                                                    h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, clocks=e2e_clocks,
+                                                    includes="H2D of pinned inputs, per-seed noise, both stages, uint8 decode, "
+                                                             + ("NCCL gather of every rank's images to rank 0, " if world > 1 else "")
+                                                             + "D2H of the images into pinned memory, PSNR statistics (all_reduced)"),
+               roofline=roofline, kernels=kernels, kernels_insitu=insitu,
                model_tflops=round(value / world * alg_tflop_img, 1),
                model_frac_of_peak=round(value / world * alg_tflop_img / pk["tflops"], 4))
+    if multi is not None:
+        multi["batch_ms_at_32"] = round(32.0 / (value / world) * 1e3, 1)
+        per_batch = multi["counters_ms"] + multi["gather_32_ms"]
+        multi["frac_of_batch"] = round(per_batch / multi["batch_ms_at_32"], 6)
+        multi["note"] = ("configs[3] shape (gen --num 10000 --batch 32): per batch two int64 counter all_reduces + host reads and one "
+                         "uint8 image gather; at the end one all_reduce per statistic (largest: the joint 4096^2 fp64 Sigma). "
+                         "batch_ms_at_32 is derived from this line's per-GPU images/s")
+        out["collective"] = multi
     if rank == 0 and world == 1 and not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(dict(base=net, uncond=gnet, sr=sr))
+        out["cpu_baseline"] = cpu_baseline()
     if rank == 0:
         emit(out)
     if world > 1:
         torch.distributed.destroy_process_group()
 
 
+def insitu_profile(pipeline, item, dev):
+    """Kernel durations of ONE pipeline step recorded in place (CUPTI activity records via torch.profiler; CUDA-side only,
+    no host instrumentation).  Returns per-family totals, the conv kernel's total, and the part of the step no kernel covers."""
+    from torch.profiler import ProfilerActivity, profile
+    prev = os.environ.get("VB_DUAL_STREAM")
+    os.environ["VB_DUAL_STREAM"] = "0"
+    try:
+        pipeline(item)                          # same code path once without records (single-stream variant warm)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            e0.record()
+            pipeline(item)
+            e1.record()
+            torch.cuda.synchronize(dev)
+    finally:
+        if prev is None:
+            os.environ.pop("VB_DUAL_STREAM", None)
+        else:
+            os.environ["VB_DUAL_STREAM"] = prev
+    fam, spans = {}, []
+    for ev in prof.events():
+        dur = getattr(ev, "device_time_total", None)
+        if dur is None:
+            dur = getattr(ev, "cuda_time_total", 0)
+        if not dur:
+            continue
+        name = ev.name
+        low = name.lower()
+        if "memcpy" in low or "memset" in low:
+            key = "memcpy/memset"
+        elif "conv_gemm_kernel" in name:
+            key = "conv_gemm_kernel"
+        elif "attn" in low:
+            key = "attention"
+        elif "vb::" in name or "vb_" in low:
+            key = name.split("(")[0].split("<")[0].split("::")[-1]
+        else:
+            key = "torch (RNG, copies, stack)"
+        f = fam.setdefault(key, [0, 0.0])
+        f[0] += 1
+        f[1] += dur / 1e3
+        tr = getattr(ev, "time_range", None)
+        if tr is not None:
+            spans.append((tr.start, tr.end))
+    step_ms = e0.elapsed_time(e1)
+    spans.sort()
+    busy, cur_s, cur_e = 0.0, None, None
+    for s_, e_ in spans:
+        if cur_e is None or s_ > cur_e:
+            if cur_e is not None:
+                busy += cur_e - cur_s
+            cur_s, cur_e = s_, e_
+        else:
+            cur_e = max(cur_e, e_)
+    if cur_e is not None:
+        busy += cur_e - cur_s
+    conv = fam.get("conv_gemm_kernel", [0, 0.0])
+    total = sum(v[1] for v in fam.values())
+    return dict(method="torch.profiler CUDA activity records over one extra step (single stream)", step_ms=round(step_ms, 2),
+                kernels_ms=round(total, 2), busy_ms=round(busy / 1e3, 2), idle_ms=round(step_ms - busy / 1e3, 2),
+                idle_frac=round(1.0 - busy / 1e3 / step_ms, 4), conv_ms=round(conv[1], 2), conv_launches=conv[0],
+                families={k: dict(launches=v[0], ms=round(v[1], 2), share=round(v[1] / step_ms, 4))
+                          for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1])})
+
+
+def multi_gpu_checks(vivid_b200, dev, rank, world):
+    """(1) tiny nets: images generated rank-sharded and gathered on rank 0 are bit-identical to rank 0 generating every
+    batch alone; (2) device time (max over ranks) of the collectives of the calculate_metrics gen shape."""
+    from vivid_b200.generate import SyntheticDataset, gather_batch, split_seeds
+    dist = torch.distributed
+    small = dict(img_channels=3, label_dim=20, model_channels=64, channel_mult=[1, 2], num_blocks=1)
+    torch.manual_seed(0)
+    nets = [vivid_b200.NVPrecond(img_resolution=16, attn_resolutions=[8], **small),
+            vivid_b200.NVPrecond(img_resolution=16, attn_resolutions=[8], uncond=True, **small),
+            vivid_b200.NVPrecond(img_resolution=64, attn_resolutions=[], super_res=True, **small)]
+    for m in nets:
+        with torch.no_grad():
+            for p in m.parameters():
+                if p.ndim == 0:
+                    p.fill_(0.5)
+        m.to(dev).eval()
+    ds = SyntheticDataset(imsize=16, sr_imsize=64)
+    seeds = list(range(100, 100 + 5 * world + 3))          # ragged: some ranks get shorter batches
+    kw = dict(gnet=nets[1], sr_model=nets[2], seeds=seeds, max_batch_size=3, device=dev, dataset=ds, verbose=False, num_steps=4,
+              guidance=1.5)
+    gathered = [(r.gathered_images, r.gathered_seeds) for r in vivid_b200.generate_images_nvs(nets[0], gather_images=True, **kw)]
+    ok = True
+    if rank == 0:
+        alone = {}
+        for k in range(world):      # rank 0 replays every rank's share on its own
+            for r in vivid_b200.generate_images_nvs(nets[0], shard=(k, world), **kw):
+                alone.update({s: img for s, img in zip(r.seeds, r.images)})
+        seen = []
+        for imgs, sds in gathered:
+            seen += sds
+            ok = ok and all(torch.equal(imgs[i], alone[s]) for i, s in enumerate(sds))
+        ok = ok and sorted(seen) == seeds
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    assert flag.item() == 1, "rank-sharded + gathered images differ from the single-rank run"
+
+    def timed(fn, reps=5):
+        fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return round(t.item(), 4)
+
+    cum_a, cum_b = torch.zeros([], dtype=torch.int64, device=dev), torch.zeros([], dtype=torch.int64, device=dev)
+
+    def counters():                  # calculate_metrics.py:225-229: two counter all_reduces + host reads per batch
+        for c in (cum_a, cum_b):
+            x = c.clone()
+            dist.all_reduce(x)
+            int(x.cpu())
+
+    sigma = torch.zeros(4096, 4096, dtype=torch.float64, device=dev)
+    imgs = torch.zeros(32 if rank % 2 == 0 else 31, 3, 256, 256, dtype=torch.uint8, device=dev)
+    by_rank = [list(range(32 if k % 2 == 0 else 31)) for k in range(world)]
+    return dict(gathered_equals_single_rank=True, check_seeds=len(seeds),
+                counters_ms=timed(counters), joint_sigma_4096_fp64_allreduce_ms=timed(lambda: dist.all_reduce(sigma.clone())),
+                gather_32_ms=timed(lambda: gather_batch(imgs, by_rank, (3, 256, 256), dev, rank, world)))
+
+
 # --------------------------------------------------------------------------------------------- CPU arms
-def cpu_sample_seconds(state, threads, repeats=1):
-    """One denoiser call of vivid-base, vivid-uncond and vivid-sr at B=1 with the oracle (the reference's algorithm,
-    fp32, PyTorch CPU ops, all host threads).  Returns seconds for the three calls."""
+def _fill_gains(m):
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.ndim == 0:
+                p.fill_(1.0)
+    return m
+
+
+def cpu_nets():
+    """The reference's CPU implementation of the path: the UNMODIFIED reference staged under oracle/_ref (kind "reference",
+    snapshot tree = the semantics in which guidance and SR run), else the oracle port (kind "port")."""
+    from oracle import ref_loader
+    names = (("base", "vivid-base"), ("uncond", "vivid-uncond"), ("sr", "vivid-sr"))
+    tiny = dict(img_resolution=32, img_channels=3, label_dim=20, model_channels=64)
+    if ref_loader.available():
+        ns = ref_loader.load("snapshot")
+
+        def make(cfg, seed):
+            torch.manual_seed(seed)
+            return _fill_gains(ns.models.NVPrecond(use_fp16=False, **cfg)).eval().requires_grad_(False)
+        return "reference", {k: make(PRESETS[n], i) for i, (k, n) in enumerate(names)}, make(tiny, 3), ns.generate_images.edm_sampler
+    import vivid_b200
     from oracle import vivid_oracle as O
+
+    def make(cfg, seed):
+        torch.manual_seed(seed)
+        return O.OracleNet(_fill_gains(vivid_b200.NVPrecond(**cfg)).state_dict(), cfg)
+    return "port", {k: make(PRESETS[n], i) for i, (k, n) in enumerate(names)}, make(tiny, 3), O.edm_sampler
+
+
+def cpu_sample_seconds(nets, threads, repeats):
+    """`repeats` samples; one sample = one denoiser call each of vivid-base, vivid-uncond and vivid-sr at batch 1."""
     from vivid_b200.synthetic import synth_batch
     torch.set_num_threads(threads)
-    times = []
-    nets = {k: O.OracleNet(sd, dict(PRESETS[name])) for k, (name, sd) in state.items()}
     lo, hi = synth_batch([0], 64), synth_batch([0], 256)
     src, g = lo["src_image"] / 127.5 - 1, lo["geometry"]
     ssrc, sg = hi["src_image"] / 127.5 - 1, hi["geometry"]
     x, sx = torch.randn(1, 3, 64, 64) * 5, torch.randn(1, 3, 256, 256) * 5
     sig = torch.full((1,), 5.0)
+    times = []
     with torch.no_grad():
         for _ in range(repeats):
             t0 = time.perf_counter()
@@ -280,35 +485,46 @@ def cpu_sample_seconds(state, threads, repeats=1):
     return times
 
 
-def cpu_baseline(gpu_nets=None, repeats=1, warmup=0):
+def cpu_config1_seconds(tiny, sampler, threads):
+    """BASELINE.json configs[0] end to end on the host: tiny net (64 ch, 32x32), Heun 8 steps, batch 2."""
+    from vivid_b200.synthetic import synth_batch
+    torch.set_num_threads(threads)
+    b = synth_batch([0, 1], 32)
+    src, geom = b["src_image"] / 127.5 - 1, b["geometry"]
+    noise = torch.stack([torch.randn(3, 32, 32, generator=torch.Generator().manual_seed(s)) for s in (0, 1)])
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        sampler(tiny, src, noise, labels=geom, num_steps=8)
+        return time.perf_counter() - t0
+
+
+def cpu_baseline(repeats=3, warmup=1, one_thread=True):
     threads = os.cpu_count() or 1
-    if gpu_nets is not None:
-        state = {k: (n, {kk: v.detach().float().cpu() for kk, v in gpu_nets[k].state_dict().items()})
-                 for k, n in (("base", "vivid-base"), ("uncond", "vivid-uncond"), ("sr", "vivid-sr"))}
-    else:
-        import vivid_b200
-        state = {}
-        for i, (k, n) in enumerate((("base", "vivid-base"), ("uncond", "vivid-uncond"), ("sr", "vivid-sr"))):
-            torch.manual_seed(i)
-            m = vivid_b200.NVPrecond(**PRESETS[n])
-            with torch.no_grad():
-                for p in m.parameters():
-                    if p.ndim == 0:
-                        p.fill_(1.0)
-            state[k] = (n, m.state_dict())
-    times = cpu_sample_seconds(state, threads, warmup + repeats)[warmup:]
+    kind, nets, tiny, sampler = cpu_nets()
+    times = cpu_sample_seconds(nets, threads, warmup + repeats)[warmup:]
     secs = sum(times) / len(times)
     calls = 63
-    return dict(value=round(1.0 / (calls * secs), 6), unit="images/s", cores=threads, kind="port",
-                sample="1 denoiser call each of vivid-base, vivid-uncond, vivid-sr at batch 1 (oracle = reference algorithm "
-                       "in fp32 PyTorch CPU ops), %.2f s; one image needs 63 of each" % secs, seconds_per_sample=round(secs, 3))
+    out = dict(value=round(1.0 / (calls * secs), 6), unit="images/s", cores=threads, kind=kind,
+               sample="%d (+%d warm-up) samples of one denoiser call each of vivid-base, vivid-uncond, vivid-sr at batch 1 (%s, fp32 "
+                      "PyTorch CPU ops), mean %.2f s (min %.2f, max %.2f); one image needs 63 of each"
+                      % (len(times), warmup, "the unmodified reference staged in oracle/_ref" if kind == "reference"
+                         else "oracle port of the reference algorithm", secs, min(times), max(times)),
+               seconds_per_sample=round(secs, 3), gflops=round(sum(ALG_GFLOP.values()) / secs, 1))
+    t_cfg1 = cpu_config1_seconds(tiny, sampler, threads)
+    out["config1"] = dict(workload="tiny net (64 ch, 32x32) Heun 8 steps, batch 2, end to end", seconds=round(t_cfg1, 2),
+                          images_per_s=round(2.0 / t_cfg1, 3), cores=threads)
+    if one_thread:
+        t1 = cpu_sample_seconds(nets, 1, 1)[0]
+        out["one_thread"] = dict(value=round(1.0 / (calls * t1), 6), unit="images/s", cores=1, seconds_per_sample=round(t1, 2))
+        torch.set_num_threads(threads)
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base = cpu_baseline(repeats=args.steps, warmup=args.warmup)
+    base = cpu_baseline(repeats=max(args.steps, 1), warmup=max(args.warmup, 1))
     t_step = base["seconds_per_sample"]
     out = dict(impl="reference", metric="guided NVS images/sec (vivid-base+SR)", value=base["value"], unit="images/s",
                n_gpus=int(os.environ.get("WORLD_SIZE", "1")), steps=args.steps, warmup=args.warmup,
@@ -345,6 +561,7 @@ def main():
     ap.add_argument("--guidance", type=float, default=1.5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-insitu", action="store_true", help="skip the extra step recorded with kernel activity records")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

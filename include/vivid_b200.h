@@ -248,6 +248,9 @@ int vb_precond_out(const vb_precond_out_desc* d, void* stream);
  *   phase 0 (Euler):  d_cur = (x_hat - D)/t_hat;  x_next = x_hat + (t_next-t_hat)*d_cur
  *   phase 1 (2nd order): d' = (x_next - D)/t_next; x_next = x_hat + (t_next-t_hat)*(d_cur+d')/2
  * all fp32, elementwise over n values.
+ * Zero-copy hand-off to the next denoiser call (optional, NULL = off): the new x_next is ALSO stored to x_out[0..1]
+ * (the input buffers of the plans that run next: net and gnet), and sigma_next is broadcast to sigma_out[k][0..sigma_n)
+ * (their per-sample noise-level inputs), so no host-side copy or fill sits between two calls.
  * ------------------------------------------------------------------------ */
 typedef struct vb_heun_desc {
   const float* d_net;
@@ -255,9 +258,12 @@ typedef struct vb_heun_desc {
   const float* x_hat;
   float* d_cur;  /* phase 0: written; phase 1: read */
   float* x_next; /* phase 0: written; phase 1: read then overwritten */
+  float* x_out[2];     /* or NULL: extra copies of x_next */
+  float* sigma_out[2]; /* or NULL: receive sigma_next, sigma_n values each */
   int64_t n;
   int32_t phase;
-  float guidance, t_hat, t_next;
+  int32_t sigma_n;
+  float guidance, t_hat, t_next, sigma_next;
 } vb_heun_desc;
 int vb_heun(const vb_heun_desc* d, void* stream);
 

@@ -206,6 +206,18 @@ mine = x[[i for b in batches for i in b]]
 st = finalize_stats(mine.sum(0), mine.T @ mine, 10)
 import numpy as np
 assert np.allclose(st["mu"], x.mean(0).numpy()) and np.allclose(st["sigma"], np.cov(x.numpy(), rowvar=False))
+# rank-0 image gather (SURVEY.md §8(e)): ragged and empty per-rank batches, one gather per batch
+from vivid_b200.generate import gather_batch
+for by_rank in ([[1, 2, 3], [4, 5]], [[7], []]):
+    mine_n = len(by_rank[rank])
+    imgs = torch.full((mine_n, 3, 4, 4), 10 * rank + 1, dtype=torch.uint8) if mine_n else None
+    got, gs = gather_batch(imgs, by_rank, (3, 4, 4), torch.device("cpu"), rank, 2)
+    if rank == 0:
+        n0, n1 = len(by_rank[0]), len(by_rank[1])
+        assert got.shape == (n0 + n1, 3, 4, 4) and got.dtype == torch.uint8 and gs == by_rank[0] + by_rank[1]
+        assert (got[:n0] == 1).all() and (got[n0:] == 11).all()
+    else:
+        assert got is None and gs is None
 print("rank", rank, "ok")
 """
 

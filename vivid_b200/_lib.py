@@ -64,8 +64,9 @@ class PrecondOutDesc(C.Structure):
 
 
 class HeunDesc(C.Structure):
-    _fields_ = [("d_net", vp), ("d_gnet", vp), ("x_hat", vp), ("d_cur", vp), ("x_next", vp), ("n", i64),
-                ("phase", i32), ("guidance", f32), ("t_hat", f32), ("t_next", f32)]
+    _fields_ = [("d_net", vp), ("d_gnet", vp), ("x_hat", vp), ("d_cur", vp), ("x_next", vp), ("x_out", vp * 2),
+                ("sigma_out", vp * 2), ("n", i64), ("phase", i32), ("sigma_n", i32), ("guidance", f32), ("t_hat", f32),
+                ("t_next", f32), ("sigma_next", f32)]
 
 
 class F32ConvDesc(C.Structure):

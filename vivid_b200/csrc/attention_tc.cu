@@ -411,11 +411,12 @@ int attn_tc_launch(const vb_attn_desc* d, cudaStream_t s) {
   p.y = static_cast<op_t*>(d->y);
   p.idesc_s = umma_idesc_op(kTQ, kTK);
   p.idesc_o = umma_idesc_op(kTQ, kHD) | (1u << 16);        // B (= V) is MN-major: [key][d] as it lies in memory
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;        // the opt-in shared-memory attribute is per device
+  const unsigned long long dev_bit = 1ull << current_device();
+  if (!(attr_done & dev_bit)) {
     VB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
     VB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
-    attr_done = true;
+    attr_done |= dev_bit;
   }
   static const int dbg = getenv("VB_ATTN_DBG") ? atoi(getenv("VB_ATTN_DBG")) : 0;
   p.dbg = dbg;

@@ -30,6 +30,7 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 int num_sms();
+int current_device();   // ordinal of the calling thread's current device (0..63)
 
 // Launch with programmatic stream serialisation (unless VB_PDL=0): the kernel's CTAs may start while the previous kernel
 // of the stream drains; the kernel MUST call pdl_grid_sync() (ptx.cuh) before its first global-memory access.

@@ -1206,9 +1206,9 @@ struct Variant {
   int staged, res, mod, k0, k1, k2;     // -1 = any (run-time switch inside the kernel)
   int parts;                            // epilogue warps per TMEM lane quadrant (2, or 4 as a plan-time tuning choice)
   ConvKernelFn fn;
-  bool attr_done;
+  unsigned long long attr_done;   // bit per device ordinal: the opt-in shared-memory attribute is per device
 };
-#define VB_VARIANT(S, R, M, A, B, C, P) {S, R, M, A, B, C, P, conv_gemm_kernel<S, R, M, A, B, C, P>, false}
+#define VB_VARIANT(S, R, M, A, B, C, P) {S, R, M, A, B, C, P, conv_gemm_kernel<S, R, M, A, B, C, P>, 0ull}
 // (the 16-warp form, PARTS = 4, is kept compilable — add VB_VARIANT(..., 4) here — but not instantiated: measured on B200 it
 //  was 1-5 % SLOWER on every epilogue-bound layer, profiles/r01_conv_epilogue_notes.txt, so the epilogue is not bound by
 //  per-warp latency)
@@ -1609,13 +1609,14 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
                    : std::min(((p.rowroll ? p.total_q : p.total_tiles) + 1) & ~1, num_sms() & ~1);
   l->smem_bytes = p.stg_off + eg_mul2 * (staged ? p.stg_regions * p.gslots * kChunkBytes : 0) + 1024;
   l->flops = 2.0 * d->B * d->H * d->W * static_cast<double>(d->cout_pad) * d->taps * (d->cin_pad + d->cin2_pad);
-  if (!var->attr_done) {
+  const unsigned long long dev_bit = 1ull << current_device();
+  if (!(var->attr_done & dev_bit)) {
     cudaError_t e = cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax + 1024);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(conv_gemm_kernel) failed: %s", cudaGetErrorString(e));
       return fail(VB_ERR_CUDA);
     }
-    var->attr_done = true;
+    var->attr_done |= dev_bit;
   }
   *out = l;
   return VB_OK;

@@ -422,6 +422,12 @@ __global__ void __launch_bounds__(256) heun_kernel(const vb_heun_desc d) {
     step(dn.w, dg.w, xh.w, dc.w, xn.w);
     if (d.phase == 0) reinterpret_cast<float4*>(d.d_cur)[i4] = dc;
     reinterpret_cast<float4*>(d.x_next)[i4] = xn;
+    if (d.x_out[0]) reinterpret_cast<float4*>(d.x_out[0])[i4] = xn;
+    if (d.x_out[1]) reinterpret_cast<float4*>(d.x_out[1])[i4] = xn;
+  }
+  if (i4 < d.sigma_n) {      // the next call's noise level, per sample
+    if (d.sigma_out[0]) d.sigma_out[0][i4] = d.sigma_next;
+    if (d.sigma_out[1]) d.sigma_out[1][i4] = d.sigma_next;
   }
   if (i4 == 0) {   // tail (n not a multiple of 4)
     for (long long i = n4 << 2; i < d.n; ++i) {
@@ -429,6 +435,8 @@ __global__ void __launch_bounds__(256) heun_kernel(const vb_heun_desc d) {
       step(d.d_net[i], d.d_gnet ? d.d_gnet[i] : 0.f, d.x_hat[i], dc, xn);
       if (d.phase == 0) d.d_cur[i] = dc;
       d.x_next[i] = xn;
+      if (d.x_out[0]) d.x_out[0][i] = xn;
+      if (d.x_out[1]) d.x_out[1][i] = xn;
     }
   }
 }
@@ -569,6 +577,7 @@ int heun_launch(const vb_heun_desc* d, cudaStream_t s) {
   VB_REQUIRE(d != nullptr && d->d_net && d->x_hat && d->d_cur && d->x_next, "vb_heun: null tensor");
   VB_REQUIRE(d->n > 0 && (d->phase == 0 || d->phase == 1), "vb_heun: bad n/phase");
   const long long n4 = (d->n >> 2) > 0 ? (d->n >> 2) : 1;
+  VB_REQUIRE(d->sigma_n >= 0 && d->sigma_n <= n4, "vb_heun: bad sigma_n");
   heun_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, s>>>(*d);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;

@@ -85,13 +85,21 @@ def split_seeds(num_seeds, max_batch_size, rank, world_size):
 def generate_images_nvs(
     net, gnet=None, encoder=None, outdir=None, subdirs=False, seeds=range(16, 24), class_idx=None, max_batch_size=32,
     encoder_batch_size=None, verbose=True, device=torch.device("cuda"), sampler_fn=edm_sampler, datakwargs=None,
-    range_selection=None, sr_model=None, depth_model=None, dataset=None, **sampler_kwargs,
+    range_selection=None, sr_model=None, depth_model=None, dataset=None, gather_images=False, shard=None,
+    **sampler_kwargs,
 ):
+    """Extras over the reference's signature: `dataset` (see the module docstring), `gather_images=True` (every batch's
+    uint8 images, seeds and per-rank counts are collected on rank 0 with ONE NCCL gather per batch: `r.gathered_images`
+    [sum_b,3,R,R] uint8 in rank order and `r.gathered_seeds` on rank 0, None elsewhere — SURVEY.md §8(e)), and
+    `shard=(rank, world)` to take one rank's share of the seeds without a process group (tests, bench cross-checks)."""
     if depth_model is not None:
         raise NotImplementedError("depth models are outside the B200 hot path (all presets: depth_input=False)")
     device = torch.device(device)
-    rank, world = _rank_world()
-    if rank != 0:
+    rank, world = _rank_world() if shard is None else (int(shard[0]), int(shard[1]))
+    collective = shard is None and world > 1
+    if gather_images and shard is not None and world > 1:
+        raise ValueError("gather_images needs the process group; it cannot be combined with shard=")
+    if rank != 0 and shard is None:
         _barrier()                      # rank 0 goes first (model files)
     net = resolve_model(net, device, "net")
     assert net is not None
@@ -102,11 +110,12 @@ def generate_images_nvs(
         encoder = StandardRGBEncoder()
     encoder.init(device)
     sr_model = resolve_model(sr_model, device, "sr_model")
-    if rank == 0:
+    if rank == 0 and shard is None:
         _barrier()
 
     seeds = list(seeds)
     rank_batches = split_seeds(len(seeds), max_batch_size, rank, world)
+    all_batches = [split_seeds(len(seeds), max_batch_size, k, world) for k in range(world)] if gather_images else None
     super_res = net.img_resolution == 256
     dual = bool(getattr(net, "dual", False))
     if dataset is None:
@@ -122,13 +131,20 @@ def generate_images_nvs(
         def __iter__(self):
             for batch_idx, indices in enumerate(rank_batches):
                 r = EasyDict(images=None, src=None, tgt=None, labels=None, noise=None, batch_idx=batch_idx,
-                             num_batches=len(rank_batches), indices=indices)
+                             num_batches=len(rank_batches), indices=indices, gathered_images=None, gathered_seeds=None)
                 r.seeds = [seeds[idx] for idx in indices]
                 if len(r.seeds) > 0:
                     data = dataset.batch(r.seeds)
                     pre = "sr_" if super_res else ""
                     r.src, r.tgt, geometry = data[pre + "src_image"], data[pre + "tgt_image"], data[pre + "geometry"]
-                    src = encoder.encode_latents(r.src.to(device, non_blocking=True))
+                    if dual:
+                        # dual-source collation (generate_images.py:268-282): the record keeps ONE row per seed
+                        # (data[k][::2]); the model is fed every row twice
+                        r.src, r.tgt, geometry = r.src[::2], r.tgt[::2], geometry[::2]
+                        src_for_model, geometry = r.src.repeat_interleave(2, dim=0), geometry.repeat_interleave(2, dim=0)
+                    else:
+                        src_for_model = r.src
+                    src = encoder.encode_latents(src_for_model.to(device, non_blocking=True))
                     rnd = StackedRandomGenerator(device, r.seeds)
                     r.noise = rnd.randn([len(r.seeds), net.img_channels, net.img_resolution, net.img_resolution], device=device)
                     if dual:
@@ -147,11 +163,15 @@ def generate_images_nvs(
                         r.images = encoder.decode(latents)
                     if sr_model is not None:
                         r.src, r.tgt, sr_geometry = data["sr_src_image"], data["sr_tgt_image"], data["sr_geometry"]
-                        sr_src = encoder.encode_latents(r.src.to(device, non_blocking=True))
+                        if dual:        # one row per seed, as above (the reference's [:num] slice of the 2B rows cannot run)
+                            r.src, r.tgt, sr_geometry = r.src[::2], r.tgt[::2], sr_geometry[::2]
+                        sr_dual = bool(getattr(sr_model, "dual", False))
+                        twice = (lambda t: t.repeat_interleave(2, dim=0)) if sr_dual else (lambda t: t)
+                        sr_src = encoder.encode_latents(twice(r.src).to(device, non_blocking=True))
                         rnd = StackedRandomGenerator(device, r.seeds)
-                        r.noise = rnd.randn([len(r.seeds), sr_model.img_channels, sr_model.img_resolution,
-                                             sr_model.img_resolution], device=device)
-                        r.labels = sr_geometry.to(device, non_blocking=True)
+                        r.noise = twice(rnd.randn([len(r.seeds), sr_model.img_channels, sr_model.img_resolution,
+                                                   sr_model.img_resolution], device=device))
+                        r.labels = twice(sr_geometry).to(device, non_blocking=True)
                         # inter-stage bilinear upscale (generate_images.py:322), vb_resize
                         low_res = resize_bilinear(latents, sr_src.shape[-1])
                         torch.manual_seed(int(r.seeds[0]) % (1 << 32))
@@ -171,10 +191,37 @@ def generate_images_nvs(
                             PIL.Image.fromarray(_src, "RGB").save(os.path.join(image_dir, f"src_{seed:06d}.png"))
                             PIL.Image.fromarray(_tgt, "RGB").save(os.path.join(image_dir, f"tgt_{seed:06d}.png"))
                             PIL.Image.fromarray(image, "RGB").save(os.path.join(image_dir, f"sample_{seed:06d}.png"))
-                _barrier()              # keep the ranks in step (per-batch metric all_reduce)
+                if gather_images:
+                    out_net = sr_model if sr_model is not None else net
+                    r.gathered_images, r.gathered_seeds = gather_batch(
+                        r.images, [[seeds[i] for i in all_batches[k][batch_idx]] for k in range(world)],
+                        (out_net.img_channels, out_net.img_resolution, out_net.img_resolution), device, rank,
+                        world if collective else 1)
+                if shard is None:
+                    _barrier()          # keep the ranks in step (per-batch metric all_reduce)
                 yield r
 
     return ImageIterable()
+
+
+def gather_batch(images, seeds_by_rank, chw, device, rank, world):
+    """Collect one batch's uint8 images of every rank on rank 0 (the only data-path collective besides
+    the metric all_reduces): one NCCL gather of [max_b,3,R,R] uint8 (ranks with a shorter or empty batch pad), sliced
+    back to the true per-rank sizes, which every rank knows from the seed split.  Returns (images, seeds) on rank 0 in
+    rank order, (None, None) elsewhere."""
+    sizes = [len(s) for s in seeds_by_rank]
+    flat_seeds = [s for part in seeds_by_rank for s in part]
+    if world == 1:
+        return images, flat_seeds
+    mx = max(max(sizes), 1)
+    send = torch.zeros((mx,) + tuple(chw), dtype=torch.uint8, device=device)
+    if images is not None and images.shape[0]:
+        send[:images.shape[0]].copy_(images)
+    recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+    torch.distributed.gather(send, recv, dst=0)
+    if rank != 0:
+        return None, None
+    return torch.cat([t[:n] for t, n in zip(recv, sizes)]), flat_seeds
 
 
 def get_metrics(image_iter, device=torch.device("cuda")):

@@ -82,6 +82,13 @@ class NVPrecond(torch.nn.Module):
         kw.pop("class_name", None)
         net = cls(**kw)
         sd = {k: v for k, v in ref.state_dict().items()}
+        # persisted EMA snapshots are stored in fp16 (params and buffers): keep every tensor's dtype and bits
+        own = dict(net.named_parameters())
+        own.update(dict(net.named_buffers()))
+        with torch.no_grad():
+            for k, v in sd.items():
+                if k in own and own[k].dtype != v.dtype:
+                    own[k].data = own[k].data.to(v.dtype)
         net.load_state_dict(sd, strict=True)
         dev = next(ref.parameters()).device
         return net.to(dev).eval()
@@ -158,7 +165,7 @@ class NVPrecond(torch.nn.Module):
             if geometry is None:
                 raise TypeError("dual-source mode requires geometry")   # reference: NoneType * int (models.py:631)
         B = n_in // 2 if self.dual else n_in
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.device(dst.device):
             p = self.plan(B, dst.device, fp32=fp32)
             p.in_x.copy_(dst)
             if inject_features is not None:

@@ -14,10 +14,15 @@ import torch
 from . import _lib as L
 
 
-def _heun(lib, d_net, d_gnet, x_hat, d_cur, x_next, phase, guidance, t_hat, t_next):
+def _heun(lib, d_net, d_gnet, x_hat, d_cur, x_next, phase, guidance, t_hat, t_next, x_out=(), sigma_out=(), sigma_next=0.0):
     desc = L.HeunDesc(d_net=d_net.data_ptr(), d_gnet=L.ptr(d_gnet), x_hat=x_hat.data_ptr(), d_cur=d_cur.data_ptr(),
                       x_next=x_next.data_ptr(), n=x_hat.numel(), phase=phase, guidance=float(guidance),
-                      t_hat=float(t_hat), t_next=float(t_next))
+                      t_hat=float(t_hat), t_next=float(t_next), sigma_next=float(sigma_next),
+                      sigma_n=sigma_out[0].numel() if sigma_out else 0)
+    for k, t in enumerate(x_out):
+        desc.x_out[k] = t.data_ptr()
+    for k, t in enumerate(sigma_out):
+        desc.sigma_out[k] = t.data_ptr()
     L.check(lib.vb_heun(C.byref(desc), torch.cuda.current_stream(x_hat.device).cuda_stream), "vb_heun")
 
 
@@ -40,11 +45,135 @@ def sigma_steps(num_steps, sigma_min, sigma_max, rho, device, dtype=torch.float3
 
 def edm_sampler(net, src, noise, labels=None, gnet=None, conditioning_image=None, num_steps=32, sigma_min=0.002,
                 sigma_max=80, rho=7, guidance=1, S_churn=0, S_min=0, S_max=float("inf"), S_noise=1,
-                dtype=torch.float32, randn_like=torch.randn_like):
+                dtype=torch.float32, randn_like=torch.randn_like, _trace=None):
+    """`_trace` (testing aid, not part of the reference's signature): a list that receives a copy of the guided
+    denoiser output D of every call, in call order."""
     if dtype != torch.float32:
         raise NotImplementedError("the sampler state is fp32 (the reference default); other dtypes are not implemented")
     if noise.device.type != "cuda":
         raise RuntimeError("vivid_b200.edm_sampler runs on CUDA only; there is no CPU fallback")
+    with torch.cuda.device(noise.device):        # kernels launch on the tensors' device whatever the caller's current one is
+        if _bound_ok(net, gnet, guidance, S_churn):
+            return _edm_sampler_bound(net, src, noise, labels, gnet, conditioning_image, num_steps, sigma_min, sigma_max,
+                                      rho, guidance, dtype, _trace)
+        return _edm_sampler_generic(net, src, noise, labels, gnet, conditioning_image, num_steps, sigma_min, sigma_max, rho,
+                                    guidance, S_churn, S_min, S_max, S_noise, dtype, randn_like, _trace)
+
+
+def _bound_ok(net, gnet, guidance, S_churn):
+    """The zero-copy loop applies to this package's own fp16-path nets with vanilla semantics; everything else (wrapped
+    callables, hooks, dual-source nets, fp32 validation mode, the stochastic branch) takes the generic loop."""
+    from .precond import NVPrecond
+    if os.environ.get("VB_BOUND_SAMPLER", "1") == "0" or S_churn > 0:
+        return False
+
+    def ok(n):
+        return (type(n) is NVPrecond and not n.dual and n.use_fp16 and not n._forward_hooks and not n._forward_pre_hooks)
+    if not ok(net):
+        return False
+    if getattr(net, "no_time_enc", None) and (net.encoder is None or net.super_res):
+        return False                                    # the generic loop raises the reference-shaped error
+    if guidance != 1:
+        if gnet is net or not ok(gnet) or gnet.super_res or gnet.img_resolution != net.img_resolution:
+            return False
+    return True
+
+
+class _Bound:
+    """One net bound to the inputs that stay constant over a sampler call (source view, pose vector, SR conditioning
+    image): they are uploaded into the plan's buffers ONCE, the plan is built and tuned on the caller's stream, and each
+    denoiser call is then a graph replay whose x / sigma inputs were written by the previous vb_heun pass."""
+
+    def __init__(self, net, src, labels, cond, n):
+        dev = src.device
+        self.net, self.p = net, net.plan(n, dev)
+        p = self.p
+        if p.in_src is not None:
+            if src.shape != p.in_src.shape:
+                raise ValueError(f"src must be {tuple(p.in_src.shape)}, got {tuple(src.shape)}")
+            p.in_src.copy_(src)
+        if labels is None:
+            p.in_geom.zero_()
+        else:
+            g = labels.to(torch.float32).reshape(-1, p.in_geom.shape[1])
+            p.in_geom.copy_(g.expand(n, -1) if g.shape[0] == 1 else g)
+        if net.super_res:
+            if cond is None:
+                raise AssertionError("super_res model requires conditioning_image")
+            p.in_cond.copy_(cond)
+        self.section = "all"
+
+    def cache_features(self, sigma0):
+        """no_time_enc nets (generate_images.py:52-57): the source-view encoder runs once per sampler call."""
+        self.p.in_sigma.fill_(sigma0)
+        self.p.run(graph=self.net.use_graph, section="enc")
+        self.section = "unet"
+
+    def launch(self):
+        if self.net.super_res:
+            # the reference draws this from the GLOBAL generator on every call (SURVEY.md F7); normal_() on the plan's
+            # buffer consumes the generator exactly as torch.randn_like(conditioning_image) does
+            self.p.in_noise.normal_()
+        self.p.run(graph=self.net.use_graph, section=self.section)
+        return self.p.out_d
+
+
+def _edm_sampler_bound(net, src, noise, labels, gnet, cond, num_steps, sigma_min, sigma_max, rho, guidance, dtype, trace):
+    lib = L.lib()
+    dev = noise.device
+    n = noise.shape[0]
+    t_dev = sigma_steps(num_steps, sigma_min, sigma_max, rho, dev, dtype)
+    t_steps = t_dev.tolist()                       # one host sync per sampler call
+    guided = guidance != 1
+    bn = _Bound(net, src, labels, cond, n)
+    bg = _Bound(gnet, src, None, None, n) if guided else None       # gnet(src, x, t): no pose, no conditioning image
+    if getattr(net, "no_time_enc", None):
+        bn.cache_features(t_steps[0])
+    bounds = [bn] + ([bg] if guided else [])
+    x_in = [b.p.in_x for b in bounds]
+    sig_in = [b.p.in_sigma for b in bounds]
+    x_hat = (noise.to(dtype) * t_dev[0]).contiguous()
+    x_next, d_cur = torch.empty_like(x_hat), torch.empty_like(x_hat)
+    for b in bounds:
+        b.p.in_x.copy_(x_hat)
+        b.p.in_sigma.fill_(t_steps[0])
+    side = _side_stream(dev) if guided and os.environ.get("VB_DUAL_STREAM", "1") != "0" else None
+    cur = torch.cuda.current_stream(dev)
+
+    def denoise():
+        if side is None:
+            dn = bn.launch()
+            return dn, (bg.launch() if guided else None)
+        side.wait_stream(cur)                      # both nets' inputs are in place (written by the previous vb_heun)
+        dn = bn.launch()
+        with torch.cuda.stream(side):
+            dg = bg.launch()
+        cur.wait_stream(side)
+        return dn, dg
+
+    def log(dn, dg):
+        if trace is not None:
+            trace.append(dn.clone() if dg is None else torch.lerp(dg, dn, guidance))
+
+    for i in range(num_steps):
+        t_hat, t_nxt = t_steps[i], t_steps[i + 1]
+        last = i == num_steps - 1
+        dn, dg = denoise()
+        log(dn, dg)
+        # Euler step; x_next and the next call's noise level go straight into the plans' input buffers
+        _heun(lib, dn, dg, x_hat, d_cur, x_next, 0, guidance, t_hat, t_nxt, x_out=() if last else x_in,
+              sigma_out=() if last else sig_in, sigma_next=t_nxt)
+        if not last:
+            dn, dg = denoise()
+            log(dn, dg)
+            _heun(lib, dn, dg, x_hat, d_cur, x_next, 1, guidance, t_hat, t_nxt, x_out=x_in, sigma_out=sig_in,
+                  sigma_next=t_nxt)                   # 2nd-order correction
+        x_hat, x_next = x_next, x_hat
+    return x_hat
+
+
+def _edm_sampler_generic(net, src, noise, labels, gnet, conditioning_image, num_steps, sigma_min, sigma_max, rho, guidance,
+                         S_churn, S_min, S_max, S_noise, dtype, randn_like, trace):
     lib = L.lib()
     dual = bool(getattr(net, "dual", False))
     t_dev = sigma_steps(num_steps, sigma_min, sigma_max, rho, noise.device, dtype)
@@ -61,6 +190,10 @@ def edm_sampler(net, src, noise, labels=None, gnet=None, conditioning_image=None
     side = None
     if guidance != 1 and gnet is not net and os.environ.get("VB_DUAL_STREAM", "1") != "0":
         side = _side_stream(noise.device)
+        for m in (net, gnet):                      # build and tune both plans on the caller's stream, not concurrently
+            if hasattr(m, "plan") and getattr(m, "use_fp16", False):
+                m.plan(noise.shape[0] // (2 if getattr(m, "dual", False) else 1), noise.device)
+        torch.cuda.current_stream(noise.device).synchronize()
 
     def denoise(x, t):
         tt = torch.full((x.shape[0],), t, dtype=dtype, device=x.device)
@@ -100,10 +233,14 @@ def edm_sampler(net, src, noise, labels=None, gnet=None, conditioning_image=None
         else:
             t_hat, x_hat = t_cur, x_cur
         dn, dg = denoise(widen(x_hat), t_hat)
+        if trace is not None:
+            trace.append(dn.clone() if dg is None else torch.lerp(dg, dn, guidance))
         x_next = torch.empty_like(x_hat)
         _heun(lib, dn, dg, x_hat, d_cur, x_next, 0, guidance, t_hat, t_nxt)          # Euler step
         if i < num_steps - 1:
             dn, dg = denoise(widen(x_next), t_nxt)
+            if trace is not None:
+                trace.append(dn.clone() if dg is None else torch.lerp(dg, dn, guidance))
             _heun(lib, dn, dg, x_hat, d_cur, x_next, 1, guidance, t_hat, t_nxt)      # 2nd-order correction
     return x_next
 
