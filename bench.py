@@ -206,7 +206,7 @@ def run_ours(args):
     insitu = None
     if not args.no_insitu:
         try:
-            insitu = insitu_profile(pipeline, resident(seeds_of(args.warmup + args.steps)), dev)
+            insitu = insitu_profile(pipeline, resident(seeds_of(args.warmup + args.steps)), dev, (net, gnet, sr))
         except Exception as e:      # the number is an attribution aid: never lose the bench line over it
             insitu = dict(error=f"{type(e).__name__}: {e}"[:200])
 
@@ -302,14 +302,21 @@ def run_ours(args):
         torch.distributed.destroy_process_group()
 
 
-def insitu_profile(pipeline, item, dev):
-    """Kernel durations of ONE pipeline step recorded in place (CUPTI activity records via torch.profiler; CUDA-side only,
-    no host instrumentation).  Returns per-family totals, the conv kernel's total, and the part of the step no kernel covers."""
+def insitu_profile(pipeline, item, dev, nets):
+    """Kernel durations of ONE pipeline step recorded in place (CUPTI activity records via torch.profiler; CUDA side only).
+    For the records to be per-kernel the step runs as an eager replay of the plans on one stream with programmatic dependent
+    launch off (under PDL a kernel is resident, and counted as running, while it still waits for its predecessor).
+    Returns per-family totals, the conv kernel's total, and the part of the step no kernel covers."""
+    import re
     from torch.profiler import ProfilerActivity, profile
+    from vivid_b200 import _lib as L
     prev = os.environ.get("VB_DUAL_STREAM")
     os.environ["VB_DUAL_STREAM"] = "0"
+    prev_pdl = L.lib().vb_set_pdl(0)
+    for n in nets:
+        n.use_graph = False
     try:
-        pipeline(item)                          # same code path once without records (single-stream variant warm)
+        pipeline(item)                          # same code path once without records (sustained clocks, caches warm)
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -318,10 +325,14 @@ def insitu_profile(pipeline, item, dev):
             e1.record()
             torch.cuda.synchronize(dev)
     finally:
+        for n in nets:
+            n.use_graph = True
+        L.lib().vb_set_pdl(prev_pdl)
         if prev is None:
             os.environ.pop("VB_DUAL_STREAM", None)
         else:
             os.environ["VB_DUAL_STREAM"] = prev
+    kname = re.compile(r"([A-Za-z0-9_]+_kernel)")
     fam, spans = {}, []
     for ev in prof.events():
         dur = getattr(ev, "device_time_total", None)
@@ -337,8 +348,9 @@ def insitu_profile(pipeline, item, dev):
             key = "conv_gemm_kernel"
         elif "attn" in low:
             key = "attention"
-        elif "vb::" in name or "vb_" in low:
-            key = name.split("(")[0].split("<")[0].split("::")[-1]
+        elif "vb::" in name:
+            m = kname.search(name)
+            key = m.group(1) if m else name[:48]
         else:
             key = "torch (RNG, copies, stack)"
         f = fam.setdefault(key, [0, 0.0])
@@ -361,7 +373,8 @@ def insitu_profile(pipeline, item, dev):
         busy += cur_e - cur_s
     conv = fam.get("conv_gemm_kernel", [0, 0.0])
     total = sum(v[1] for v in fam.values())
-    return dict(method="torch.profiler CUDA activity records over one extra step (single stream)", step_ms=round(step_ms, 2),
+    return dict(method="torch.profiler CUDA activity records over one extra step (eager replay, one stream, PDL off)",
+                step_ms=round(step_ms, 2),
                 kernels_ms=round(total, 2), busy_ms=round(busy / 1e3, 2), idle_ms=round(step_ms - busy / 1e3, 2),
                 idle_frac=round(1.0 - busy / 1e3 / step_ms, 4), conv_ms=round(conv[1], 2), conv_launches=conv[0],
                 families={k: dict(launches=v[0], ms=round(v[1], 2), share=round(v[1] / step_ms, 4))

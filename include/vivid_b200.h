@@ -48,6 +48,10 @@ int vb_device_check(void);
 /* Measurement plumbing: occupies `stream` for the given time (one spinning thread) so that work enqueued behind it
  * executes back to back, independent of the host's launch rate. */
 int vb_spin(int microseconds, void* stream);
+/* Programmatic dependent launch of the library's kernels (default on; VB_PDL=0 in the environment turns it off).  Returns
+ * the previous setting.  Affects launches and graph captures made AFTER the call (measurement aid: with it off, kernel
+ * activity records of consecutive kernels do not overlap). */
+int vb_set_pdl(int on);
 /* sizeof() of the descriptor structs below, in declaration order (0 = vb_weight_prep_desc ... 7 = vb_heun_desc, 8 = vb_stats_desc, 9 = vb_f32_conv_desc, 10 = vb_f32_op_desc);
  * lets a foreign-language binding verify its mirror of the layout.  -1 for an unknown index. */
 int vb_struct_size(int which);

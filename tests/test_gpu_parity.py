@@ -96,12 +96,17 @@ CONV_CASES = [
     (2, 64, 128, 128, 9, 128, 0, 3, 1, (1, 4)),         # residual scaled by the producer's per-pixel 1/rms side channel
     (3, 256, 64, 64, 9, 64, 0, 3, 1, (1, 4, 2)),        # ... at SR resolution (CTA pair, resident weights)
     (9, 8, 512, 512, 9, 128, 0, 1, 1, (1, 2)),          # 8x8 level: 2 images per tile, 4 N tiles, K = 72 blocks
+    (40, 16, 384, 384, 1, 192, 0, 1, 1, (1, 2)),        # 1x1 attn_proj shape: 2 N tiles, several tiles per CTA
+    (40, 16, 384, 1152, 1, 192, 0, 0, 0, (1,)),         # 1x1, 6 N tiles (resident weights: grid rounded to a multiple of 6)
+    (9, 8, 512, 512, 1, 128, 0, 1, 1, (1, 2)),          # 1x1 at the 8x8 level, 4 N tiles, fewer tiles than SMs
+    (3, 32, 128, 256, 1, 64, 1, 0, 0, (1,)),            # 1x1, K = 2 blocks, 4 N tiles
 ]
 
 
 # vb_conv_desc.tune: library default | single CTA | CTA pair | per-tap boxes | shared haloed boxes | row-rolling layout |
 # ping-pong epilogue | ping-pong + pair.  Layouts a layer cannot take (shared-memory budget, shape) are skipped.
-TUNES = [0, 1, 2, 4, 8, 16, 64, 66]
+# 128: 1x1 layers keep their N tile's weights resident (| single, pair, ping-pong).
+TUNES = [0, 1, 2, 4, 8, 16, 64, 66, 128, 129, 130, 192]
 
 
 @pytest.mark.parametrize("tune", TUNES)
@@ -110,6 +115,8 @@ def test_conv_gemm_vs_conv2d(env, B, R, cin, cout, taps, bn, modsilu, res_mode, 
     """vb_conv (+vb_weight_prep) vs MPConv semantics (models.py:115-126) with the fused epilogues, in every layout the
     plan-time tuner (or a maintainer) can ask for."""
     L, lib, dev = env
+    if tune & 128 and taps != 1:
+        pytest.skip("resident-weight layout is for 1x1 layers")
     dt = L.operand_torch_dtype()
     g = torch.Generator().manual_seed(B * 1000 + R + cin + cout)
     cin_pad, k = pad_to(cin, 64), 3 if taps == 9 else 1
@@ -155,7 +162,7 @@ def test_conv_gemm_vs_conv2d(env, B, R, cin, cout, taps, bn, modsilu, res_mode, 
     rc = lib.vb_conv(C.byref(d), stream())
     if rc != 0 and tune != 0:
         msg = lib.vb_last_error().decode()
-        assert any(k in msg for k in ("ping-pong", "row-rolling", "budget")), msg
+        assert any(k in msg for k in ("ping-pong", "row-rolling", "budget", "resident")), msg
         pytest.skip(f"layout not available for this layer: {msg}")
     L.check(rc, "vb_conv")
     torch.cuda.synchronize()
@@ -208,9 +215,11 @@ def test_conv_two_source_and_narrow_output(env):
     assert o32[..., 3:].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("tune", [0, 2, 128, 130])
 @pytest.mark.parametrize("B,R,ch,heads,D,parts,seg_div,bn", [(2, 16, 128, 2, 64, 3, 1, 128), (2, 8, 256, 4, 64, 2, 1, 128),
-                                                           (4, 8, 256, 4, 64, 2, 2, 64), (2, 32, 256, 8, 32, 3, 1, 64)])
-def test_qkv_epilogue(env, B, R, ch, heads, D, parts, seg_div, bn):
+                                                           (4, 8, 256, 4, 64, 2, 2, 64), (2, 32, 256, 8, 32, 3, 1, 64),
+                                                           (40, 16, 384, 6, 64, 3, 1, 192), (12, 8, 512, 8, 64, 2, 1, 128)])
+def test_qkv_epilogue(env, B, R, ch, heads, D, parts, seg_div, bn, tune):
     """1x1 GEMM + per-(token, head, q|k|v) normalise + scatter (models.py:192-193, 283-297)."""
     L, lib, dev = env
     dt = L.operand_torch_dtype()
@@ -227,8 +236,13 @@ def test_qkv_epilogue(env, B, R, ch, heads, D, parts, seg_div, bn):
     d = L.ConvDesc(x=x_nhwc.data_ptr(), w=wp.data_ptr(), part_out=(C.c_void_p * 3)(*[o.data_ptr() for o in outs] + [None] * (3 - parts)),
                    B=B, H=R, W=R, cin_pad=ch, cin2_pad=0, cout_pad=cout, taps=1, block_n=bn, epi_mode=L.VB_EPI_QKVNORM,
                    head_dim=D, parts=parts, seg_div=seg_div, part_seq=(C.c_int32 * 3)(*(seq + [0] * (3 - parts))),
-                   part_off=(C.c_int32 * 3)(*(off + [0] * (3 - parts))))
-    L.check(lib.vb_conv(C.byref(d), stream()), "vb_conv qkv")
+                   part_off=(C.c_int32 * 3)(*(off + [0] * (3 - parts))), tune=tune)
+    rc = lib.vb_conv(C.byref(d), stream())
+    if rc != 0 and tune != 0:
+        msg = lib.vb_last_error().decode()
+        assert any(k in msg for k in ("budget", "resident")), msg
+        pytest.skip(f"layout not available for this layer: {msg}")
+    L.check(rc, "vb_conv qkv")
     torch.cuda.synchronize()
     y = torch.nn.functional.conv2d(x_nhwc.float().permute(0, 3, 1, 2), ref_weight(w).to(dt).float())
     y = y.reshape(B, heads, D, parts, S)

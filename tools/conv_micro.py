@@ -4,6 +4,7 @@ Env: VB_B batch, VB_REPS repetitions, VB_ONLY comma list of shape indices, VB_EP
   simple  one raw output                         mod    conv_res0: modulation + mp_silu -> raw
   r1s     mp_sum(res) + clip -> raw, silu        r2ns   mp_sum(pixel_norm(res)) + clip -> raw, norm_silu
   r2nss   ... -> raw, norm_silu, silu            (library knobs: VB_TAP_MODE, VB_DBG, VB_GENERIC_EPI)
+  qkv     1x1 only: per-head normalise + scatter to [B,h,S,64] (cout = heads*3*64)          VB_TUNE: vb_conv_desc.tune
 """
 import ctypes as C
 import os
@@ -23,6 +24,7 @@ SHAPES = [  # R, cin, cout, taps, bn
     (16, 384, 384, 9, 128), (8, 512, 512, 9, 64), (8, 512, 512, 9, 128), (16, 384, 1152, 1, 192), (256, 128, 64, 1, 64),
     (256, 128, 64, 9, 64), (64, 192, 192, 9, 192), (16, 384, 384, 9, 192), (64, 128, 128, 1, 128),
     (8, 384, 512, 1, 64), (16, 384, 384, 1, 192), (8, 512, 512, 1, 64),
+    (8, 512, 1536, 1, 192), (32, 256, 768, 1, 256), (16, 384, 768, 1, 192), (32, 256, 256, 1, 256), (8, 512, 512, 1, 128),
 ]
 B = int(os.environ.get("VB_B", "32"))
 reps = int(os.environ.get("VB_REPS", "10"))
@@ -40,9 +42,18 @@ for idx, (R, cin, cout, taps, bn) in enumerate(SHAPES):
     fullrow = cout == bn and cout <= 256
     for epi in epis:
         d = L.ConvDesc(x=x.data_ptr(), w=w.data_ptr(), B=B, H=R, W=R, cin_pad=cin, cin2_pad=0, cout_pad=cout, taps=taps,
-                       block_n=bn, epi_mode=0, flags=0, res_mode=0, res_t=0.3, clip=256.0)
+                       block_n=bn, epi_mode=0, flags=0, res_mode=0, res_t=0.3, clip=256.0, tune=int(os.environ.get("VB_TUNE", "0")))
         kinds = [L.VB_OUT_RAW]
-        if epi == "mod":
+        if epi == "qkv":
+            if taps != 1 or cout % 192:
+                continue
+            heads = cout // 192
+            qkv = [torch.empty(B * heads * R * R, 64, dtype=dt, device=dev) for _ in range(3)]
+            d.epi_mode, d.head_dim, d.parts, d.seg_div = L.VB_EPI_QKVNORM, 64, 3, 1
+            for j in range(3):
+                d.part_out[j], d.part_seq[j], d.part_off[j] = qkv[j].data_ptr(), R * R, 0
+            kinds = []
+        elif epi == "mod":
             d.flags, d.mod, d.mod_stride = L.VB_F_MODSILU, mod.data_ptr(), cout
         elif epi != "simple":
             d.flags, d.res = L.VB_F_CLIP, res.data_ptr()
@@ -57,7 +68,10 @@ for idx, (R, cin, cout, taps, bn) in enumerate(SHAPES):
             d.out[i], d.out_kind[i], d.out_scale[i] = outs[i].data_ptr(), k, 1.0
         plan = C.c_void_p()
         L.check(lib.vb_plan_create(C.byref(plan)), "create")
-        L.check(lib.vb_plan_add_conv(plan, C.byref(d)), "add")
+        if lib.vb_plan_add_conv(plan, C.byref(d)) != 0:
+            print(f"[{idx}] {R}x{R} cin{cin} cout{cout} taps{taps} bn{bn} B{B} {epi:6s}: n/a ({lib.vb_last_error().decode()})", flush=True)
+            lib.vb_plan_destroy(plan)
+            continue
         for _ in range(3):
             L.check(lib.vb_plan_run(plan, 0, -1, stream), "run")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

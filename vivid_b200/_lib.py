@@ -124,6 +124,7 @@ SIGNATURES = {
     "vb_plan_add_precond_out": (C.c_int, [vp, C.POINTER(PrecondOutDesc)]),
     "vb_plan_add_heun": (C.c_int, [vp, C.POINTER(HeunDesc)]),
     "vb_spin": (C.c_int, [C.c_int, vp]),
+    "vb_set_pdl": (C.c_int, [C.c_int]),
     "vb_debug_conv_cycles": (C.c_int, [C.POINTER(C.c_ulonglong)]),
     "vb_debug_conv_stamps": (C.c_int, [C.POINTER(C.c_longlong)]),
     "vb_plan_num_ops": (C.c_int, [vp]),

@@ -77,6 +77,7 @@ struct ConvKernelParams {
   uint32_t idesc128, idesc64;
   int eg;               // ping-pong epilogue (kernel variants with PARTS == 1)
   int tune_tap;         // plan-time tuning: 0 auto, 1 no shared haloed boxes, 2 haloed boxes wherever they fit
+  int want_res1;        // plan-time tuning (tune bit 7): 1x1 layers keep their N tile's weights resident (see plan_mainloop)
   int pair, total_q;    // CTA-pair mode (cluster of 2, cta_group::2 MMA); work items per CTA / per pair
   int taps, kc_a, kc_b;
   int block_n;
@@ -402,7 +403,8 @@ __device__ __forceinline__ void producer_act(const ConvKernelParams& p, const Ro
       }
     }
   } else {
-    const uint32_t tx = static_cast<uint32_t>(kAStageBytes + p.b_bytes) * mul;
+    // (resident 1x1 weights: the stage carries the activation box only)
+    const uint32_t tx = static_cast<uint32_t>(kAStageBytes + (p.b_resident ? 0 : p.b_bytes)) * mul;
     const uint32_t nslots = p.num_stages, slot_bytes = p.stage_bytes;
     uint32_t dst = c.smem;
     for (int q = c.q0; q < p.total_q; q += c.qstride) {
@@ -485,6 +487,14 @@ __device__ __forceinline__ void producer_wgt(const ConvKernelParams& p, const Ro
         }
       }
     }
+  } else if (p.b_resident) {
+    // 1x1 layer, resident weights: the grid is a multiple of the number of N tiles, so every work item of this CTA has
+    // the SAME N tile; its K x block_n weight slab is loaded once and the ring carries activations only
+    if (c.q0 >= p.total_q) return;
+    const int col = decode_tile(p, tile_of(p, c.q0, c.rank)).col0 + wrow;
+    if (lead) mbar_expect_tx_addr(c.bfull, static_cast<uint32_t>(kct) * b_bytes * mul);
+    uint32_t dst = c.smem + p.b_off;
+    for (int i = 0; i < kct; ++i, dst += b_bytes) tma_wgt<PAIR>(map_w, c.bfull_dst, dst, i * kBlockK, col);
   } else {
     const uint32_t nslots = p.num_stages, slot_bytes = p.stage_bytes, base = c.smem + kAStageBytes;
     const int k_blocks = p.taps * kct;
@@ -652,17 +662,24 @@ __device__ __forceinline__ void mma_role(const ConvKernelParams& p, const RoleCt
     const uint32_t nstages = p.num_stages;
     uint32_t stage = 0, phase = 0, a_lo = s_base;
     const int k_blocks = p.taps * kct;
+    const bool resident = p.b_resident != 0;
+    const uint32_t b_res = umma_desc_lo(c.smem + p.b_off);
+    if (resident && c.q0 < p.total_q) {
+      mbar_wait_addr(c.bfull, 0);
+      tc_fence_after();
+    }
     for (int q = c.q0; q < p.total_q; q += c.qstride, ++it) {
       const uint32_t buf = it & 1;
       mbar_wait_addr(c.tmem_empty + buf * 8, (static_cast<uint32_t>(it >> 1) & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = c.tmem_base + buf * kAccStride;
       uint32_t accumulate = 0;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      uint32_t b_next = b_res;
+      for (int kb = 0; kb < k_blocks; ++kb, b_next += b_tile_lo) {
         mbar_wait_addr(c.full + stage * 8, phase);
         if (it == 0 && kb == 0) VB_TS(2);
         tc_fence_after();
-        const uint32_t b_lo = a_lo + (kAStageBytes >> 4);
+        const uint32_t b_lo = resident ? b_next : a_lo + (kAStageBytes >> 4);
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
           mma(d_tmem, a_lo + 2 * k, b_lo + 2 * k, accumulate);
@@ -1280,7 +1297,21 @@ static bool plan_mainloop(ConvKernelParams& p, int budget, bool want_good) {
   static const int env_forced = getenv("VB_TAP_MODE") ? atoi(getenv("VB_TAP_MODE")) : -1;    // -1 auto, 0 off (A/B testing)
   const int forced = p.tune_tap == 1 ? 0 : (p.tune_tap == 2 ? 2 : env_forced);
   p.tap_mode = 0;
+  p.b_resident = 0;
   const int kct = p.kc_a + p.kc_b;
+  if (p.taps == 1 && p.want_res1) {
+    // 1x1 layer with its N tile's weights resident: K x block_n slab + a ring of activation boxes.  The L2 -> shared-memory
+    // fill per tile drops from (128 + block_n) x K x 2 bytes to 128 x K x 2 (the fill rate, ~69 B/clk/SM, is what bounds
+    // these layers: profiles/r01_tma_rate.txt).  Explicit request only: does not fit -> not a legal layout.
+    const int resident = kct * p.b_bytes;
+    const int stages = std::min(kMaxStages, (budget - resident) / kAStageBytes);
+    if (stages < 3) return false;
+    p.b_resident = 1;
+    p.num_stages = stages;
+    p.stage_bytes = kAStageBytes;
+    p.b_off = stages * kAStageBytes;
+    return true;
+  }
   if (p.taps == 9 && p.bn == 1 && forced != 0) {
     const int mode = p.bh == 1 ? 1 : 2;
     const int rows = mode == 1 ? p.bw + 2 : (p.bh + 2) * p.bw;
@@ -1325,7 +1356,7 @@ static bool plan_mainloop(ConvKernelParams& p, int budget, bool want_good) {
 // Quality of a main-loop layout (higher is better): resident weights >> shared haloed boxes >> per-tap stages, then depth.
 static int mainloop_score(const ConvKernelParams& p) {
   if (p.tap_mode != 0) return (p.b_resident ? 2000 : 1000) + 10 * std::min(p.a_slots, 5) + std::min(p.b_slots, 12);
-  return 10 * std::min(p.num_stages, 6);
+  return (p.b_resident ? 500 : 0) + 10 * std::min(p.num_stages, 6);
 }
 
 int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
@@ -1372,6 +1403,8 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
                             d->H % 16 == 0 && d->epi_mode == VB_EPI_PLAIN);
   const int forced_pair = want_rowroll ? 0 : ((d->tune & 3) == 1 ? 0 : ((d->tune & 3) == 2 ? 1 : env_pair));
   p.tune_tap = want_rowroll ? 0 : (d->tune >> 2) & 3;
+  static const int env_res1 = getenv("VB_RES1") ? atoi(getenv("VB_RES1")) : 0;                   // A/B testing
+  p.want_res1 = (d->taps == 1 && (((d->tune >> 7) & 1) || env_res1)) ? 1 : 0;
   const int m_tiles = p.tiles_x * p.tiles_y * tiles_nb;
   // each CTA's half of the weight tile must be whole 8-row swizzle groups, and there must be two M tiles to pair up
   const bool pair_possible = d->block_n % 32 == 0 && m_tiles >= 2;
@@ -1557,7 +1590,7 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
     p.idesc64 = umma_idesc_op(kBlockM, 64);
   }
   const int main_bytes = p.tap_mode != 0 ? p.b_off + (p.b_resident ? 9 * (p.kc_a + p.kc_b) : p.b_slots) * p.b_bytes
-                                         : p.num_stages * p.stage_bytes;
+                         : (p.b_resident ? p.b_off + (p.kc_a + p.kc_b) * p.b_bytes : p.num_stages * p.stage_bytes);
   p.res_off = main_bytes;
   const int eg_mul2 = p.eg ? 2 : 1;
   p.stg_off = p.res_off + eg_mul2 * (p.res_mode != VB_RES_NONE ? p.res_slots * kChunkBytes : 0);
@@ -1607,6 +1640,16 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
   // independently (pair == 0): the grid is kept even, a surplus CTA finds no work item and exits.
   l->grid = p.pair ? std::min(2 * p.total_q, num_sms() & ~1)
                    : std::min(((p.rowroll ? p.total_q : p.total_tiles) + 1) & ~1, num_sms() & ~1);
+  if (p.tap_mode == 0 && p.b_resident) {
+    // resident 1x1 weights: every CTA must keep ONE N tile -> the work-item stride (CTAs, or pairs) is a multiple of n_tiles
+    const int unit = p.n_tiles * (p.pair ? 2 : 1);
+    const int step = unit % 2 == 0 ? unit : 2 * unit;
+    l->grid = l->grid / step * step;
+    if (l->grid == 0) {
+      set_error("vb_conv: resident 1x1 weights need at least %d work items", step);
+      return fail(VB_ERR_INVALID);
+    }
+  }
   l->smem_bytes = p.stg_off + eg_mul2 * (staged ? p.stg_regions * p.gslots * kChunkBytes : 0) + 1024;
   l->flops = 2.0 * d->B * d->H * d->W * static_cast<double>(d->cout_pad) * d->taps * (d->cin_pad + d->cin2_pad);
   const unsigned long long dev_bit = 1ull << current_device();

@@ -16,13 +16,14 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static int g_pdl = -1;      // -1: not decided yet (VB_PDL environment variable), 0 off, 1 on
+
 bool pdl_enabled() {
-  static int cached = -1;
-  if (cached < 0) {
+  if (g_pdl < 0) {
     const char* e = getenv("VB_PDL");
-    cached = (e != nullptr && e[0] == '0') ? 0 : 1;
+    g_pdl = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
-  return cached != 0;
+  return g_pdl != 0;
 }
 
 int current_device() {
@@ -124,6 +125,12 @@ extern "C" int vb_operand_dtype(void) { return VB_BF16; }
 #else
 extern "C" int vb_operand_dtype(void) { return VB_F16; }
 #endif
+extern "C" int vb_set_pdl(int on) {
+  const int prev = vb::pdl_enabled() ? 1 : 0;
+  vb::g_pdl = on ? 1 : 0;
+  return prev;
+}
+
 extern "C" int vb_device_check(void) {
   int dev = 0;
   cudaDeviceProp prop;

@@ -234,6 +234,10 @@ class Plan:
                 cands = [(n, t) for n in ns for t in (0, 1, 2)]
                 # ping-pong epilogue (tune bit 6, block_n <= 128): same arithmetic per element, other schedule
                 cands += [(n, t | 64) for n in ns if n <= 128 and outs for t in (0, 1, 2)]
+                if taps == 1:
+                    # 1x1 layers: the N tile's weights resident per CTA (tune bit 7) — the K order is unchanged as well
+                    cands += [(n, t | 128) for n in ns for t in (0, 1, 2)]
+                    cands += [(n, t | 64 | 128) for n in ns if n <= 128 and outs for t in (0, 1, 2)]
                 _TUNE_CACHE[key] = self._tune_conv(d, cands)
                 if os.environ.get("VB_TUNE_LOG"):
                     print("tune", key[:8], "heuristic bn", ns[0], "->", _TUNE_CACHE[key], flush=True)
