@@ -118,7 +118,7 @@ typedef struct vb_conv_desc {
   float* out_f32;   /* optional fp32 [B*H*W][ld_f32] copy of v, direct stores (the 3-channel out_conv) */
   float* out_rnorm; /* optional fp32 [B*H*W]: 1/(1e-4 + rms_c(v)) per pixel, written when a NORM kind is emitted */
   const float* res_rnorm; /* VB_RES_SCALED: fp32 [B*H*W] per-pixel scale of the residual */
-  void* part_out[3]; /* QKVNORM: q,k,v (or k,v) 16-bit [B/seg_div][heads][part_seq[j]][head_dim] */
+  void* part_out[3]; /* QKVNORM: q,k,v (or k,v) 16-bit [B/seg_div][heads][part_seq[j]][part_ld or head_dim] */
   int32_t B, H, W;
   int32_t cin_pad, cin2_pad;
   int32_t cout_pad; /* multiple of block_n */
@@ -131,12 +131,16 @@ typedef struct vb_conv_desc {
   int32_t head_dim, parts, seg_div;
   int32_t part_seq[3]; /* total sequence length of each destination */
   int32_t part_off[3]; /* first sequence slot written by image segment 0 */
-  float out_scale[3];  /* VB_OUT_SILU: mp_silu(v * scale) (mp_cat weight folded in) */
+  float out_scale[3];  /* VB_OUT_SILU: mp_silu(v * scale) (mp_cat weight folded in).  VB_EPI_QKVNORM: out_scale[j] != 0 multiplies
+                          the normalised rows of part j (the plans fold the softmax's log2(e)/sqrt(D) into q this way) */
   float res_t, clip;
   int32_t tune;        /* plan-time autotuning; 0 = the library decides.  bits 0-1: 1 single CTA, 2 CTA pair;
                         * bits 2-3: 1 per-tap operand boxes, 2 shared haloed boxes wherever they fit;
                         * bits 4-5: 1 row-rolling input-stationary layout (3x3, 64 -> 64 channels, rows >= 128 px);
-                        * bit 6: ping-pong epilogue (two groups of four warps on alternate tiles; block_n == 64) */
+                        * bit 6: ping-pong epilogue (two groups of four warps on alternate tiles; block_n == 64);
+                        * bit 7: 1x1 layers keep their N tile's weights resident in shared memory */
+  int32_t part_ld;     /* QKVNORM: elements per destination row; 0 = head_dim.  64 with head_dim 32: the rows are written into
+                        * zero-initialised 64-element rows (the upper half is never touched), see vb_attn_desc.ld */
 } vb_conv_desc;
 int vb_conv(const vb_conv_desc* d, void* stream);
 /* Diagnostics (micro-benchmarks only): with the environment variable VB_DBG & 16 set when an op is prepared, the conv
@@ -162,6 +166,10 @@ typedef struct vb_attn_desc {
   void* y;       /* 16-bit [B][sq][heads*D] (NHWC) */
   int32_t B, heads, sq, sk, head_dim;
   int32_t zero_keys;
+  int32_t ld;          /* elements per q/k/v row; 0 = head_dim.  64 with head_dim 32: rows zero-padded to 64 elements (what the
+                          plans emit for D = 32 so that the tcgen05 kernel serves it; y stays dense [.., heads*32]) */
+  int32_t q_prescaled; /* != 0: q already carries log2(e)/sqrt(D) (the QKV GEMM epilogue folded it in: vb_conv_desc.out_scale[0]
+                          in VB_EPI_QKVNORM mode), the kernel computes p = 2^(q.k) without a per-logit multiply */
 } vb_attn_desc;
 int vb_attn(const vb_attn_desc* d, void* stream);
 

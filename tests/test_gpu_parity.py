@@ -257,7 +257,8 @@ def test_qkv_epilogue(env, B, R, ch, heads, D, parts, seg_div, bn, tune):
 @pytest.mark.parametrize("B,h,sq,sk,D,zk", [(2, 4, 1024, 2048, 64, 0), (3, 8, 64, 128, 64, 0), (2, 8, 64, 64, 64, 64),
                                            (2, 2, 16, 48, 64, 0), (1, 8, 1024, 2048, 32, 0), (2, 6, 256, 768, 64, 0),
                                            (1, 4, 16, 16, 32, 16), (2, 4, 256, 256, 64, 512), (40, 6, 256, 512, 64, 0),
-                                           (1, 1, 128, 128, 64, 0)])
+                                           (1, 1, 128, 128, 64, 0), (3, 3, 64, 192, 64, 0), (1, 1, 64, 64, 64, 0),
+                                           (37, 8, 64, 128, 64, 64)])
 def test_fused_attention(env, B, h, sq, sk, D, zk):
     """vb_attn vs softmax(q k^T / sqrt(D)) v on normalised q,k,v, incl. analytic zero keys and ragged lengths."""
     L, lib, dev = env
@@ -279,6 +280,41 @@ def test_fused_attention(env, B, h, sq, sk, D, zk):
     w = (q.float() @ kz.transpose(-1, -2) / math.sqrt(D)).softmax(-1)
     ref = (w @ vz).permute(0, 2, 1, 3).reshape(B, sq, h * D)
     assert rel(y.float(), ref) < (2e-3 if dt == torch.float16 else 6e-3)
+    # the form the plans use: log2(e)/sqrt(D) folded into q by the QKV GEMM epilogue (vb_conv_desc.out_scale[0])
+    qs = (q.float() * (math.log2(math.e) / math.sqrt(D))).to(dt)
+    y2 = torch.zeros_like(y)
+    d.q, d.y, d.q_prescaled = qs.data_ptr(), y2.data_ptr(), 1
+    L.check(lib.vb_attn(C.byref(d), stream()), "vb_attn prescaled")
+    torch.cuda.synchronize()
+    assert rel(y2.float(), ref) < (2e-3 if dt == torch.float16 else 6e-3)
+
+
+def test_fused_attention_zero_padded_head_dim_32(env):
+    """head_dim 32 in 64-element rows (vb_attn_desc.ld = 64: what the plans emit for the SR UNet so that the tcgen05 kernel
+    serves it): same result as the dense D = 32 call; y stays dense."""
+    L, lib, dev = env
+    dt = L.operand_torch_dtype()
+    g = torch.Generator().manual_seed(5)
+    B, h, sq, sk, D = 2, 8, 1024, 2048, 32
+
+    def nrm(t):
+        return (t / (1e-4 + t.norm(dim=-1, keepdim=True) / math.sqrt(D))).to(dt)
+    q, k, v = (nrm(torch.randn(B, h, n, D, generator=g)).to(dev) for n in (sq, sk, sk))
+    pad = [torch.zeros(B, h, t.shape[2], 64, dtype=dt, device=dev) for t in (q, k, v)]
+    for dst, src in zip(pad, (q, k, v)):
+        dst[..., :D] = src
+    y = torch.zeros(B, sq, h * D, dtype=dt, device=dev)
+    d = L.AttnDesc(q=pad[0].data_ptr(), k=pad[1].data_ptr(), v=pad[2].data_ptr(), y=y.data_ptr(), B=B, heads=h, sq=sq, sk=sk,
+                   head_dim=D, zero_keys=7, ld=64)
+    L.check(lib.vb_attn(C.byref(d), stream()), "vb_attn padded")
+    torch.cuda.synchronize()
+    kz = torch.cat([k.float(), torch.zeros(B, h, 7, D, device=dev)], 2)
+    vz = torch.cat([v.float(), torch.zeros(B, h, 7, D, device=dev)], 2)
+    w = (q.float() @ kz.transpose(-1, -2) / math.sqrt(D)).softmax(-1)
+    ref = (w @ vz).permute(0, 2, 1, 3).reshape(B, sq, h * D)
+    assert rel(y.float(), ref) < (2e-3 if dt == torch.float16 else 6e-3)
+    d.sq = 48                                   # a shape the tcgen05 kernel does not take: padded rows are refused, not misread
+    assert lib.vb_attn(C.byref(d), stream()) != 0 and b"zero-padded" in lib.vb_last_error()
 
 
 def test_elementwise_passes(env):

@@ -178,6 +178,17 @@ def test_compose_geometry_and_schedule_match_reference(golden):
     assert torch.allclose(synthetic.compose_geometry(g["ext"], g["k_src"], g["k_tgt"], 64), g["compose_geometry_64"], atol=1e-6)
     assert torch.allclose(synthetic.compose_geometry(g["ext"], g["k_src"] * 4, g["k_tgt"] * 4, 256),
                           g["compose_geometry_256"], atol=1e-6)
+    # the snapshot tree's call form: 3x3 K matrices (experiments/code/training/utils.py:65-75), against ITS golden
+    v = golden["vanilla"]["ops"]
+    K = synthetic.decompose_K
+    assert torch.allclose(synthetic.compose_geometry(v["ext"], K(v["k_src"]), K(v["k_tgt"]), 64), v["compose_geometry_64"], atol=1e-6)
+    assert torch.allclose(synthetic.compose_geometry(v["ext"], K(v["k_src"] * 4), K(v["k_tgt"] * 4), 256),
+                          v["compose_geometry_256"], atol=1e-6)
+    assert torch.equal(synthetic.compose_K(K(v["k_src"])), v["k_src"])
+    ext, ks, kt = synthetic.decompose_geometry(v["compose_geometry_64"], 64)
+    assert torch.allclose(ext, v["ext"], atol=1e-4) and torch.allclose(synthetic.compose_K(ks)[..., :2], v["k_src"][..., :2], atol=1e-3)
+    assert torch.allclose(synthetic.resize_geometry(v["compose_geometry_64"], 64, 256)[..., :14],
+                          v["compose_geometry_256"][..., :14], atol=1e-4)
     t = sigma_steps(32, 0.002, 80, 7, "cpu")
     assert torch.equal(t[:-1], golden["vanilla"]["nets"]["t_steps_32"]) and t[-1] == 0
     from vivid_b200 import StackedRandomGenerator

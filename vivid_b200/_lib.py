@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvividb200.so")
+# (VB_LIB_PATH: A/B measurements against another build of the same ABI — tools only; the product loads the in-tree library)
+LIB_PATH = os.environ.get("VB_LIB_PATH") or os.path.join(_HERE, "libvividb200.so")
 
 VB_F32, VB_F16, VB_BF16, VB_F64, VB_U8 = 0, 1, 2, 3, 4
 VB_EPI_PLAIN, VB_EPI_QKVNORM = 0, 1
@@ -32,12 +33,12 @@ class ConvDesc(C.Structure):
                 ("cout_pad", i32), ("taps", i32), ("block_n", i32), ("epi_mode", i32), ("flags", i32),
                 ("mod_stride", i32), ("ld_f32", i32), ("res_mode", i32), ("out_kind", i32 * 3), ("head_dim", i32),
                 ("parts", i32), ("seg_div", i32), ("part_seq", i32 * 3), ("part_off", i32 * 3),
-                ("out_scale", f32 * 3), ("res_t", f32), ("clip", f32), ("tune", i32)]
+                ("out_scale", f32 * 3), ("res_t", f32), ("clip", f32), ("tune", i32), ("part_ld", i32)]
 
 
 class AttnDesc(C.Structure):
     _fields_ = [("q", vp), ("k", vp), ("v", vp), ("y", vp), ("B", i32), ("heads", i32), ("sq", i32), ("sk", i32),
-                ("head_dim", i32), ("zero_keys", i32)]
+                ("head_dim", i32), ("zero_keys", i32), ("ld", i32), ("q_prescaled", i32)]
 
 
 class EwDesc(C.Structure):

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const op_t* __restri
                                                             const op_t* __restrict__ k,
                                                             const op_t* __restrict__ v,
                                                             op_t* __restrict__ y, int heads, int sq, int sk,
-                                                            int zero_keys) {
+                                                            int zero_keys, int q_prescaled) {
   constexpr int kKSteps = D / 16;    // k-steps of the QK^T product
   constexpr int kDTiles = D / 8;     // n-tiles of the PV product
   __shared__ __align__(128) op_t s_q[kBlockQ * D];
@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(const op_t* __restri
         const int c = 2 * ks + (lane >> 4);
         ldmatrix_x4(smem_u32(s_q + swz<D>(r, c) * 8), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) qf[ks][i] = scale_pk(qf[ks][i], c1);
+        for (int i = 0; i < 4; ++i)
+          if (!q_prescaled) qf[ks][i] = scale_pk(qf[ks][i], c1);       // (else: folded into q by the QKV GEMM epilogue)
       }
     }
     // S = Q K^T : 16 x 64 per warp
@@ -254,16 +255,18 @@ int attn_launch(const vb_attn_desc* d, cudaStream_t s) {
   VB_REQUIRE(d->B > 0 && d->heads > 0 && d->sq > 0 && d->sk > 0, "vb_attn: empty problem");
   VB_REQUIRE(d->head_dim == 64 || d->head_dim == 32, "vb_attn: head_dim must be 32 or 64 (got %d)", d->head_dim);
   VB_REQUIRE(d->zero_keys >= 0, "vb_attn: zero_keys < 0");
+  VB_REQUIRE(d->ld == 0 || d->ld == d->head_dim || (d->ld == 64 && d->head_dim == 32), "vb_attn: ld must be 0, head_dim, or 64 with head_dim 32");
   if (attn_tc_supported(d)) return attn_tc_launch(d, s);       // tcgen05 path (attention_tc.cu)
+  VB_REQUIRE(d->ld == 0 || d->ld == d->head_dim, "vb_attn: zero-padded rows (ld 64, head_dim 32) need sq %% 256 == 0 and sk %% 128 == 0");
   const dim3 grid((d->sq + kBlockQ - 1) / kBlockQ, d->heads, d->B);
   const op_t* q = static_cast<const op_t*>(d->q);
   const op_t* k = static_cast<const op_t*>(d->k);
   const op_t* v = static_cast<const op_t*>(d->v);
   op_t* y = static_cast<op_t*>(d->y);
   if (d->head_dim == 64)
-    VB_CHECK_CUDA(launch_pdl(attn_kernel<64>, grid, dim3(kAttnThreads), 0, s, q, k, v, y, d->heads, d->sq, d->sk, d->zero_keys));
+    VB_CHECK_CUDA(launch_pdl(attn_kernel<64>, grid, dim3(kAttnThreads), 0, s, q, k, v, y, d->heads, d->sq, d->sk, d->zero_keys, d->q_prescaled));
   else
-    VB_CHECK_CUDA(launch_pdl(attn_kernel<32>, grid, dim3(kAttnThreads), 0, s, q, k, v, y, d->heads, d->sq, d->sk, d->zero_keys));
+    VB_CHECK_CUDA(launch_pdl(attn_kernel<32>, grid, dim3(kAttnThreads), 0, s, q, k, v, y, d->heads, d->sq, d->sk, d->zero_keys, d->q_prescaled));
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }

@@ -42,6 +42,12 @@ constexpr int kColS = 0, kSBufs = 3, kColO = kSBufs * kTK, kAtCols = 512;     //
 struct AttnTcParams {
   int n_items, q_pairs, n_kv;        // items = B*heads*q_pairs; key blocks per item
   int heads, sq, sk;
+  // tiles = 2: an item is two 128-row query tiles of one (batch, head) sharing every K/V block (sq % 256 == 0).
+  // tiles = 1, small = 1 (sq == 64, the 8x8 level): an item is ONE 128-row tile holding the queries of TWO consecutive
+  // (batch, head) pairs; its keys are the 2 sk rows of both (contiguous in [B][heads][sk][D]) and a 64-key sub-block only
+  // counts for the rows of the pair it belongs to (block-diagonal logits: the other half of P is written as zeros).
+  int tiles, small, n_bh;
+  int out_d;                         // real head dim written out (32: q/k/v rows are zero-padded to 64 elements)
   float c1;                          // log2(e)/sqrt(D) still to be applied to the logits (1 if folded into q)
   float zero_keys;
   op_t* y;
@@ -103,6 +109,29 @@ __device__ __forceinline__ uint32_t ex2_pk2(uint32_t x) {
 #endif
   return r;
 }
+// 2^x of a packed fp16 pair on the FMA/ALU pipes (no MUFU): x = r + f with r = rint(x) (magic-number rounding: x + 1536 has
+// an ulp of 1 in fp16, its low mantissa bits are r + 512), f in [-0.5, 0.5]; 2^f by a cubic (least-squares fit weighted for
+// relative error; evaluated in fp16 its error is that of rounding the exact value: max 6.5e-4, mean 1.8e-4 relative over
+// |x| <= 11.6 — the softmax's range, |q.k| log2(e)/sqrt(D) <= 8 log2(e)); 2^r is added into the exponent field with lane-wise
+// integer arithmetic arranged so that no carry crosses the 16-bit lanes.  ex2.approx.f16x2 costs TWO MUFU issues on sm_100a
+// and the softmax is MUFU-bound (profiles/r01_attn_tc.txt): every POLY-th pair takes this path instead.
+__device__ __forceinline__ uint32_t ex2_poly_pk2(uint32_t x2) {
+#ifdef VB_OP_BF16
+  return ex2_pk2(x2);
+#else
+  const __half2 x = *reinterpret_cast<__half2*>(&x2);
+  const __half2 magic = __float2half2_rn(1536.f);
+  const __half2 y = __hadd2(x, magic);
+  const __half2 r = __hsub2(y, magic);
+  const __half2 f = __hsub2(x, r);
+  __half2 pl = __hfma2(f, __float2half2_rn(0.05460186f), __float2half2_rn(0.24192564f));
+  pl = __hfma2(pl, f, __float2half2_rn(0.69331678f));
+  pl = __hfma2(pl, f, __float2half2_rn(1.0f));
+  const uint32_t yb = *reinterpret_cast<const uint32_t*>(&y);
+  const uint32_t t = ((yb & 0x03FF03FFu) - 0x01F001F0u) << 10;       // (r + 16) << 10 per lane, r in [-12, 12]
+  return *reinterpret_cast<uint32_t*>(&pl) + t - 0x40004000u;
+#endif
+}
 __device__ __forceinline__ uint32_t add_pk2(uint32_t a, uint32_t b) {
 #ifdef VB_OP_BF16
   __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
@@ -112,10 +141,11 @@ __device__ __forceinline__ uint32_t add_pk2(uint32_t a, uint32_t b) {
   return *reinterpret_cast<uint32_t*>(&r);
 }
 
-template <bool SCALE>
+template <bool SCALE, int POLY, bool SMALL>
 __global__ void __launch_bounds__(kAtThreads, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ AttnTcParams p) {
+  constexpr int kTiles = SMALL ? 1 : 2;      // query tiles per item (see AttnTcParams)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t b_q_full, b_q_empty;
   __shared__ __align__(8) uint64_t b_k_full[kKvStages], b_k_empty[kKvStages], b_v_full[kKvStages], b_v_empty[kKvStages];
@@ -179,10 +209,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++it) {
         const int bh = w / p.q_pairs, qp = w - bh * p.q_pairs;
         bar_wait(q_empty, (it & 1u) ^ 1u);
-        bar_expect(q_full, 2 * kTile);
-        tma_2d(&map_q, q_full, sm + kOffQ, 0, bh * p.sq + qp * 2 * kTQ);
-        tma_2d(&map_q, q_full, sm + kOffQ + kTile, 0, bh * p.sq + qp * 2 * kTQ + kTQ);
-        const int krow = bh * p.sk;
+        bar_expect(q_full, kTiles * kTile);
+        const int qrow = SMALL ? w * kTQ : bh * p.sq + qp * 2 * kTQ;
+        tma_2d(&map_q, q_full, sm + kOffQ, 0, qrow);
+        if (kTiles == 2) tma_2d(&map_q, q_full, sm + kOffQ + kTile, 0, qrow + kTQ);
+        const int krow = SMALL ? w * 2 * p.sk : bh * p.sk;
         for (int j = 0; j < p.n_kv; ++j) {
           bar_wait(k_empty + stage * 8, phase ^ 1u);
           bar_expect(k_full + stage * 8, kTile);
@@ -199,7 +230,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (elect_one_sync()) {
       uint32_t stage = 0, phase = 0;
       for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
-        const int krow = (w / p.q_pairs) * p.sk;
+        const int krow = SMALL ? w * 2 * p.sk : (w / p.q_pairs) * p.sk;
         for (int j = 0; j < p.n_kv; ++j) {
           bar_wait(v_empty + stage * 8, phase ^ 1u);
           bar_expect(v_full + stage * 8, kTile);
@@ -229,6 +260,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           bar_wait(k_full + ks * 8, kph);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
+            if (t >= kTiles) break;
             bar_wait(s_empty + sbuf * 8, sph ^ 1u);
             tc_fence_after();
 #pragma unroll
@@ -268,6 +300,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           bar_wait(v_full + vs * 8, vph);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
+            if (t >= kTiles) break;
             bar_wait(p_full + t * 8, pph);
             if (j == 0) bar_wait(o_empty + t * 8, (it & 1u) ^ 1u);     // previous item's O of this tile has been read out
             tc_fence_after();
@@ -296,12 +329,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16);
     uint32_t blk = 0, it = 0;        // key blocks done by this group over the life of the CTA
-    const int ldy = p.heads * kHD;
-    for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++it) {
+    const int ldy = p.heads * p.out_d;
+    const int mine = row >> 6;       // small mode: which of the tile's two (batch, head) pairs this row belongs to
+    for (int w = blockIdx.x; w < p.n_items && t < kTiles; w += gridDim.x, ++it) {
       const int bh = w / p.q_pairs, qp = w - bh * p.q_pairs;
       float l = 0.f;
       for (int j = 0; j < p.n_kv; ++j, ++blk) {
-        const uint32_t n = 2 * blk + t;                 // logit tile number -> S ring slot and phase
+        const uint32_t n = kTiles * blk + t;           // logit tile number -> S ring slot and phase
         const uint32_t sbuf = n % kSBufs, sph = (n / kSBufs) & 1u;
         bar_wait(s_full + sbuf * 8, sph);
         tc_fence_after();
@@ -315,20 +349,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
+          // small mode: keys [j*128 + sub*64, +64) of the item's 2 sk belong to pair 0 (< sk) or pair 1 (warp-uniform test)
+          const bool other = SMALL && ((j * kTK + sub * 64 >= p.sk) ? 1 : 0) != mine;
           float v[64];
-          tmem_ld32(lane_addr + kColS + sbuf * kTK + sub * 64, v);
-          tmem_ld32(lane_addr + kColS + sbuf * kTK + sub * 64 + 32, v + 32);
-          tmem_ld_wait();
+          if (!other) {
+            tmem_ld32(lane_addr + kColS + sbuf * kTK + sub * 64, v);
+            tmem_ld32(lane_addr + kColS + sbuf * kTK + sub * 64 + 32, v + 32);
+            tmem_ld_wait();
+          }
           if (sub == 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) bar_arrive(s_empty + sbuf * 8);
           }
+          if (other) {            // logits against the other pair's keys: P = 0, nothing added to the row sum
+            if (sub == 0) bar_wait(p_empty + t * 8, (blk & 1u) ^ 1u);
+            uint8_t* prow0 = smem + kOffP + (t * 2 + sub) * kTile + row * 128;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4*>(prow0 + (u << 4)) = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+          }
           uint32_t pk[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             pk[i] = SCALE ? pk2(v[2 * i] * p.c1, v[2 * i + 1] * p.c1) : pk2(v[2 * i], v[2 * i + 1]);
-            if (!(p.dbg & 2)) pk[i] = ex2_pk2(pk[i]);
+            if (!(p.dbg & 2)) pk[i] = (POLY > 0 && i % (POLY > 0 ? POLY : 1) == POLY - 1) ? ex2_poly_pk2(pk[i]) : ex2_pk2(pk[i]);
           }
           // row sum: packed adds over 8 pairs (<= 8 * 2981 per lane, exact enough in 16 bits), then fp32
 #pragma unroll
@@ -361,12 +406,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) bar_arrive(o_empty + t * 8);
-      const int b = bh / p.heads, h = bh - b * p.heads;
-      uint4* dst = reinterpret_cast<uint4*>(p.y + (static_cast<size_t>(b) * p.sq + (qp * 2 + t) * kTQ + row) * ldy + h * kHD);
+      const int bh_row = SMALL ? 2 * w + mine : bh;
+      if (bh_row >= p.n_bh) continue;                       // odd number of (batch, head) pairs: the last tile is half empty
+      const int b = bh_row / p.heads, h = bh_row - b * p.heads;
+      const int srow = SMALL ? (row & 63) : (qp * 2 + t) * kTQ + row;
+      uint4* dst = reinterpret_cast<uint4*>(p.y + (static_cast<size_t>(b) * p.sq + srow) * ldy + h * p.out_d);
 #pragma unroll
       for (int u = 0; u < 8; ++u)
-        dst[u] = make_uint4(pk2(o[8 * u] * inv, o[8 * u + 1] * inv), pk2(o[8 * u + 2] * inv, o[8 * u + 3] * inv),
-                            pk2(o[8 * u + 4] * inv, o[8 * u + 5] * inv), pk2(o[8 * u + 6] * inv, o[8 * u + 7] * inv));
+        if (8 * u < p.out_d)
+          dst[u] = make_uint4(pk2(o[8 * u] * inv, o[8 * u + 1] * inv), pk2(o[8 * u + 2] * inv, o[8 * u + 3] * inv),
+                              pk2(o[8 * u + 4] * inv, o[8 * u + 5] * inv), pk2(o[8 * u + 6] * inv, o[8 * u + 7] * inv));
     }
   }
 
@@ -382,7 +431,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
 bool attn_tc_supported(const vb_attn_desc* d) {
   static const bool off = getenv("VB_ATTN_TC") != nullptr && atoi(getenv("VB_ATTN_TC")) == 0;     // A/B testing
-  return !off && d->head_dim == kHD && d->sq % (2 * kTQ) == 0 && d->sk % kTK == 0;
+  const int ld = d->ld > 0 ? d->ld : d->head_dim;
+  if (off || ld != kHD || (d->head_dim != kHD && d->head_dim != 32)) return false;     // rows of 64 elements (D = 32: zero-padded)
+  if (d->sq % (2 * kTQ) == 0 && d->sk % kTK == 0) return true;
+  // The 8x8 level (sq == 64): two (batch, head) pairs per query tile, block-diagonal logits.  Correct and tested, but the
+  // items are too short for this pipeline (11.9 us against 7.6 us for the mma.sync kernel at B=64, profiles/r02_attention.txt):
+  // opt-in with VB_ATTN_SMALL=1.
+  const char* e = getenv("VB_ATTN_SMALL");
+  return e != nullptr && atoi(e) != 0 && d->sq == 64 && d->sk % 64 == 0 && d->head_dim == kHD;
 }
 
 int attn_tc_launch(const vb_attn_desc* d, cudaStream_t s) {
@@ -400,29 +456,41 @@ int attn_tc_launch(const vb_attn_desc* d, cudaStream_t s) {
   if (rc != VB_OK) return rc;
   AttnTcParams p;
   memset(&p, 0, sizeof(p));
-  p.q_pairs = d->sq / (2 * kTQ);
-  p.n_items = d->B * d->heads * p.q_pairs;
-  p.n_kv = d->sk / kTK;
+  p.small = d->sq == 64 ? 1 : 0;
+  p.tiles = p.small ? 1 : 2;
+  p.n_bh = d->B * d->heads;
+  p.out_d = d->head_dim;
+  p.q_pairs = p.small ? 1 : d->sq / (2 * kTQ);
+  p.n_items = p.small ? (p.n_bh + 1) / 2 : p.n_bh * p.q_pairs;
+  p.n_kv = p.small ? 2 * d->sk / kTK : d->sk / kTK;
   p.heads = d->heads;
   p.sq = d->sq;
   p.sk = d->sk;
-  p.c1 = 1.4426950408889634f / sqrtf(static_cast<float>(kHD));
+  p.c1 = 1.4426950408889634f / sqrtf(static_cast<float>(d->head_dim));
   p.zero_keys = static_cast<float>(d->zero_keys);
   p.y = static_cast<op_t*>(d->y);
   p.idesc_s = umma_idesc_op(kTQ, kTK);
   p.idesc_o = umma_idesc_op(kTQ, kHD) | (1u << 16);        // B (= V) is MN-major: [key][d] as it lies in memory
-  static unsigned long long attr_done = 0;        // the opt-in shared-memory attribute is per device
-  const unsigned long long dev_bit = 1ull << current_device();
-  if (!(attr_done & dev_bit)) {
-    VB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
-    VB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
-    attr_done |= dev_bit;
-  }
   static const int dbg = getenv("VB_ATTN_DBG") ? atoi(getenv("VB_ATTN_DBG")) : 0;
+  // share of the 2^x evaluations moved from the MUFU pipe to the FMA pipe: every POLY-th packed pair (0: none)
+  static const int poly_env = getenv("VB_ATTN_POLY") ? atoi(getenv("VB_ATTN_POLY")) : 0;
   p.dbg = dbg;
+  const bool scale = !(d->q_prescaled || (dbg & 1));
+  typedef void (*Fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnTcParams);
+  Fn fn;
+  int slot;
+  if (p.small) { fn = scale ? attn_tc_kernel<true, 0, true> : attn_tc_kernel<false, 0, true>; slot = scale ? 6 : 7; }
+  else if (poly_env == 2) { fn = scale ? attn_tc_kernel<true, 2, false> : attn_tc_kernel<false, 2, false>; slot = scale ? 0 : 1; }
+  else if (poly_env == 3) { fn = scale ? attn_tc_kernel<true, 3, false> : attn_tc_kernel<false, 3, false>; slot = scale ? 2 : 3; }
+  else { fn = scale ? attn_tc_kernel<true, 0, false> : attn_tc_kernel<false, 0, false>; slot = scale ? 4 : 5; }
+  static unsigned long long attr_done[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // the opt-in shared-memory attribute is per device
+  const unsigned long long dev_bit = 1ull << current_device();
+  if (!(attr_done[slot] & dev_bit)) {
+    VB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    attr_done[slot] |= dev_bit;
+  }
   const int grid = std::min(p.n_items, num_sms());
-  if (dbg & 1) VB_CHECK_CUDA(launch_pdl(attn_tc_kernel<false>, dim3(grid), dim3(kAtThreads), kAtSmem, s, mq, mk, mv, p));
-  else VB_CHECK_CUDA(launch_pdl(attn_tc_kernel<true>, dim3(grid), dim3(kAtThreads), kAtSmem, s, mq, mk, mv, p));
+  VB_CHECK_CUDA(launch_pdl(fn, dim3(grid), dim3(kAtThreads), kAtSmem, s, mq, mk, mv, p));
   VB_CHECK_CUDA(cudaGetLastError());
   return VB_OK;
 }

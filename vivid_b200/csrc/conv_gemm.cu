@@ -60,6 +60,17 @@ __device__ unsigned long long g_conv_cycles;
 // VB_DBG & 32: clock64 time stamps of CTA 0's phases (see vb_debug_conv_cycles).
 __device__ long long g_conv_ts[8];
 #define VB_TS(i) do { if (p.dbg & 32) { if (blockIdx.x == 0) g_conv_ts[i] = clock64(); } } while (0)
+// -DVB_EPI_PROF (measurement builds only): CTA 0's epilogue leader and one other epilogue thread accumulate the cycles they
+// spend in each phase of the per-chunk loop and print them when the kernel ends.
+#ifdef VB_EPI_PROF
+#define VB_EP_DECL long long ep_t = clock64(), ep_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const bool ep_on = blockIdx.x == 0 && (lane == 0) && (warp == kFirstEpiWarp || warp == kFirstEpiWarp + 5)
+#define VB_EP(i) do { if (ep_on) { const long long n_ = clock64(); ep_acc[i] += n_ - ep_t; ep_t = n_; } } while (0)
+#define VB_EP_PRINT do { if (ep_on) printf("epi warp %d leader %d: res_wait %lld tmem_ld %lld math %lld put %lld fence+drain %lld barrier %lld tma_issue %lld other %lld\n", warp, (int)leader, ep_acc[0], ep_acc[1], ep_acc[2], ep_acc[3], ep_acc[4], ep_acc[5], ep_acc[6], ep_acc[7]); } while (0)
+#else
+#define VB_EP_DECL
+#define VB_EP(i)
+#define VB_EP_PRINT
+#endif
 
 struct ConvKernelParams {
   int B, H, W;
@@ -114,6 +125,8 @@ struct ConvKernelParams {
   int part_seq[3];
   int part_off[3];
   float norm_scale;   // 1/sqrt(head_dim)
+  int part_ld;          // QKVNORM: elements per destination row (head_dim, or 64 for zero-padded D = 32 rows)
+  float part_scale[3];  // QKVNORM: multiplier of the normalised rows of part j (q: log2(e)/sqrt(D) of the softmax)
   int dbg;            // ablation switches for micro-benchmarks (VB_DBG): 1 = epilogue does no work, 2 = no TMA stores,
                       // 16 = record CTA lifetimes
 };
@@ -210,9 +223,10 @@ __device__ __forceinline__ void epi_group_qkv(const ConvKernelParams& p, uint32_
   float ss = 0.f;
 #pragma unroll
   for (int j = 0; j < D; ++j) ss += v[j] * v[j];
-  const float inv = 1.0f / (1e-4f + sqrtf(ss) * p.norm_scale);
   const int gg = gcol / D;
   const int part = gg % p.parts;
+  const float inv = (part == 0 ? p.part_scale[0] : (part == 1 ? p.part_scale[1] : p.part_scale[2])) /
+                    (1e-4f + sqrtf(ss) * p.norm_scale);
   const int head = gg / p.parts;
   const int b = n / p.seg_div;
   const int seg = n - b * p.seg_div;
@@ -220,7 +234,7 @@ __device__ __forceinline__ void epi_group_qkv(const ConvKernelParams& p, uint32_
   const int seq = part == 0 ? p.part_seq[0] : (part == 1 ? p.part_seq[1] : p.part_seq[2]);
   const int off = part == 0 ? p.part_off[0] : (part == 1 ? p.part_off[1] : p.part_off[2]);
   const size_t tok = (static_cast<size_t>(b) * p.heads + head) * seq + off + seg * (p.H * p.W) + s;
-  uint4* o = reinterpret_cast<uint4*>(base + tok * D);
+  uint4* o = reinterpret_cast<uint4*>(base + tok * p.part_ld);
 #pragma unroll
   for (int j = 0; j < D / 8; ++j)
     o[j] = make_uint4(pack_op2(v[8 * j] * inv, v[8 * j + 1] * inv), pack_op2(v[8 * j + 2] * inv, v[8 * j + 3] * inv),
@@ -829,6 +843,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int half = EG ? 0 : wq;                                   // which CW columns of every 64-column chunk (part)
     const int row = quad * 32 + lane;
     const bool leader = elect_one_sync() && warp == kFirstEpiWarp + 4 * group;  // one thread per group issues its TMA traffic
+    VB_EP_DECL;
     const int rx = row % p.bw;
     const int r2 = row / p.bw;
     const int ry = r2 % p.bh;
@@ -891,22 +906,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
       // The leader keeps the residual ring full ACROSS tile boundaries: the next tile's residual is in flight while
       // this tile is being finished.
+      // (the leader's instruction stream is serial and sits on every chunk's critical path: the tile of the next residual
+      //  item is decoded once per tile and the item index advances by adds — no divisions per item)
+      uint32_t rt_item = 0;                      // item within the tile whose residual is issued next
+      uint32_t rt_tile = EG ? group : 0;         // CTA-local index of that tile
+      bool rt_have = false;
+      TileCoord rt_t = {0, 0, 0, 0};
       auto res_topup = [&]() {
         if (has_res && leader) {
           while (res_issued < res_q + static_cast<uint32_t>(p.res_slots)) {
-            const uint32_t tg = res_issued / items;                  // this group's tile number ...
-            const uint32_t ti = EG ? 2 * tg + group : tg;            // ... and its CTA-local index
-            const int wl = p.rowroll ? static_cast<int>(ti >> p.strip_shift) : static_cast<int>(ti);
-            const int ql = q0 + wl * qstride;
-            if (ql >= p.total_q) break;
-            const TileCoord tt = p.rowroll ? strip_tile(p, ql, static_cast<int>(ti) & (p.strip_rows - 1))
-                                           : decode_tile(p, tile_of(p, ql, rank));
+            if (!rt_have) {
+              const int wl = p.rowroll ? static_cast<int>(rt_tile >> p.strip_shift) : static_cast<int>(rt_tile);
+              const int ql = q0 + wl * qstride;
+              if (ql >= p.total_q) break;
+              rt_t = p.rowroll ? strip_tile(p, ql, static_cast<int>(rt_tile) & (p.strip_rows - 1))
+                               : decode_tile(p, tile_of(p, ql, rank));
+              rt_have = true;
+            }
             const uint32_t slot = res_issued & rmask;
             mbar_wait(&res_empty_g[slot], ((res_issued >> rshift) & 1u) ^ 1u);
             mbar_expect_tx(&res_full_g[slot], kChunkBytes);
-            tma_load_4d(&map_res, &res_full_g[slot], res_ring + slot * kChunkBytes,
-                        tt.col0 + static_cast<int>((res_issued % items) % chunks) * 64, tt.x0, tt.y0, tt.n0);
+            const int rc = static_cast<int>(rt_item >= static_cast<uint32_t>(chunks) ? rt_item - chunks : rt_item);
+            tma_load_4d(&map_res, &res_full_g[slot], res_ring + slot * kChunkBytes, rt_t.col0 + rc * 64, rt_t.x0, rt_t.y0,
+                        rt_t.n0);
             ++res_issued;
+            if (++rt_item == static_cast<uint32_t>(items)) {
+              rt_item = 0;
+              rt_tile += EG ? 2 : 1;
+              rt_have = false;
+            }
           }
         }
       };
@@ -928,11 +956,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       auto stg_region = [&]() -> uint8_t* { return stg_ring + greg * p.gslots * kChunkBytes; };
       // All 256 threads wrote their part of the region: publish it to the async proxy and let the leader store it.
       auto stg_commit = [&](const TileCoord& t, int c, bool norm_pass, int only = -1) {
+        VB_EP(3);
         fence_proxy_async();
         if (leader) {
           if (p.stg_regions == 3) bulk_wait_read<1>(); else bulk_wait_read<0>();
         }
+        VB_EP(4);
         named_bar_sync(kEpiBarrier + group, kEpiThreads);
+        VB_EP(5);
         if (leader && !(p.dbg & 2)) {
           const uint8_t* reg = stg_region();
           int di = 0;
@@ -941,6 +972,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if ((only < 0 || only == 2) && (norm_pass ? kind_norm(k2) : kind_direct(k2))) tma_store_4d(&map_out.m[2], reg + (di++) * kChunkBytes, t.col0 + c * 64, t.x0, t.y0, t.n0);
           bulk_commit();
         }
+        VB_EP(6);
         if (++greg == static_cast<uint32_t>(p.stg_regions)) greg = 0;
       };
 
@@ -1022,7 +1054,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         };
         if (modsilu) mod_fetch(0, half);
 
+        VB_EP(7);
         mbar_wait(&tmem_full[buf], bphase);
+#ifdef VB_EPI_PROF
+        if (ep_on) ep_t = clock64();          // (waiting for the accumulator is not epilogue work)
+#endif
         if (leader && it == 0) VB_TS(4);
         tc_fence_after();
 
@@ -1035,7 +1071,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
         for (int c = 0; c < MAXC; ++c) {
           if (c < chunks) {
+            VB_EP(7);
             const uint8_t* rrow = has_res ? res_acquire() : nullptr;
+            VB_EP(0);
             uint32_t r16h[HH][CW / 2];
 #pragma unroll
             for (int hh = 0; hh < HH; ++hh) {
@@ -1045,6 +1083,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               float v[CW];
               if (CW == 32) tmem_ld32(ta, v); else tmem_ld16(ta, v);
               tmem_ld_wait();
+              VB_EP(1);
               if (c == chunks - 1 && hh == HH - 1) {   // accumulator fully read: the MMA warp may start the tile after next
                 if (p.rowroll) slot_clear(taddr);
                 tc_fence_before();
@@ -1110,6 +1149,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               }
             }
             if (has_res) res_release();
+            VB_EP(2);
             if (any_direct) {
               // one output after the other through a single staging slot (ping-pong epilogue: its two rings must fit), or
               // all outputs of the chunk side by side and one commit
@@ -1201,6 +1241,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       if (leader) bulk_wait_read<0>();          // staging smem must outlive the last TMA store's read
       if (leader) VB_TS(5);
+      VB_EP_PRINT;
     }
   }
 
@@ -1356,7 +1397,9 @@ static bool plan_mainloop(ConvKernelParams& p, int budget, bool want_good) {
 // Quality of a main-loop layout (higher is better): resident weights >> shared haloed boxes >> per-tap stages, then depth.
 static int mainloop_score(const ConvKernelParams& p) {
   if (p.tap_mode != 0) return (p.b_resident ? 2000 : 1000) + 10 * std::min(p.a_slots, 5) + std::min(p.b_slots, 12);
-  return (p.b_resident ? 500 : 0) + 10 * std::min(p.num_stages, 6);
+  // 1x1 layers have 2-16 K blocks per tile: four stages cover the TMA latency, and what bounds them is the epilogue — a deep
+  // residual ring (4 slots) is worth more than a fifth and sixth stage (profiles/r02_conv1_epilogue.txt)
+  return (p.b_resident ? 500 : 0) + 10 * std::min(p.num_stages, p.taps == 1 ? 4 : 6);
 }
 
 int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
@@ -1569,8 +1612,12 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
     for (int j = 0; j < 3; ++j) {
       p.part_seq[j] = d->part_seq[j];
       p.part_off[j] = d->part_off[j];
+      p.part_scale[j] = d->out_scale[j] != 0.f ? d->out_scale[j] : 1.0f;
     }
     p.norm_scale = 1.0f / sqrtf(static_cast<float>(d->head_dim));
+    VB_REQUIRE_L(d->part_ld == 0 || d->part_ld == d->head_dim || (d->part_ld == 64 && d->head_dim == 32),
+                 "vb_conv: part_ld must be 0, head_dim, or 64 with head_dim 32");
+    p.part_ld = d->part_ld > 0 ? d->part_ld : d->head_dim;
     if (forced_pair == 1 && pair_possible) set_pair(1);
     VB_REQUIRE_L(plan_mainloop(p, kSmemMax, false), "vb_conv: shared memory budget exceeded");
   }

@@ -216,6 +216,9 @@ class Plan:
         if qkv:
             parts = qkv["parts"]
             d.head_dim, d.parts, d.seg_div = qkv["D"], parts, qkv.get("seg_div", 1)
+            d.part_ld = qkv.get("ld", 0)
+            if parts == 3:      # the softmax's log2(e)/sqrt(D) rides on q: one multiply per q element instead of one per logit
+                d.out_scale[0] = math.log2(math.e) / math.sqrt(qkv["D"])
             for j in range(parts):
                 d.part_out[j] = qkv["out"][j].data_ptr()
                 d.part_seq[j] = qkv["seq"][j]
@@ -262,9 +265,10 @@ class Plan:
         wr = 2.0 * P * ctot * ((out is not None) + (out_silu is not None))
         self.op_info.append(("eltwise", f"kind{kind} {R}x{R} c{ctot}", 0.0, rd + wr))
 
-    def attention(self, q, k, v, y, B, heads, sq, sk, D, zero_keys):
+    def attention(self, q, k, v, y, B, heads, sq, sk, D, zero_keys, ld=0):
+        # q carries log2(e)/sqrt(D) already (folded into the QKV GEMM epilogue, see run_unet): p = 2^(q.k)
         d = L.AttnDesc(q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), y=y.data_ptr(), B=B, heads=heads, sq=sq, sk=sk,
-                       head_dim=D, zero_keys=zero_keys)
+                       head_dim=D, zero_keys=zero_keys, q_prescaled=1, ld=ld)
         L.check(self.lib.vb_plan_add_attn(self.handle, C.byref(d)), "vb_plan_add_attn")
         self.alg_flops += 4.0 * B * heads * sq * sk * D
         self.op_info.append(("attn", f"h{heads} sq{sq} sk{sk} d{D}", 4.0 * B * heads * sq * sk * D,
@@ -455,22 +459,30 @@ class Plan:
                 nseg = feat_seg if s.xattn else 0
                 real_seg = 0 if zero_feature_keys else nseg
                 sk = S * (1 + real_seg)
-                q = self.act(B * h * S, D)
-                k = self.act(B * h * sk, D)
-                v = self.act(B * h * sk, D)
+                # D = 32 (the SR UNet): rows zero-padded to 64 elements so that the tcgen05 attention kernel (64-wide
+                # operand rows) serves them; the buffers are private to this layer and zeroed once — the GEMM epilogue only
+                # ever writes the lower 32 elements.  (Twice the attention FLOPs of a dense D = 32 kernel, 0.7 % of the SR net.)
+                ld = 64 if (D == 32 and S % 256 == 0 and sk % 128 == 0) else 0
+                if ld:
+                    q, k, v = (self.buf((B * h * n, ld), self.op_dtype, zero=True) for n in (S, sk, sk))
+                else:
+                    q = self.act(B * h * S, D)
+                    k = self.act(B * h * sk, D)
+                    v = self.act(B * h * sk, D)
                 wq = self.prep_weight(mod_.attn_qkv.weight, perm=(3, D))
-                self.conv(xr, wq, B, R, Cc, 3 * Cc, 1, qkv=dict(D=D, parts=3, out=[q, k, v], seq=[S, sk, sk], off=[0, 0, 0]))
+                self.conv(xr, wq, B, R, Cc, 3 * Cc, 1,
+                          qkv=dict(D=D, parts=3, out=[q, k, v], seq=[S, sk, sk], off=[0, 0, 0], ld=ld))
                 if s.xattn and not zero_feature_keys:
                     f = features.pop(0)
                     assert f.C == Cc and f.R == R, f"{s.name}: feature map mismatch"
                     wkv = self.prep_weight(mod_.x_attn_kv.weight, perm=(2, D))
                     self.conv(f.raw, wkv, f.B, R, Cc, 2 * Cc, 1,
-                              qkv=dict(D=D, parts=2, out=[k, v], seq=[sk, sk], off=[S, S], seg_div=feat_seg))
+                              qkv=dict(D=D, parts=2, out=[k, v], seq=[sk, sk], off=[S, S], seg_div=feat_seg, ld=ld))
                     # f.raw stays allocated for the life of the plan: return_features / inject_features read and write it
                 y = self.a16(B, R, Cc)
-                temps += [q, k, v, y]
+                temps += [y] if ld else [q, k, v, y]           # (padded q/k/v are private: never recycled through the pool)
                 # unconditional model: x_attn_kv(0) == 0 -> the S*nseg zero keys are accounted for analytically
-                self.attention(q, k, v, y, B, h, S, sk, D, S * nseg if zero_feature_keys else 0)
+                self.attention(q, k, v, y, B, h, S, sk, D, S * nseg if zero_feature_keys else 0, ld=ld)
                 wp = self.prep_weight(mod_.attn_proj.weight)
                 outs = alloc_outs(out, want(i))
                 self.conv(y, wp, B, R, Cc, Cc, 1, res=xr, res_mode=L.VB_RES_PLAIN, res_t=mod_.attn_balance, clip=clip,

@@ -14,15 +14,53 @@ GEOM_STD = (0.1104, 0.0346, 0.2279, 0.4930, 0.0347, 0.0091, 0.0367, 0.2208, 0.22
             6.6511, 0.0, 0.0, 6.6464, 6.6511, 0.0, 0.0)
 
 
-def compose_geometry(tgt2src, src_k, tgt_k, imsize=64):
-    """Pack [R|t] (3x4) + two [fx,fy,cx,cy] intrinsics into the normalised 20-vector the networks are
-    conditioned on (mirror of training/utils.py:64-81: zero where the statistic's std is 0)."""
-    mean = torch.tensor(GEOM_MEAN, dtype=tgt2src.dtype, device=tgt2src.device).clone()
-    std = torch.tensor(GEOM_STD, dtype=tgt2src.dtype, device=tgt2src.device).clone()
+def compose_K(K):
+    """3x3 intrinsic matrices -> [fx, fy, cx, cy] (snapshot experiments/code/training/utils.py:48-52)."""
+    return torch.stack((K[..., 0, 0], K[..., 1, 1], K[..., 0, 2], K[..., 1, 2]), -1)
+
+
+def decompose_K(t):
+    """[fx, fy, cx, cy] -> 3x3 intrinsic matrices (snapshot utils.py:55-62)."""
+    K = torch.zeros(size=t.shape[:-1] + (3, 3), dtype=t.dtype, device=t.device)
+    K[..., 0, 0], K[..., 1, 1], K[..., 0, 2], K[..., 1, 2] = t.unbind(-1)
+    K[..., 2, 2] = 1
+    return K
+
+
+def _geom_stats(ref, imsize):
+    mean = torch.tensor(GEOM_MEAN, dtype=ref.dtype, device=ref.device).clone()
+    std = torch.tensor(GEOM_STD, dtype=ref.dtype, device=ref.device).clone()
     mean[12:] *= imsize / 64
     std[12:] *= (imsize / 64) ** 2
+    return mean, std
+
+
+def compose_geometry(tgt2src, src_k, tgt_k, imsize=64):
+    """Pack [R|t] (3x4) + two intrinsics into the normalised 20-vector the networks are conditioned on (zero where the
+    statistic's std is 0).  Both call forms of the reference are accepted: [fx,fy,cx,cy] vectors (current tree,
+    training/utils.py:64-81) and 3x3 K matrices (snapshot experiments/code/training/utils.py:65-75, via compose_K)."""
+    if src_k.shape[-2:] == (3, 3) and src_k.ndim == tgt2src.ndim:
+        src_k = compose_K(src_k)
+    if tgt_k.shape[-2:] == (3, 3) and tgt_k.ndim == tgt2src.ndim:
+        tgt_k = compose_K(tgt_k)
+    mean, std = _geom_stats(tgt2src, imsize)
     flat = torch.cat((tgt2src.reshape(*tgt2src.shape[:-2], 12), src_k, tgt_k), dim=-1)
     return torch.where(std > 0, (flat - mean) / std, torch.zeros_like(flat))
+
+
+def decompose_geometry(t, imsize=64):
+    """Inverse of compose_geometry: (tgt2src [.,3,4], src_K [.,3,3], tgt_K [.,3,3]) (snapshot utils.py:78-87)."""
+    mean, std = _geom_stats(t, imsize)
+    t = t * std + mean
+    return t[..., :12].reshape(*t.shape[:-1], 3, 4), decompose_K(t[..., 12:16]), decompose_K(t[..., 16:])
+
+
+def resize_geometry(geometry, _from, _to):
+    """Re-express a pose vector for another image size (snapshot utils.py:90-97)."""
+    tgt2src, src_K, tgt_K = decompose_geometry(geometry, _from)
+    src_K[..., :2, :] = src_K[..., :2, :] * _to / _from
+    tgt_K[..., :2, :] = tgt_K[..., :2, :] * _to / _from
+    return compose_geometry(tgt2src, src_K, tgt_K, _to)
 
 
 def _rot(yaw, pitch, roll):
