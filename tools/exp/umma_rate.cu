@@ -53,10 +53,22 @@ __global__ void __launch_bounds__(128) rate_kernel(long long* out, int N, int it
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tm, 512); }
 }
 
-int main() {
+int main(int argc, char** argv) {
   long long* d; cudaMalloc(&d, 148 * 8);
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const int iters = 2000;
+  if (argc > 1) {
+    // "cal": four launches of back-to-back MMAs (N = 64, 128, 192, 256; the last two keep the tensor pipe 100 % busy) — the
+    // calibration run for ncu's tensor-pipe counters (profiles/r02_tensor_pipe_metric.txt)
+    for (int N : {64, 128, 192, 256}) {
+      rate_kernel<<<148, 128, 100 * 1024>>>(d, N, 4 * iters, 1, 0, 0);
+      cudaDeviceSynchronize();
+      long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+      long long mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+      printf("cal N=%3d : %.1f cycles per MMA (tensor-pipe floor %d), %lld cycles in the MMA sequence\n", N, (double)mx / (iters * 16), N / 2, mx);
+    }
+    return 0;
+  }
   const int Ns[] = {64, 128, 192, 256};
   for (int N : Ns)
     for (int mode = 0; mode < 2; ++mode)

@@ -59,7 +59,8 @@ int encode_tmap_16(CUtensorMap* map, const void* base, int rank, const uint64_t*
 // ---- prepared launches (tensor maps encoded once, replayable) ----
 struct ConvLaunch;   // conv_gemm.cu
 int conv_prepare(const vb_conv_desc* d, ConvLaunch** out);
-int conv_launch(const ConvLaunch* l, cudaStream_t s);
+// chained: the previous kernel of the stream is another op of the same plan (it cannot have written this op's weights)
+int conv_launch(const ConvLaunch* l, cudaStream_t s, bool chained);
 void conv_free(ConvLaunch* l);
 double conv_flops(const ConvLaunch* l);
 

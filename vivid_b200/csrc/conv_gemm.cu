@@ -129,6 +129,7 @@ struct ConvKernelParams {
   float part_scale[3];  // QKVNORM: multiplier of the normalised rows of part j (q: log2(e)/sqrt(D) of the softmax)
   int dbg;            // ablation switches for micro-benchmarks (VB_DBG): 1 = epilogue does no work, 2 = no TMA stores,
                       // 16 = record CTA lifetimes
+  int wgt_nowait;     // set per launch: the weight producer need not wait for the previous kernel (see the PDL note in the kernel)
 };
 
 struct TileCoord {
@@ -190,6 +191,18 @@ __device__ __forceinline__ uint32_t mp_silu_pk(uint32_t x2, float scale) {
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(hu));
   const __half2 c = __float2half2_rn(0.5f / 0.596f);
   __half2 y = __hmul2(x, __hfma2(*reinterpret_cast<__half2*>(&tu), c, c));
+#endif
+  return *reinterpret_cast<uint32_t*>(&y);
+}
+
+// Clamp of a packed fp16 pair to [-c, c] (c exactly representable in fp16).
+__device__ __forceinline__ uint32_t clamp_pk(uint32_t x2, float c) {
+#ifdef VB_OP_BF16
+  __nv_bfloat162 cc = __float2bfloat162_rn(c);
+  __nv_bfloat162 y = __hmin2(__hmax2(*reinterpret_cast<__nv_bfloat162*>(&x2), __hneg2(cc)), cc);
+#else
+  __half2 cc = __float2half2_rn(c);
+  __half2 y = __hmin2(__hmax2(*reinterpret_cast<__half2*>(&x2), __hneg2(cc)), cc);
 #endif
   return *reinterpret_cast<uint32_t*>(&y);
 }
@@ -739,6 +752,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   constexpr int kEpiWarps = EG ? 8 : 4 * PARTS;
   constexpr int kTileWarps = EG ? 4 : kEpiWarps;      // warps working on one tile
   constexpr int kEpiThreads = kTileWarps * 32;
+  // specialised variant without pixel-norm outputs (nothing is kept across the chunks of a tile)
+  constexpr bool kNoNormT = K0_T >= 0 && K1_T >= 0 && K2_T >= 0 && K0_T < VB_OUT_NORM && K1_T < VB_OUT_NORM && K2_T < VB_OUT_NORM;
   constexpr int CW = 64 / NP;             // accumulator columns per thread per part
   constexpr int U = CW / 8;               // 16-byte units per part per chunk row
   extern __shared__ uint8_t smem_raw[];
@@ -806,7 +821,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (p.pair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  pdl_grid_sync();      // everything above overlapped the previous kernel's tail; global memory is touched from here on
+  // Everything above overlapped the previous kernel's tail; dependent global memory is touched from here on.  The weight
+  // producer (warp 3) does NOT wait: prepared weights are constants of the plan (written at plan build, long before any
+  // replay), so its first tiles — or the whole resident slab — arrive while the previous kernel is still draining.
+  // (Only when the launch says the previous kernel of the stream is another op of the same plan, p.wgt_nowait: a one-shot
+  // vb_conv, or the first op of a replayed range, may directly follow the kernel that wrote its weights.)
+  if (warp != 3 || !p.wgt_nowait) pdl_grid_sync(); else pdl_launch_dependents();
   if (threadIdx.x == 0) VB_TS(1);
 
   if (warp < 2 || warp == 3) {
@@ -870,10 +890,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (leader && it == 0) VB_TS(4);
         tc_fence_after();
         if (p.epi_mode == VB_EPI_QKVNORM) {
+          // the column groups of a tile are dealt to the PARTS warps of a lane quadrant starting with a different warp on
+          // every tile: with an odd number of groups (block_n = 192, D = 64) the extra one alternates instead of always
+          // landing on the same warp (2 : 1 became 3 : 3 over two tiles)
+          const int first = (half + it) % PARTS;
           if (p.head_dim == 64) {
-            for (int c = half * 64; c < p.block_n; c += 64 * PARTS) epi_group_qkv<64>(p, taddr + c, t.col0 + c, n, s_img, valid);
+            for (int c = first * 64; c < p.block_n; c += 64 * PARTS) epi_group_qkv<64>(p, taddr + c, t.col0 + c, n, s_img, valid);
           } else {
-            for (int c = half * 32; c < p.block_n; c += 32 * PARTS) epi_group_qkv<32>(p, taddr + c, t.col0 + c, n, s_img, valid);
+            for (int c = first * 32; c < p.block_n; c += 32 * PARTS) epi_group_qkv<32>(p, taddr + c, t.col0 + c, n, s_img, valid);
           }
         } else {
           for (int c = half * 16; c < p.block_n; c += 16 * PARTS) epi_f32_16(p, taddr + c, t.col0 + c, pix, valid);
@@ -1068,9 +1092,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         float ssp[HH];                              // sum of squares per column part (summed in the same order in every layout)
 #pragma unroll
         for (int hh = 0; hh < HH; ++hh) ssp[hh] = 0.f;
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
-          if (c < chunks) {
+        // One 64-column chunk of pass M.  (A lambda so that the chunk loop can be rolled or unrolled, see below.)
+        auto pass_m = [&](const int c) {
+          {
             VB_EP(7);
             const uint8_t* rrow = has_res ? res_acquire() : nullptr;
             VB_EP(0);
@@ -1126,8 +1150,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                   v[8 * j + 7] = fmaf(d.y, res_scale, v[8 * j + 7] * p.res_b);
                 }
               }
+#ifdef VB_OP_BF16
+              constexpr bool kClampPacked = false;
+#else
+              // fp16 stream without pixel-norm outputs: the saturating pack replaces the +-65504 clamp, and the clip of
+              // Block.forward (a bound that fp16 represents exactly, so clip-then-round == round-then-clip) runs on the packed
+              // pairs — 16 (or 0) instructions per 32 columns instead of 64
+              constexpr bool kClampPacked = kNoNormT;
+#endif
+              if (!kClampPacked || p.out_f32 != nullptr) {
 #pragma unroll
-              for (int j = 0; j < CW; ++j) v[j] = fminf(fmaxf(v[j], -clampv), clampv);
+                for (int j = 0; j < CW; ++j) v[j] = fminf(fmaxf(v[j], -clampv), clampv);
+              }
               if (needs_norm) {
 #pragma unroll
                 for (int j = 0; j < CW; ++j) ssp[hh] = fmaf(v[j], v[j], ssp[hh]);
@@ -1137,8 +1171,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < CW / 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
               }
+              if (kClampPacked) {
 #pragma unroll
-              for (int j = 0; j < CW / 2; ++j) r16h[hh][j] = pack_op2_nosat(v[2 * j], v[2 * j + 1]);
+                for (int j = 0; j < CW / 2; ++j) r16h[hh][j] = pack_sat2(v[2 * j], v[2 * j + 1]);
+                if (p.flags & VB_F_CLIP) {
+#pragma unroll
+                  for (int j = 0; j < CW / 2; ++j) r16h[hh][j] = clamp_pk(r16h[hh][j], clampv);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < CW / 2; ++j) r16h[hh][j] = pack_op2_nosat(v[2 * j], v[2 * j + 1]);
+              }
               if (mod_pk) {
 #pragma unroll
                 for (int j = 0; j < CW / 2; ++j) r16h[hh][j] = mp_silu_pk(r16h[hh][j], 1.0f);
@@ -1184,6 +1227,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 stg_commit(t, c, false);
               }
             }
+          }
+        };
+        // Variants without pixel-norm outputs keep nothing across chunks, so their chunk loop stays ROLLED: the epilogue of a
+        // tile is then ~0.6 k instructions instead of MAXC x that.  It matters because the short layers (16x16 / 8x8: one or two
+        // tiles per CTA) execute this code once or twice per launch, straight out of L2: with four unrolled copies (35-64 KiB
+        // per tile pass against a 32 KiB L1.5 / 6 KiB L0 instruction cache) half of the epilogue warps' stall samples on the
+        // 1x1 attn_proj layers were instruction fetches (stall_no_inst, profiles/r02_conv_icache.txt).
+        if (kNoNormT) {
+#pragma unroll 1
+          for (int c = 0; c < chunks; ++c) pass_m(c);
+        } else {
+#pragma unroll
+          for (int c = 0; c < MAXC; ++c) {
+            if (c < chunks) pass_m(c);
           }
         }
 
@@ -1712,7 +1769,10 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
   return VB_OK;
 }
 
-int conv_launch(const ConvLaunch* l, cudaStream_t s) {
+int conv_launch(const ConvLaunch* l, cudaStream_t s, bool chained) {
+  static const bool nowait_off = getenv("VB_WGT_NOWAIT") != nullptr && atoi(getenv("VB_WGT_NOWAIT")) == 0;     // A/B testing
+  ConvKernelParams kp = l->p;
+  kp.wgt_nowait = (chained && !nowait_off) ? 1 : 0;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(l->grid);
@@ -1728,7 +1788,7 @@ int conv_launch(const ConvLaunch* l, cudaStream_t s) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, l->fn, l->map_a, l->map_a2, l->map_w, l->map_res, l->map_out, l->p));
+  VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, l->fn, l->map_a, l->map_a2, l->map_w, l->map_res, l->map_out, kp));
   return VB_OK;
 }
 
@@ -1754,7 +1814,7 @@ extern "C" int vb_conv(const vb_conv_desc* d, void* stream) {
   vb::ConvLaunch* l = nullptr;
   int rc = vb::conv_prepare(d, &l);
   if (rc != VB_OK) return rc;
-  rc = vb::conv_launch(l, static_cast<cudaStream_t>(stream));
+  rc = vb::conv_launch(l, static_cast<cudaStream_t>(stream), false);
   vb::conv_free(l);
   return rc;
 }

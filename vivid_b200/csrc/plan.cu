@@ -40,9 +40,10 @@ struct vb_plan {
   std::vector<Range> graphs;
 };
 
-static int run_op(const Op& op, cudaStream_t s) {
+// chained: op i-1 of the same plan was launched into the stream right before (see vb::conv_launch)
+static int run_op(const Op& op, cudaStream_t s, bool chained) {
   switch (op.kind) {
-    case OP_CONV: return vb::conv_launch(op.conv, s);
+    case OP_CONV: return vb::conv_launch(op.conv, s, chained);
     case OP_ATTN: return vb::attn_launch(&op.attn, s);
     case OP_EW: return vb::eltwise_launch(&op.ew, s);
     case OP_EMB: return vb::embed_launch(&op.emb, s);
@@ -127,7 +128,7 @@ extern "C" int vb_plan_run(vb_plan* p, int first, int last, void* stream) {
   if (last < 0 || last > n) last = n;
   VB_REQUIRE(first >= 0 && first <= last, "vb_plan_run: bad range [%d,%d)", first, last);
   for (int i = first; i < last; ++i) {
-    int rc = run_op(p->ops[i], static_cast<cudaStream_t>(stream));
+    int rc = run_op(p->ops[i], static_cast<cudaStream_t>(stream), i > first);
     if (rc != VB_OK) return rc;
   }
   return VB_OK;
@@ -153,7 +154,7 @@ extern "C" int vb_plan_launch_graph_range(vb_plan* p, int first, int last, void*
       return VB_ERR_CUDA;
     }
     int rc = VB_OK;
-    for (int i = first; i < last && rc == VB_OK; ++i) rc = run_op(p->ops[i], cap);
+    for (int i = first; i < last && rc == VB_OK; ++i) rc = run_op(p->ops[i], cap, i > first);
     cudaGraph_t g = nullptr;
     e = cudaStreamEndCapture(cap, &g);
     cudaStreamDestroy(cap);
