@@ -129,6 +129,9 @@ struct ConvKernelParams {
   float part_scale[3];  // QKVNORM: multiplier of the normalised rows of part j (q: log2(e)/sqrt(D) of the softmax)
   int dbg;            // ablation switches for micro-benchmarks (VB_DBG): 1 = epilogue does no work, 2 = no TMA stores,
                       // 16 = record CTA lifetimes
+  int qkv_stg;        // QKVNORM, D = 64: the normalised (token, head, q|k|v) rows leave through a shared-memory staging ring and
+                      // TMA stores (map_out.m[part]: {64, rows} 2-D maps of the three destinations) instead of per-thread stores
+  int qkv_rows;       // ... rows per store box = min(128, H*W)
   int wgt_nowait;     // set per launch: the weight producer need not wait for the previous kernel (see the PDL note in the kernel)
 };
 
@@ -252,6 +255,28 @@ __device__ __forceinline__ void epi_group_qkv(const ConvKernelParams& p, uint32_
   for (int j = 0; j < D / 8; ++j)
     o[j] = make_uint4(pack_op2(v[8 * j] * inv, v[8 * j + 1] * inv), pack_op2(v[8 * j + 2] * inv, v[8 * j + 3] * inv),
                       pack_op2(v[8 * j + 4] * inv, v[8 * j + 5] * inv), pack_op2(v[8 * j + 6] * inv, v[8 * j + 7] * inv));
+}
+
+// The same for D = 64 through shared memory: the thread writes its normalised 128-byte row into a SWIZZLE_128B staging
+// sub-tile (conflict-free 16-byte stores); one thread per column group then hands the 128 rows to a TMA store.  (Written by
+// the thread itself, a row costs eight store instructions that each touch 32 different 128-byte lines, 16 bytes apiece:
+// ~3 k LSU cycles per 128x192 tile, as long as the tile's main loop.)
+__device__ __forceinline__ void epi_group_qkv_stage(const ConvKernelParams& p, uint32_t taddr, int gcol, uint8_t* srow, int row) {
+  float v[64];
+  tmem_ld32(taddr, v);
+  tmem_ld32(taddr + 32, v + 32);
+  tmem_ld_wait();
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) ss += v[j] * v[j];
+  const int part = (gcol >> 6) % p.parts;
+  const float inv = (part == 0 ? p.part_scale[0] : (part == 1 ? p.part_scale[1] : p.part_scale[2])) /
+                    (1e-4f + sqrtf(ss) * p.norm_scale);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<uint4*>(srow + swz(j, row)) =
+        make_uint4(pack_op2(v[8 * j] * inv, v[8 * j + 1] * inv), pack_op2(v[8 * j + 2] * inv, v[8 * j + 3] * inv),
+                   pack_op2(v[8 * j + 4] * inv, v[8 * j + 5] * inv), pack_op2(v[8 * j + 6] * inv, v[8 * j + 7] * inv));
 }
 
 // fp32 direct-store epilogue for narrow outputs (out_conv: 16 padded columns).
@@ -862,7 +887,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int group = EG ? wq : 0;                                  // EG: which of the two alternating tile streams
     const int half = EG ? 0 : wq;                                   // which CW columns of every 64-column chunk (part)
     const int row = quad * 32 + lane;
-    const bool leader = elect_one_sync() && warp == kFirstEpiWarp + 4 * group;  // one thread per group issues its TMA traffic
+    // one thread per group issues its TMA traffic (staged QKVNORM epilogue: one per column part)
+    const bool leader = elect_one_sync() && warp == kFirstEpiWarp + 4 * ((!STAGED && p.qkv_stg) ? wq : group);
     VB_EP_DECL;
     const int rx = row % p.bw;
     const int r2 = row / p.bw;
@@ -877,6 +903,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     };
 
     if (!STAGED) {
+      uint32_t qkv_g = 0;               // staged QKVNORM: groups this warp has processed (staging slot = parity)
       for (int q = q0; q < p.total_q; q += qstride, ++it) {
         const int buf = it & 1;
         const uint32_t bphase = static_cast<uint32_t>(it >> 1) & 1u;
@@ -889,7 +916,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(&tmem_full[buf], bphase);
         if (leader && it == 0) VB_TS(4);
         tc_fence_after();
-        if (p.epi_mode == VB_EPI_QKVNORM) {
+        if (p.epi_mode == VB_EPI_QKVNORM && p.qkv_stg) {
+          // Each column part (the four warps `half` of the four lane quadrants) works through its own groups with its own
+          // two staging slots, named barrier and store-issuing thread; groups rotate over the parts as below.
+          const int first = (half + it) % PARTS;
+          uint8_t* stg = smem + p.stg_off + half * 2 * kChunkBytes;
+          for (int c = first * 64; c < p.block_n; c += 64 * PARTS) {
+            uint8_t* slot = stg + (qkv_g & 1u) * kChunkBytes;
+            epi_group_qkv_stage(p, taddr + c, t.col0 + c, slot + row * 128, row);
+            fence_proxy_async();
+            // the store issued two groups ago read THIS group's next slot; it must be done before anybody passes the barrier
+            if (leader) bulk_wait_read<0>();
+            named_bar_sync(kEpiBarrier + half, 128);
+            if (leader) {
+              const int gg = (t.col0 + c) >> 6;
+              const int part = gg % p.parts, head = gg / p.parts;
+              const int seq = part == 0 ? p.part_seq[0] : (part == 1 ? p.part_seq[1] : p.part_seq[2]);
+              const int off = part == 0 ? p.part_off[0] : (part == 1 ? p.part_off[1] : p.part_off[2]);
+              const int hw = p.H * p.W;
+              for (int j = 0; j < p.bn; ++j) {                  // one box per image of the tile (bn = 2 at 8x8)
+                const int nj = t.n0 + j;
+                if (nj >= p.B) break;
+                const int b = nj / p.seg_div, seg = nj - b * p.seg_div;
+                const int tok = (b * p.heads + head) * seq + off + seg * hw + (p.bn == 1 ? t.y0 * p.W + t.x0 : 0);
+                tma_store_2d(&map_out.m[part], slot + j * p.qkv_rows * 128, 0, tok);
+              }
+              bulk_commit();
+            }
+            ++qkv_g;
+          }
+        } else if (p.epi_mode == VB_EPI_QKVNORM) {
           // the column groups of a tile are dealt to the PARTS warps of a lane quadrant starting with a different warp on
           // every tile: with an odd number of groups (block_n = 192, D = 64) the extra one alternates instead of always
           // landing on the same warp (2 : 1 became 3 : 3 over two tiles)
@@ -906,6 +962,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         __syncwarp();
         if (lane == 0) acc_release(buf);
       }
+      if (p.qkv_stg && leader) bulk_wait_read<0>();      // staging smem must outlive the last TMA store's read
     } else {
       const int res_mode = RES_T >= 0 ? RES_T : p.res_mode;
       const bool modsilu = MOD_T >= 0 ? MOD_T != 0 : (p.flags & VB_F_MODSILU) != 0;
@@ -1676,7 +1733,15 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
                  "vb_conv: part_ld must be 0, head_dim, or 64 with head_dim 32");
     p.part_ld = d->part_ld > 0 ? d->part_ld : d->head_dim;
     if (forced_pair == 1 && pair_possible) set_pair(1);
-    VB_REQUIRE_L(plan_mainloop(p, kSmemMax, false), "vb_conv: shared memory budget exceeded");
+    static const bool qkv_stg_off = getenv("VB_QKV_STAGED") != nullptr && atoi(getenv("VB_QKV_STAGED")) == 0;     // A/B testing
+    const int qkv_stage_bytes = 2 * 2 * kChunkBytes;         // two column parts x two slots
+    if (!qkv_stg_off && d->head_dim == 64 && p.part_ld == 64 && d->H * d->W >= 64 && d->block_n % 64 == 0 &&
+        plan_mainloop(p, kSmemMax - qkv_stage_bytes, true)) {
+      p.qkv_stg = 1;
+      p.qkv_rows = std::min(kBlockM, d->H * d->W);
+    } else {
+      VB_REQUIRE_L(plan_mainloop(p, kSmemMax, false), "vb_conv: shared memory budget exceeded");
+    }
   }
   if (want_rowroll) {
     VB_REQUIRE_L(d->taps == 9 && p.bh == 1 && p.bw == kBlockM && d->cin_pad == 64 && d->cin2_pad == 0 && d->block_n == 64 &&
@@ -1698,6 +1763,7 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
   p.res_off = main_bytes;
   const int eg_mul2 = p.eg ? 2 : 1;
   p.stg_off = p.res_off + eg_mul2 * (p.res_mode != VB_RES_NONE ? p.res_slots * kChunkBytes : 0);
+  const int qkv_stg_bytes = p.qkv_stg ? 2 * 2 * kChunkBytes : 0;
 
   // tune bit 6: sixteen epilogue warps (the specialised staged variants only; the row-rolling layout keeps eight)
   const int want_parts = p.eg ? 1 : 2;
@@ -1730,6 +1796,17 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
     rc = encode_act_map(&l->map_out.m[s], d->out[s], d->cout_pad, d->W, d->H, d->B, p.bw, p.bh, p.bn);
     if (rc != VB_OK) return fail(rc);
   }
+  if (p.qkv_stg) {
+    // destinations [B/seg_div][heads][seq][64]: 2-D {64, rows} maps, one {64, min(128, H*W)} box per image part of a tile
+    for (int j = 0; j < p.parts; ++j) {
+      const uint64_t rows = static_cast<uint64_t>(d->B / d->seg_div) * p.heads * d->part_seq[j];
+      const uint64_t dims[2] = {64, rows};
+      const uint64_t strides[1] = {128};
+      const uint32_t box[2] = {64, static_cast<uint32_t>(p.qkv_rows)};
+      rc = encode_tmap_16(&l->map_out.m[j], d->part_out[j], 2, dims, strides, box);
+      if (rc != VB_OK) return fail(rc);
+    }
+  }
   {
     const uint64_t ktot = static_cast<uint64_t>(d->taps) * (d->cin_pad + d->cin2_pad);
     const uint64_t dims[2] = {ktot, static_cast<uint64_t>(d->cout_pad)};
@@ -1754,7 +1831,7 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
       return fail(VB_ERR_INVALID);
     }
   }
-  l->smem_bytes = p.stg_off + eg_mul2 * (staged ? p.stg_regions * p.gslots * kChunkBytes : 0) + 1024;
+  l->smem_bytes = p.stg_off + eg_mul2 * (staged ? p.stg_regions * p.gslots * kChunkBytes : 0) + qkv_stg_bytes + 1024;
   l->flops = 2.0 * d->B * d->H * d->W * static_cast<double>(d->cout_pad) * d->taps * (d->cin_pad + d->cin2_pad);
   const unsigned long long dev_bit = 1ull << current_device();
   if (!(var->attr_done & dev_bit)) {
