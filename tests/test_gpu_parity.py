@@ -218,7 +218,11 @@ def test_conv_two_source_and_narrow_output(env):
 @pytest.mark.parametrize("tune", [0, 2, 128, 130])
 @pytest.mark.parametrize("B,R,ch,heads,D,parts,seg_div,bn", [(2, 16, 128, 2, 64, 3, 1, 128), (2, 8, 256, 4, 64, 2, 1, 128),
                                                            (4, 8, 256, 4, 64, 2, 2, 64), (2, 32, 256, 8, 32, 3, 1, 64),
-                                                           (40, 16, 384, 6, 64, 3, 1, 192), (12, 8, 512, 8, 64, 2, 1, 128)])
+                                                           (40, 16, 384, 6, 64, 3, 1, 192), (12, 8, 512, 8, 64, 2, 1, 128),
+                                                           # odd batch at 8x8 (two images per tile: the last tile is half empty),
+                                                           # 4x4 (below the staged-store path's 64 rows per image), 64x64
+                                                           (3, 8, 256, 4, 64, 3, 1, 128), (5, 4, 128, 2, 64, 3, 1, 64),
+                                                           (1, 64, 128, 2, 64, 3, 1, 128)])
 def test_qkv_epilogue(env, B, R, ch, heads, D, parts, seg_div, bn, tune):
     """1x1 GEMM + per-(token, head, q|k|v) normalise + scatter (models.py:192-193, 283-297)."""
     L, lib, dev = env

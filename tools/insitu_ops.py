@@ -45,7 +45,7 @@ for i, name in enumerate(("vivid-base", "vivid-uncond", "vivid-sr")):
             for ev in prof.events():
                 dur = getattr(ev, "device_time_total", 0)
                 tr = getattr(ev, "time_range", None)
-                if dur and tr is not None and "_kernel" in ev.name:
+                if tr is not None and "_kernel" in ev.name:
                     evs.append((tr.start, dur / 1e3, ev.name))
             evs.sort()
             if len(evs) != per_call:            # a dropped activity record: this replay cannot be attributed
