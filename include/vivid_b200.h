@@ -380,6 +380,33 @@ int vb_plan_launch_graph_range(vb_plan* p, int first, int last, void* stream);
 /* Algorithmic work of one plan run: kind 0 = GEMM+attention FLOPs, 1 = kernel launches. */
 double vb_plan_query(const vb_plan* p, int kind);
 
+/* ------------------------------------------------------------------------
+ * Whole-call entry point: one NVPrecond.forward — reference training/models.py:589-689 (current tree),
+ * experiments/code/training/models.py:547-638 (snapshot) — on a recorded plan, with plain device pointers.
+ * The host that BUILT the plan (vivid_b200/engine.py walks the module tree) registers the plan's persistent input /
+ * output buffers once; any host can then run denoiser calls without knowing the op sequence.
+ * ------------------------------------------------------------------------ */
+typedef struct vb_io_desc {
+  float* in_x;     /* [n_x, 3, R, R] noisy images (dual-source: 2B interleaved)                     required */
+  float* in_src;   /* [n_x, 3, R, R] source views; NULL for nets without source-view encoder                 */
+  float* in_sigma; /* [n_x] noise levels                                                            required */
+  float* in_geom;  /* [n_x, geom_dim] pose vectors (zeros when the call passes none)                required */
+  float* in_cond;  /* [B, 3, R, R] SR conditioning image; NULL unless super_res                              */
+  float* in_noise; /* [B, 3, R, R] SR conditioning noise (the kernel forms cond + noisy_sr * noise)          */
+  float* out_d;    /* [B, 3, R, R] D_x                                                              required */
+  int64_t n_x, n_out, img_elems /* 3*R*R */, geom_dim;
+  int64_t workspace_bytes; /* device bytes the plan holds (weights, activations, I/O): reported by vb_workspace_bytes */
+} vb_io_desc;
+int vb_plan_bind_io(vb_plan* p, const vb_io_desc* io);
+/* D_out = D(x; sigma | src, geometry[, cond]) for the plan's batch.  All pointers are DEVICE pointers to contiguous fp32;
+ * sigma_n is 1 (broadcast) or n_x; geometry may be NULL (zeros) and geometry_rows is 1 (broadcast) or n_x; src is ignored by
+ * nets without encoder; cond and noise are required for super_res plans (noise: N(0,1) drawn by the caller, the reference
+ * draws it with torch.randn_like on every call, experiments/code/training/models.py:608-611).  Copies the inputs into the
+ * plan's buffers, replays the plan as one CUDA graph and copies D_x out, all on `stream`, no host synchronisation. */
+int vb_denoise(vb_plan* p, const float* src, const float* x, const float* sigma, int32_t sigma_n, const float* geometry,
+               int32_t geometry_rows, const float* cond, const float* noise, float* D_out, void* stream);
+int64_t vb_workspace_bytes(const vb_plan* p);
+
 #ifdef __cplusplus
 }
 #endif

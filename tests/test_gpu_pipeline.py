@@ -345,3 +345,48 @@ def test_against_unmodified_reference_on_gpu(env):
     dec = vivid_b200.StandardRGBEncoder().decode
     enc = ns.encoders.StandardRGBEncoder()
     assert psnr_u8(dec(got), enc.decode(want)) >= 40.0 and rel(got, want) <= 1e-2
+
+
+# ------------------------------------------------------------------------------- whole-call C entry point
+@pytest.mark.parametrize("name,B", [("vivid-base", 3), ("vivid-uncond", 2), ("vivid-sr", 1), ("vivid-base-dual", 2)])
+def test_vb_denoise_whole_call_entry_point(env, name, B):
+    """vb_denoise (include/vivid_b200.h) runs one NVPrecond.forward on a recorded plan from plain device
+    pointers: bit-identical to the Python surface's forward on the same inputs, incl. sigma / pose broadcast, a missing
+    pose vector, and the SR conditioning noise drawn by the caller (reference: torch.randn_like per call, :608-611)."""
+    import ctypes as C
+    L, lib, dev = env
+    net, _ = make_pair(name, 5, dev)
+    dual = "dual" in name
+    R = net.img_resolution
+    src, tgt, geom = synth(list(range(B)), R, dev, dual=dual)
+    n_x = src.shape[0]
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = (tgt + 2.0 * torch.randn(tgt.shape, generator=g).to(dev)).contiguous()
+    sigma = torch.full((n_x,), 2.0, device=dev)
+    cond = torch.randn(B, 3, R, R, generator=g).to(dev) if net.super_res else None
+    torch.manual_seed(11)
+    ref = net(src, x, sigma, geom, cond).clone()
+    plan = net.plan(B, dev)
+    assert lib.vb_workspace_bytes(plan.handle) == plan.owned_bytes > 0
+    torch.manual_seed(11)
+    noise = torch.randn_like(cond) if cond is not None else None       # the draw forward() makes internally
+    out = torch.full_like(ref, float("nan"))
+    st = torch.cuda.current_stream().cuda_stream
+
+    def call(sig, sig_n, geo, geo_rows):
+        L.check(lib.vb_denoise(plan.handle, src.data_ptr(), x.data_ptr(), sig.data_ptr(), sig_n, L.ptr(geo), geo_rows, L.ptr(cond),
+                               L.ptr(noise), out.data_ptr(), st), "vb_denoise")
+        torch.cuda.synchronize()
+        return out.clone()
+
+    gfull = geom.to(torch.float32).reshape(n_x, -1).contiguous()
+    assert torch.equal(call(sigma, n_x, gfull, n_x), ref)
+    assert torch.equal(call(sigma[:1].contiguous(), 1, gfull, n_x), ref)              # sigma broadcast
+    if not dual:                                                                      # no pose vector == zeros (vanilla trees)
+        torch.manual_seed(11)
+        ref0 = net(src, x, sigma, None, cond).clone()
+        assert torch.equal(call(sigma, n_x, None, 0), ref0)
+    # argument errors come back as codes, never exceptions from the library
+    assert lib.vb_denoise(plan.handle, src.data_ptr(), x.data_ptr(), sigma.data_ptr(), n_x + 1, None, 0, L.ptr(cond), L.ptr(noise),
+                          out.data_ptr(), st) != 0
+    assert b"sigma_n" in lib.vb_last_error()

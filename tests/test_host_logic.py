@@ -263,3 +263,27 @@ def test_metrics_host_logic_and_cpu_refusal():
         vivid_b200.get_metrics(iter([]), device=torch.device("cpu"))
     with pytest.raises(NotImplementedError):
         vivid_b200.calculate_stats_for_iterable_nvs([], metrics=["fid"])
+
+
+def test_whole_call_entry_point_argument_validation(lib):
+    """vb_plan_bind_io / vb_denoise / vb_workspace_bytes reject bad arguments with an error code (no CUDA call is made)."""
+    import ctypes as C
+    from vivid_b200 import _lib as L
+    plan = C.c_void_p()
+    assert lib.vb_plan_create(C.byref(plan)) == 0
+    try:
+        assert lib.vb_workspace_bytes(plan) == 0
+        assert lib.vb_denoise(plan, None, None, None, 1, None, 0, None, None, None, None) != 0
+        assert b"bound" in lib.vb_last_error()
+        io = L.IoDesc()
+        assert lib.vb_plan_bind_io(plan, C.byref(io)) != 0 and b"required" in lib.vb_last_error()
+        io = L.IoDesc(in_x=8, in_sigma=8, in_geom=8, out_d=8, n_x=2, n_out=2, img_elems=12, geom_dim=4, in_cond=8, workspace_bytes=99)
+        assert lib.vb_plan_bind_io(plan, C.byref(io)) != 0 and b"come together" in lib.vb_last_error()
+        io.in_cond = None
+        assert lib.vb_plan_bind_io(plan, C.byref(io)) == 0
+        assert lib.vb_workspace_bytes(plan) == 99
+        assert lib.vb_denoise(plan, None, None, None, 1, None, 0, None, None, None, None) != 0
+        assert b"required" in lib.vb_last_error()
+        assert lib.vb_plan_bind_io(None, C.byref(io)) != 0
+    finally:
+        lib.vb_plan_destroy(plan)

@@ -92,6 +92,11 @@ class StatsDesc(C.Structure):
 
 
 # name -> (restype, argtypes); the smoke/CPU tests check that every one of these is exported.
+class IoDesc(C.Structure):
+    _fields_ = [("in_x", vp), ("in_src", vp), ("in_sigma", vp), ("in_geom", vp), ("in_cond", vp), ("in_noise", vp), ("out_d", vp),
+                ("n_x", i64), ("n_out", i64), ("img_elems", i64), ("geom_dim", i64), ("workspace_bytes", i64)]
+
+
 SIGNATURES = {
     "vb_last_error": (C.c_char_p, []),
     "vb_abi_version": (C.c_int, []),
@@ -133,9 +138,12 @@ SIGNATURES = {
     "vb_plan_launch_graph": (C.c_int, [vp, vp]),
     "vb_plan_launch_graph_range": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "vb_plan_query": (C.c_double, [vp, C.c_int]),
+    "vb_plan_bind_io": (C.c_int, [vp, C.POINTER(IoDesc)]),
+    "vb_denoise": (C.c_int, [vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, vp]),
+    "vb_workspace_bytes": (C.c_int64, [vp]),
 }
 
-STRUCTS = [WeightPrepDesc, ConvDesc, AttnDesc, EwDesc, EmbDesc, PrecondInDesc, PrecondOutDesc, HeunDesc, StatsDesc, F32ConvDesc, F32OpDesc]
+STRUCTS = [WeightPrepDesc, ConvDesc, AttnDesc, EwDesc, EmbDesc, PrecondInDesc, PrecondOutDesc, HeunDesc, StatsDesc, F32ConvDesc, F32OpDesc, IoDesc]
 
 _lib = None
 

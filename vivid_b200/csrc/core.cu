@@ -160,6 +160,7 @@ extern "C" int vb_struct_size(int which) {
     case 8: return static_cast<int>(sizeof(vb_stats_desc));
     case 9: return static_cast<int>(sizeof(vb_f32_conv_desc));
     case 10: return static_cast<int>(sizeof(vb_f32_op_desc));
+    case 11: return static_cast<int>(sizeof(vb_io_desc));
     default: return -1;
   }
 }

@@ -38,6 +38,8 @@ struct vb_plan {
     cudaGraphExec_t exec;
   };
   std::vector<Range> graphs;
+  vb_io_desc io;
+  bool io_bound = false;
 };
 
 // chained: op i-1 of the same plan was launched into the stream right before (see vb::conv_launch)
@@ -183,4 +185,55 @@ extern "C" int vb_plan_launch_graph(vb_plan* p, void* stream) { return vb_plan_l
 extern "C" double vb_plan_query(const vb_plan* p, int kind) {
   if (p == nullptr) return 0.0;
   return kind == 0 ? p->flops : static_cast<double>(p->launches);
+}
+
+// ------------------------------------------------------------------------------------------------ whole-call entry point
+namespace {
+// dst[r][c] = src[(src_rows == 1 ? 0 : r)][c]   (row broadcast of sigma / the pose vector), or zeros when src == nullptr
+__global__ void bcast_rows_kernel(float* dst, const float* src, long long rows, long long dim, int src_rows) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * dim) return;
+  dst[i] = src == nullptr ? 0.f : src[src_rows == 1 ? i % dim : i];
+}
+}  // namespace
+
+extern "C" int vb_plan_bind_io(vb_plan* p, const vb_io_desc* io) {
+  VB_REQUIRE(p != nullptr && io != nullptr, "vb_plan_bind_io: null argument");
+  VB_REQUIRE(io->in_x && io->in_sigma && io->in_geom && io->out_d, "vb_plan_bind_io: in_x, in_sigma, in_geom and out_d are required");
+  VB_REQUIRE(io->n_x > 0 && io->n_out > 0 && io->img_elems > 0 && io->geom_dim > 0, "vb_plan_bind_io: bad extents");
+  VB_REQUIRE((io->in_cond == nullptr) == (io->in_noise == nullptr), "vb_plan_bind_io: in_cond and in_noise come together");
+  p->io = *io;
+  p->io_bound = true;
+  return VB_OK;
+}
+
+extern "C" int64_t vb_workspace_bytes(const vb_plan* p) { return (p != nullptr && p->io_bound) ? p->io.workspace_bytes : 0; }
+
+extern "C" int vb_denoise(vb_plan* p, const float* src, const float* x, const float* sigma, int32_t sigma_n,
+                          const float* geometry, int32_t geometry_rows, const float* cond, const float* noise, float* D_out,
+                          void* stream) {
+  VB_REQUIRE(p != nullptr && p->io_bound, "vb_denoise: the plan has no bound I/O buffers (vb_plan_bind_io)");
+  VB_REQUIRE(x != nullptr && sigma != nullptr && D_out != nullptr, "vb_denoise: x, sigma and D_out are required");
+  const vb_io_desc& io = p->io;
+  VB_REQUIRE(sigma_n == 1 || sigma_n == io.n_x, "vb_denoise: sigma_n must be 1 or %lld (got %d)", static_cast<long long>(io.n_x), sigma_n);
+  VB_REQUIRE(geometry == nullptr || geometry_rows == 1 || geometry_rows == io.n_x, "vb_denoise: geometry_rows must be 1 or %lld (got %d)",
+             static_cast<long long>(io.n_x), geometry_rows);
+  VB_REQUIRE(io.in_src == nullptr || src != nullptr, "vb_denoise: this plan has a source-view encoder: src is required");
+  VB_REQUIRE(io.in_cond == nullptr || (cond != nullptr && noise != nullptr), "vb_denoise: super_res plan: cond and noise are required");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t img = static_cast<size_t>(io.img_elems) * sizeof(float);
+  VB_CHECK_CUDA(cudaMemcpyAsync(io.in_x, x, io.n_x * img, cudaMemcpyDeviceToDevice, s));
+  if (io.in_src != nullptr) VB_CHECK_CUDA(cudaMemcpyAsync(io.in_src, src, io.n_x * img, cudaMemcpyDeviceToDevice, s));
+  if (io.in_cond != nullptr) {
+    VB_CHECK_CUDA(cudaMemcpyAsync(io.in_cond, cond, io.n_out * img, cudaMemcpyDeviceToDevice, s));
+    VB_CHECK_CUDA(cudaMemcpyAsync(io.in_noise, noise, io.n_out * img, cudaMemcpyDeviceToDevice, s));
+  }
+  bcast_rows_kernel<<<static_cast<unsigned>((io.n_x + 255) / 256), 256, 0, s>>>(io.in_sigma, sigma, io.n_x, 1, sigma_n);
+  const long long ng = io.n_x * io.geom_dim;
+  bcast_rows_kernel<<<static_cast<unsigned>((ng + 255) / 256), 256, 0, s>>>(io.in_geom, geometry, io.n_x, io.geom_dim, geometry_rows);
+  VB_CHECK_CUDA(cudaGetLastError());
+  const int rc = vb_plan_launch_graph_range(p, 0, -1, stream);
+  if (rc != VB_OK) return rc;
+  VB_CHECK_CUDA(cudaMemcpyAsync(D_out, io.out_d, io.n_out * img, cudaMemcpyDeviceToDevice, s));
+  return VB_OK;
 }

@@ -69,6 +69,7 @@ class Plan:
         self.dual = net.dual
         self.Bx = 2 * B if net.dual else B
         self.keep = []                  # every buffer the plan touches (keeps them alive)
+        self.owned_bytes = 0            # device bytes allocated by this plan (prepared weights, activations, I/O)
         self.pool = {}                  # numel -> free activation buffers
         self.op_info = []               # per recorded op: (kind, label, algorithmic flops, algorithmic bytes)
         self.handle = C.c_void_p()
@@ -90,6 +91,7 @@ class Plan:
     # ------------------------------------------------------------------ buffers
     def buf(self, shape, dtype, zero=False):
         t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+        self.owned_bytes += t.numel() * t.element_size()
         self.keep.append(t)
         return t
 
@@ -561,6 +563,12 @@ class Plan:
         L.check(self.lib.vb_plan_add_precond_out(self.handle, C.byref(d)), "vb_plan_add_precond_out")
         self.op_info.append(("precond", "out", 0.0, B * R * R * (12.0 + 64.0 + 12.0)))
         self.num_ops = self.lib.vb_plan_num_ops(self.handle)
+        # whole-call C entry point (vb_denoise): any host can now run this plan with plain device pointers
+        io = L.IoDesc(in_x=self.in_x.data_ptr(), in_src=L.ptr(self.in_src), in_sigma=self.in_sigma.data_ptr(),
+                      in_geom=self.in_geom.data_ptr(), in_cond=L.ptr(self.in_cond), in_noise=L.ptr(self.in_noise),
+                      out_d=self.out_d.data_ptr(), n_x=Bx, n_out=B, img_elems=3 * R * R, geom_dim=self.in_geom.shape[1],
+                      workspace_bytes=self.owned_bytes)
+        L.check(self.lib.vb_plan_bind_io(self.handle, C.byref(io)), "vb_plan_bind_io")
         self.launches = int(self.lib.vb_plan_query(self.handle, 1))
         self.padded_flops = self.lib.vb_plan_query(self.handle, 0)
 
