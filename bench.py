@@ -214,14 +214,17 @@ def run_ours(args):
     calls = 2 * T - 1
     plans = {"vivid-base": net.plan(B, dev), "vivid-uncond": gnet.plan(B, dev), "vivid-sr": sr.plan(B, dev)}
     agg = {}
+    pk = peaks()
     for name, p in plans.items():
         for kind, label, fl, by, op_ms in p.profile(repeats=2):
-            a = agg.setdefault(kind, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+            a = agg.setdefault(kind, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0, bound_ms=0.0))
             a["ms"] += op_ms * calls
             a["flops"] += fl * calls
             a["bytes"] += by * calls
             a["launches"] += calls
-    pk = peaks()
+            # the op's own combined roofline: the slower of its FLOPs at the tensor peak and its algorithmic bytes at the HBM
+            # copy rate (an HBM-bound 1x1 conv at its byte roofline is not "far from the tensor peak")
+            a["bound_ms"] += max(fl / (pk["tflops_burst"] * 1e9), by / (pk["gbs"] * 1e6)) * calls
     conv_ms = agg["conv3"]["ms"] + agg["conv1"]["ms"]
     conv_fl = agg["conv3"]["flops"] + agg["conv1"]["flops"]
     conv_n = agg["conv3"]["launches"] + agg["conv1"]["launches"]
@@ -265,7 +268,12 @@ def run_ours(args):
         else:
             k["gbs"] = round(a["bytes"] / (a["ms"] / 1e3) / 1e9, 1)
             k["frac_of_hbm_peak"] = round(k["gbs"] / pk["gbs"], 4)
+        k["roofline_ms"] = round(a["bound_ms"], 2)
+        k["frac_of_roofline"] = round(a["bound_ms"] / a["ms"], 4)
         kernels[kind] = k
+    kernels["_note"] = ("isolated regime (each op timed alone behind a blocker): frac_of_tensor_peak / frac_of_hbm_peak against the "
+                        "sustained tensor peak / copy rate; frac_of_roofline = sum over ops of max(FLOPs / burst tensor peak, "
+                        "algorithmic bytes / copy rate) / measured time")
     alg_tflop_img = calls * (ALG_GFLOP["vivid-base"] + ALG_GFLOP["vivid-uncond"] + ALG_GFLOP["vivid-sr"]) / 1e3
     launches = calls * sum(p.launches for p in plans.values()) + 2 * calls + 1 + calls + 2     # + Heun, SR noise, resize, decode
 

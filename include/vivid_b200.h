@@ -93,12 +93,14 @@ int vb_weight_prep(const vb_weight_prep_desc* d, void* stream);
  *   flags VB_F_MODSILU : v = mp_silu(v * mod[b][c])                 (:175-176)
  *   res_mode           : v = mp_sum(res, v, res_t)                  (:184,202)
  *   flags VB_F_CLIP    : v = clamp(v, -clip, clip)                  (:204-205)
+ *   flags VB_F_RESB_FOLDED : the prepared weights already carry mp_sum's coefficient of v (t / sqrt((1-t)^2 + t^2), e.g.
+ *                        through vb_weight_prep_desc.gain): the epilogue adds the residual term only
  *   epi  VB_EPI_QKVNORM: per-(token, head, q|k|v) normalize over D and scatter
  *                        to [B][heads][seq][D] 16-bit tensors       (:192-193,283-297)
  * GEMM view: M = B*H*W pixels, N = cout, K = taps*(cin_pad+cin2_pad).
  * ------------------------------------------------------------------------ */
 enum { VB_EPI_PLAIN = 0, VB_EPI_QKVNORM = 1 };
-enum { VB_F_MODSILU = 1, VB_F_CLIP = 4 };
+enum { VB_F_MODSILU = 1, VB_F_CLIP = 4, VB_F_RESB_FOLDED = 8 };
 /* residual input: none | mp_sum(res, v) | mp_sum(pixel_norm(res), v)  (the enc-flavour block normalises its input
  * before using it as the residual base, models.py:171,184; recomputed in the epilogue instead of stored) |
  * mp_sum(res * res_rnorm[pixel], v): the same, with the per-pixel 1/(eps + rms) taken from the fp32 side channel the

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("VB_LIB_PATH") or os.path.join(_HERE, "libvividb200.so
 
 VB_F32, VB_F16, VB_BF16, VB_F64, VB_U8 = 0, 1, 2, 3, 4
 VB_EPI_PLAIN, VB_EPI_QKVNORM = 0, 1
-VB_F_MODSILU, VB_F_CLIP = 1, 4
+VB_F_MODSILU, VB_F_CLIP, VB_F_RESB_FOLDED = 1, 4, 8
 VB_RES_NONE, VB_RES_PLAIN, VB_RES_PIXNORM, VB_RES_SCALED = 0, 1, 2, 3
 VB_OUT_NONE, VB_OUT_RAW, VB_OUT_SILU, VB_OUT_NORM, VB_OUT_NORM_SILU = 0, 1, 2, 3, 4
 VB_EW_PIXNORM, VB_EW_DOWN_PIXNORM, VB_EW_UP, VB_EW_CAT, VB_EW_SILU = 0, 1, 2, 3, 4

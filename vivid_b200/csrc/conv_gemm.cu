@@ -198,6 +198,26 @@ __device__ __forceinline__ uint32_t mp_silu_pk(uint32_t x2, float scale) {
   return *reinterpret_cast<uint32_t*>(&y);
 }
 
+// ... with scale == 1 (conv_res0: the modulation has been applied in fp32 already): one packed multiply less per pair.
+__device__ __forceinline__ uint32_t mp_silu_pk1(uint32_t x2) {
+#ifdef VB_OP_BF16
+  const __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&x2);
+  __nv_bfloat162 h = __hmul2(x, __float2bfloat162_rn(0.5f));
+  uint32_t hu = *reinterpret_cast<uint32_t*>(&h), tu;
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(tu) : "r"(hu));
+  const __nv_bfloat162 c = __float2bfloat162_rn(0.5f / 0.596f);
+  __nv_bfloat162 y = __hmul2(x, __hfma2(*reinterpret_cast<__nv_bfloat162*>(&tu), c, c));
+#else
+  const __half2 x = *reinterpret_cast<__half2*>(&x2);
+  __half2 h = __hmul2(x, __float2half2_rn(0.5f));
+  uint32_t hu = *reinterpret_cast<uint32_t*>(&h), tu;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(hu));
+  const __half2 c = __float2half2_rn(0.5f / 0.596f);
+  __half2 y = __hmul2(x, __hfma2(*reinterpret_cast<__half2*>(&tu), c, c));
+#endif
+  return *reinterpret_cast<uint32_t*>(&y);
+}
+
 // Clamp of a packed fp16 pair to [-c, c] (c exactly representable in fp16).
 __device__ __forceinline__ uint32_t clamp_pk(uint32_t x2, float c) {
 #ifdef VB_OP_BF16
@@ -1193,18 +1213,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if (!EG && c + 1 < chunks) mod_fetch(c + 1, half);
               }
               if (has_res) {
+                // mp_sum(res, v, t) = res * a + v * b.  Plans fold b into the prepared weights (VB_F_RESB_FOLDED: one multiply per
+                // element less in every residual layer's epilogue); the descriptor form with plain weights keeps it here.
+                if (p.flags & VB_F_RESB_FOLDED) {
 #pragma unroll
-                for (int j = 0; j < U; ++j) {
-                  const uint4 q = *reinterpret_cast<const uint4*>(rrow + swz(part * U + j, row));
-                  const float2 a = unpack_op2(q.x), b = unpack_op2(q.y), cc = unpack_op2(q.z), d = unpack_op2(q.w);
-                  v[8 * j + 0] = fmaf(a.x, res_scale, v[8 * j + 0] * p.res_b);
-                  v[8 * j + 1] = fmaf(a.y, res_scale, v[8 * j + 1] * p.res_b);
-                  v[8 * j + 2] = fmaf(b.x, res_scale, v[8 * j + 2] * p.res_b);
-                  v[8 * j + 3] = fmaf(b.y, res_scale, v[8 * j + 3] * p.res_b);
-                  v[8 * j + 4] = fmaf(cc.x, res_scale, v[8 * j + 4] * p.res_b);
-                  v[8 * j + 5] = fmaf(cc.y, res_scale, v[8 * j + 5] * p.res_b);
-                  v[8 * j + 6] = fmaf(d.x, res_scale, v[8 * j + 6] * p.res_b);
-                  v[8 * j + 7] = fmaf(d.y, res_scale, v[8 * j + 7] * p.res_b);
+                  for (int j = 0; j < U; ++j) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(rrow + swz(part * U + j, row));
+                    const float2 a = unpack_op2(q.x), b = unpack_op2(q.y), cc = unpack_op2(q.z), d = unpack_op2(q.w);
+                    v[8 * j + 0] = fmaf(a.x, res_scale, v[8 * j + 0]);
+                    v[8 * j + 1] = fmaf(a.y, res_scale, v[8 * j + 1]);
+                    v[8 * j + 2] = fmaf(b.x, res_scale, v[8 * j + 2]);
+                    v[8 * j + 3] = fmaf(b.y, res_scale, v[8 * j + 3]);
+                    v[8 * j + 4] = fmaf(cc.x, res_scale, v[8 * j + 4]);
+                    v[8 * j + 5] = fmaf(cc.y, res_scale, v[8 * j + 5]);
+                    v[8 * j + 6] = fmaf(d.x, res_scale, v[8 * j + 6]);
+                    v[8 * j + 7] = fmaf(d.y, res_scale, v[8 * j + 7]);
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < U; ++j) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(rrow + swz(part * U + j, row));
+                    const float2 a = unpack_op2(q.x), b = unpack_op2(q.y), cc = unpack_op2(q.z), d = unpack_op2(q.w);
+                    v[8 * j + 0] = fmaf(a.x, res_scale, v[8 * j + 0] * p.res_b);
+                    v[8 * j + 1] = fmaf(a.y, res_scale, v[8 * j + 1] * p.res_b);
+                    v[8 * j + 2] = fmaf(b.x, res_scale, v[8 * j + 2] * p.res_b);
+                    v[8 * j + 3] = fmaf(b.y, res_scale, v[8 * j + 3] * p.res_b);
+                    v[8 * j + 4] = fmaf(cc.x, res_scale, v[8 * j + 4] * p.res_b);
+                    v[8 * j + 5] = fmaf(cc.y, res_scale, v[8 * j + 5] * p.res_b);
+                    v[8 * j + 6] = fmaf(d.x, res_scale, v[8 * j + 6] * p.res_b);
+                    v[8 * j + 7] = fmaf(d.y, res_scale, v[8 * j + 7] * p.res_b);
+                  }
                 }
               }
 #ifdef VB_OP_BF16
@@ -1241,7 +1279,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               }
               if (mod_pk) {
 #pragma unroll
-                for (int j = 0; j < CW / 2; ++j) r16h[hh][j] = mp_silu_pk(r16h[hh][j], 1.0f);
+                for (int j = 0; j < CW / 2; ++j) r16h[hh][j] = mp_silu_pk1(r16h[hh][j]);
               }
               if (needs_norm) {
 #pragma unroll

@@ -52,6 +52,7 @@ class Act:
 _DT = {torch.float32: L.VB_F32, torch.float16: L.VB_F16, torch.bfloat16: L.VB_BF16}
 AUTOTUNE = os.environ.get("VB_AUTOTUNE", "1") != "0"    # plan-time layout tuning of the conv layers (see Plan._tune_conv)
 _TUNE_CACHE = {}
+FOLD_RES = os.environ.get("VB_FOLD_RES", "1") != "0"    # mp_sum's coefficient of the GEMM result folded into the prepared weights
 FULLROW_MAX = 256          # widest channel count one GEMM tile (and TMEM accumulator buffer) can hold
 
 
@@ -195,7 +196,7 @@ class Plan:
 
     def conv(self, x, w, B, R, cin_pad, cout, taps, *, x2=None, cin2_pad=0, cout_pad=None, flags=0, mod=None,
              mod_stride=0, res=None, res_mode=L.VB_RES_NONE, res_t=0.3, clip=None, outs=(), out_f32=None, qkv=None,
-             k_real=None, out_rnorm=None, res_rnorm=None):
+             k_real=None, out_rnorm=None, res_rnorm=None, res_folded=False):
         """outs: sequence of (tensor, kind, scale)."""
         cout_pad = cout_pad or _pad(cout, 16)
         fullrow = res_mode == L.VB_RES_PIXNORM or any(k >= L.VB_OUT_NORM for _, k, _ in outs)
@@ -205,6 +206,9 @@ class Plan:
         assert bn is not None and (not fullrow or bn <= FULLROW_MAX), (cout_pad, bn)
         if clip is not None:
             flags |= L.VB_F_CLIP
+        if res_folded:
+            assert res is not None
+            flags |= L.VB_F_RESB_FOLDED
         d = L.ConvDesc(x=x.data_ptr(), x2=L.ptr(x2), w=w.data_ptr(), mod=mod if isinstance(mod, int) else L.ptr(mod),
                        res=L.ptr(res), out_f32=L.ptr(out_f32), out_rnorm=L.ptr(out_rnorm), res_rnorm=L.ptr(res_rnorm), B=B,
                        H=R, W=R, cin_pad=cin_pad, cin2_pad=cin2_pad,
@@ -307,6 +311,11 @@ class Plan:
         return mod, offs, total
 
     # ------------------------------------------------------------------ one UNet / encoder
+    @staticmethod
+    def sum_coeff(t):
+        """mp_sum's coefficient of its second operand (training/models.py:71-72)."""
+        return float(t) / math.sqrt((1.0 - float(t)) ** 2 + float(t) ** 2)
+
     @staticmethod
     def cat_weights(na, nb, t):
         """mp_cat scale factors (training/models.py:78-84)."""
@@ -446,17 +455,19 @@ class Plan:
             mo = offs[(s.group, s.name)]
             self.conv(a0, w0, B, R, k0, Cc, 9, x2=x2, cin2_pad=k2, flags=L.VB_F_MODSILU, mod=mod.data_ptr() + 4 * mo,
                       mod_stride=mod_total, outs=[(y0, L.VB_OUT_RAW, 1.0)])
-            w1 = self.prep_weight(mod_.conv_res1.weight)
+            # mp_sum(x, y, t) = (x (1-t) + y t) / sqrt((1-t)^2 + t^2): y's coefficient rides on the prepared weights of the GEMM that
+            # produces y (one fp32 multiply per output element less in the epilogue of every residual layer)
+            w1 = self.prep_weight(mod_.conv_res1.weight, gain=self.sum_coeff(mod_.res_balance) if FOLD_RES else 1.0)
             clip = mod_.clip_act
             if s.heads == 0:
                 outs = alloc_outs(out, want(i))
                 self.conv(y0, w1, B, R, Cc, Cc, 9, res=res, res_mode=res_mode, res_rnorm=res_rnorm, res_t=mod_.res_balance,
-                          clip=clip, outs=outs, out_rnorm=out.rnorm)
+                          clip=clip, outs=outs, out_rnorm=out.rnorm, res_folded=FOLD_RES)
             else:
                 xr = self.a16(B, R, Cc)
                 temps.append(xr)
                 self.conv(y0, w1, B, R, Cc, Cc, 9, res=res, res_mode=res_mode, res_rnorm=res_rnorm, res_t=mod_.res_balance,
-                          outs=[(xr, L.VB_OUT_RAW, 1.0)])
+                          outs=[(xr, L.VB_OUT_RAW, 1.0)], res_folded=FOLD_RES)
                 S, D, h = R * R, s.head_dim, s.heads
                 nseg = feat_seg if s.xattn else 0
                 real_seg = 0 if zero_feature_keys else nseg
@@ -485,10 +496,10 @@ class Plan:
                 temps += [y] if ld else [q, k, v, y]           # (padded q/k/v are private: never recycled through the pool)
                 # unconditional model: x_attn_kv(0) == 0 -> the S*nseg zero keys are accounted for analytically
                 self.attention(q, k, v, y, B, h, S, sk, D, S * nseg if zero_feature_keys else 0, ld=ld)
-                wp = self.prep_weight(mod_.attn_proj.weight)
+                wp = self.prep_weight(mod_.attn_proj.weight, gain=self.sum_coeff(mod_.attn_balance) if FOLD_RES else 1.0)
                 outs = alloc_outs(out, want(i))
                 self.conv(y, wp, B, R, Cc, Cc, 1, res=xr, res_mode=L.VB_RES_PLAIN, res_t=mod_.attn_balance, clip=clip,
-                          outs=outs, out_rnorm=out.rnorm)
+                          outs=outs, out_rnorm=out.rnorm, res_folded=FOLD_RES)
             if out.is_feature:
                 feats_out.append(out)
             if s.group == "enc":
