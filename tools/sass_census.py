@@ -35,7 +35,7 @@ for fn, c in per.items():
     a[1].update(c)
 print(f"# cuobjdump -sass {os.path.relpath(LIB, ROOT)} ({os.path.getsize(LIB)} bytes): instruction census per kernel family")
 print(f"# UTCHMMA = tcgen05.mma, UTCBAR = tcgen05.commit, UTMALDG/UTMASTG = TMA tensor load/store, LDTM/STTM = tcgen05.ld/st,")
-print(f"# HMMA = legacy mma.sync (none in any kernel a production plan launches since round 2 — see DESIGN.md §4.1b)")
+print(f"# HMMA = legacy mma.sync (attn_kernel only: the 8x8 attention level, 9 us per launch — DESIGN.md §4)")
 print(f"{'kernel family':28s} {'variants':>8s} {'instr':>8s} " + " ".join(f"{m:>8s}" for m in MN))
 tot = collections.Counter()
 for key, (n, c) in fam.items():
