@@ -180,20 +180,22 @@ __device__ __forceinline__ uint32_t pack_op2_nosat(float lo, float hi) {
 // three packed multiplies per TWO elements (the fp32 form costs five instructions and one MUFU op per element; the
 // epilogue of the narrow SR layers is issue-bound).  Same error class as tanh.approx.f32 followed by 16-bit rounding.
 __device__ __forceinline__ uint32_t mp_silu_pk(uint32_t x2, float scale) {
+  // y = (x c)(1 + tanh(x/2)) with x = scale * x2: both scalings ride on constants — h = x2 (scale/2), xc = x2 (scale c),
+  // y = fma(xc, tanh(h), xc): three packed operations and the tanh per pair
 #ifdef VB_OP_BF16
-  __nv_bfloat162 x = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&x2), __float2bfloat162_rn(scale));
-  __nv_bfloat162 h = __hmul2(x, __float2bfloat162_rn(0.5f));
+  const __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&x2);
+  __nv_bfloat162 h = __hmul2(x, __float2bfloat162_rn(0.5f * scale));
+  const __nv_bfloat162 xc = __hmul2(x, __float2bfloat162_rn(scale * (0.5f / 0.596f)));
   uint32_t hu = *reinterpret_cast<uint32_t*>(&h), tu;
   asm("tanh.approx.bf16x2 %0, %1;" : "=r"(tu) : "r"(hu));
-  const __nv_bfloat162 c = __float2bfloat162_rn(0.5f / 0.596f);
-  __nv_bfloat162 y = __hmul2(x, __hfma2(*reinterpret_cast<__nv_bfloat162*>(&tu), c, c));
+  __nv_bfloat162 y = __hfma2(xc, *reinterpret_cast<__nv_bfloat162*>(&tu), xc);
 #else
-  __half2 x = __hmul2(*reinterpret_cast<__half2*>(&x2), __float2half2_rn(scale));
-  __half2 h = __hmul2(x, __float2half2_rn(0.5f));
+  const __half2 x = *reinterpret_cast<__half2*>(&x2);
+  __half2 h = __hmul2(x, __float2half2_rn(0.5f * scale));
+  const __half2 xc = __hmul2(x, __float2half2_rn(scale * (0.5f / 0.596f)));
   uint32_t hu = *reinterpret_cast<uint32_t*>(&h), tu;
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(hu));
-  const __half2 c = __float2half2_rn(0.5f / 0.596f);
-  __half2 y = __hmul2(x, __hfma2(*reinterpret_cast<__half2*>(&tu), c, c));
+  __half2 y = __hfma2(xc, *reinterpret_cast<__half2*>(&tu), xc);
 #endif
   return *reinterpret_cast<uint32_t*>(&y);
 }
@@ -256,9 +258,10 @@ __device__ __forceinline__ void epi_group_qkv(const ConvKernelParams& p, uint32_
   if (D == 64) tmem_ld32(taddr + 32, v + 32);
   tmem_ld_wait();
   if (!valid) return;
-  float ss = 0.f;
+  float s0 = 0.f, s1 = 0.f;             // (even / odd partial sums: the same order as the staged form below)
 #pragma unroll
-  for (int j = 0; j < D; ++j) ss += v[j] * v[j];
+  for (int j = 0; j < D; j += 2) fma2(s0, s1, v[j], v[j + 1], v[j], v[j + 1]);
+  const float ss = s0 + s1;
   const int gg = gcol / D;
   const int part = gg % p.parts;
   const float inv = (part == 0 ? p.part_scale[0] : (part == 1 ? p.part_scale[1] : p.part_scale[2])) /
@@ -286,17 +289,20 @@ __device__ __forceinline__ void epi_group_qkv_stage(const ConvKernelParams& p, u
   tmem_ld32(taddr, v);
   tmem_ld32(taddr + 32, v + 32);
   tmem_ld_wait();
-  float ss = 0.f;
+  float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 64; ++j) ss += v[j] * v[j];
+  for (int j = 0; j < 64; j += 2) fma2(s0, s1, v[j], v[j + 1], v[j], v[j + 1]);
+  const float ss = s0 + s1;
   const int part = (gcol >> 6) % p.parts;
   const float inv = (part == 0 ? p.part_scale[0] : (part == 1 ? p.part_scale[1] : p.part_scale[2])) /
                     (1e-4f + sqrtf(ss) * p.norm_scale);
 #pragma unroll
+  for (int j = 0; j < 64; j += 2) mul2(v[j], v[j + 1], inv, inv);
+#pragma unroll
   for (int j = 0; j < 8; ++j)
     *reinterpret_cast<uint4*>(srow + swz(j, row)) =
-        make_uint4(pack_op2(v[8 * j] * inv, v[8 * j + 1] * inv), pack_op2(v[8 * j + 2] * inv, v[8 * j + 3] * inv),
-                   pack_op2(v[8 * j + 4] * inv, v[8 * j + 5] * inv), pack_op2(v[8 * j + 6] * inv, v[8 * j + 7] * inv));
+        make_uint4(pack_op2(v[8 * j], v[8 * j + 1]), pack_op2(v[8 * j + 2], v[8 * j + 3]),
+                   pack_op2(v[8 * j + 4], v[8 * j + 5]), pack_op2(v[8 * j + 6], v[8 * j + 7]));
 }
 
 // fp32 direct-store epilogue for narrow outputs (out_conv: 16 padded columns).
@@ -985,6 +991,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (p.qkv_stg && leader) bulk_wait_read<0>();      // staging smem must outlive the last TMA store's read
     } else {
       const int res_mode = RES_T >= 0 ? RES_T : p.res_mode;
+      const bool rowroll = !EG && p.rowroll != 0;          // (the ping-pong variants never run the row-rolling layout: compile-time false)
       const bool modsilu = MOD_T >= 0 ? MOD_T != 0 : (p.flags & VB_F_MODSILU) != 0;
       const int k0 = K0_T >= 0 ? K0_T : p.out_kind[0];
       const int k1 = K1_T >= 0 ? K1_T : p.out_kind[1];
@@ -1017,10 +1024,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (has_res && leader) {
           while (res_issued < res_q + static_cast<uint32_t>(p.res_slots)) {
             if (!rt_have) {
-              const int wl = p.rowroll ? static_cast<int>(rt_tile >> p.strip_shift) : static_cast<int>(rt_tile);
+              const int wl = rowroll ? static_cast<int>(rt_tile >> p.strip_shift) : static_cast<int>(rt_tile);
               const int ql = q0 + wl * qstride;
               if (ql >= p.total_q) break;
-              rt_t = p.rowroll ? strip_tile(p, ql, static_cast<int>(rt_tile) & (p.strip_rows - 1))
+              rt_t = rowroll ? strip_tile(p, ql, static_cast<int>(rt_tile) & (p.strip_rows - 1))
                                : decode_tile(p, tile_of(p, ql, rank));
               rt_have = true;
             }
@@ -1083,8 +1090,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tmem_st32_fill(taddr_slot, 0u);
         tmem_st_wait();
       };
-      const int nblk = p.rowroll ? p.strip_rows + 2 : 1;            // accumulator blocks per work item
-      if (p.rowroll) {                                              // all eight slots start cleared and free
+      const int nblk = rowroll ? p.strip_rows + 2 : 1;            // accumulator blocks per work item
+      if (rowroll) {                                              // all eight slots start cleared and free
         for (int sl = 0; sl < 8; ++sl) {
           slot_clear(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(sl * 64 + half * CW));
           tc_fence_before();
@@ -1093,20 +1100,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       }
       for (;; ++it) {
-        const int wi = p.rowroll ? it / nblk : it;                  // CTA-local work item (tile, or strip of rows)
-        const int jb = p.rowroll ? it - wi * nblk : 0;              // block within the strip: 0,1 carry no output row
+        const int wi = rowroll ? it / nblk : it;                  // CTA-local work item (tile, or strip of rows)
+        const int jb = rowroll ? it - wi * nblk : 0;              // block within the strip: 0,1 carry no output row
         const int q = q0 + wi * qstride;
         if (q >= p.total_q) break;
         if (EG && (it & 1) != group) continue;
-        const int buf = p.rowroll ? (it & 7) : (it & 1);
-        const uint32_t bphase = static_cast<uint32_t>(p.rowroll ? it >> 3 : it >> 1) & 1u;
-        const TileCoord t = p.rowroll ? strip_tile(p, q, jb - 2) : decode_tile(p, tile_of(p, q, rank));
+        const int buf = rowroll ? (it & 7) : (it & 1);
+        const uint32_t bphase = static_cast<uint32_t>(rowroll ? it >> 3 : it >> 1) & 1u;
+        const TileCoord t = rowroll ? strip_tile(p, q, jb - 2) : decode_tile(p, tile_of(p, q, rank));
         const int n = t.n0 + rn;
         const bool valid = n < p.B;
         const size_t pix = static_cast<size_t>(n) * p.H * p.W + (t.y0 + ry) * p.W + t.x0 + rx;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                               static_cast<uint32_t>((p.rowroll ? buf * 64 : buf * kAccStride) + half * CW);
-        if (p.rowroll && jb < 2) {                                  // partial sums of rows outside the strip: discard
+                               static_cast<uint32_t>((rowroll ? buf * 64 : buf * kAccStride) + half * CW);
+        if (rowroll && jb < 2) {                                  // partial sums of rows outside the strip: discard
           mbar_wait(&tmem_full[buf], bphase);
           tc_fence_after();
           slot_clear(taddr);
@@ -1120,7 +1127,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (p.dbg & 1) {
           mbar_wait(&tmem_full[buf], bphase);
           tc_fence_after();
-          if (p.rowroll) slot_clear(taddr);
+          if (rowroll) slot_clear(taddr);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) acc_release(buf);
@@ -1186,7 +1193,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               tmem_ld_wait();
               VB_EP(1);
               if (c == chunks - 1 && hh == HH - 1) {   // accumulator fully read: the MMA warp may start the tile after next
-                if (p.rowroll) slot_clear(taddr);
+                if (rowroll) slot_clear(taddr);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) acc_release(buf);
@@ -1199,10 +1206,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 for (int j = 0; j < CW / 4; ++j) {
                   const float4 mm = mreg[j];
                   if (mod_pk) {
-                    v[4 * j + 0] *= mm.x;
-                    v[4 * j + 1] *= mm.y;
-                    v[4 * j + 2] *= mm.z;
-                    v[4 * j + 3] *= mm.w;
+                    mul2(v[4 * j + 0], v[4 * j + 1], mm.x, mm.y);
+                    mul2(v[4 * j + 2], v[4 * j + 3], mm.z, mm.w);
                   } else {
                     v[4 * j + 0] = mp_silu_fast(v[4 * j + 0] * mm.x);
                     v[4 * j + 1] = mp_silu_fast(v[4 * j + 1] * mm.y);
@@ -1220,14 +1225,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                   for (int j = 0; j < U; ++j) {
                     const uint4 q = *reinterpret_cast<const uint4*>(rrow + swz(part * U + j, row));
                     const float2 a = unpack_op2(q.x), b = unpack_op2(q.y), cc = unpack_op2(q.z), d = unpack_op2(q.w);
-                    v[8 * j + 0] = fmaf(a.x, res_scale, v[8 * j + 0]);
-                    v[8 * j + 1] = fmaf(a.y, res_scale, v[8 * j + 1]);
-                    v[8 * j + 2] = fmaf(b.x, res_scale, v[8 * j + 2]);
-                    v[8 * j + 3] = fmaf(b.y, res_scale, v[8 * j + 3]);
-                    v[8 * j + 4] = fmaf(cc.x, res_scale, v[8 * j + 4]);
-                    v[8 * j + 5] = fmaf(cc.y, res_scale, v[8 * j + 5]);
-                    v[8 * j + 6] = fmaf(d.x, res_scale, v[8 * j + 6]);
-                    v[8 * j + 7] = fmaf(d.y, res_scale, v[8 * j + 7]);
+                    fma2(v[8 * j + 0], v[8 * j + 1], a.x, a.y, res_scale, res_scale);
+                    fma2(v[8 * j + 2], v[8 * j + 3], b.x, b.y, res_scale, res_scale);
+                    fma2(v[8 * j + 4], v[8 * j + 5], cc.x, cc.y, res_scale, res_scale);
+                    fma2(v[8 * j + 6], v[8 * j + 7], d.x, d.y, res_scale, res_scale);
                   }
                 } else {
 #pragma unroll
@@ -1257,9 +1258,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < CW; ++j) v[j] = fminf(fmaxf(v[j], -clampv), clampv);
               }
-              if (needs_norm) {
+              if (needs_norm) {          // two partial sums (even / odd columns) in one packed FMA per pair — in every layout alike
+                float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                for (int j = 0; j < CW; ++j) ssp[hh] = fmaf(v[j], v[j], ssp[hh]);
+                for (int j = 0; j < CW; j += 2) fma2(s0, s1, v[j], v[j + 1], v[j], v[j + 1]);
+                ssp[hh] += s0 + s1;
               }
               if (p.out_f32 != nullptr && valid) {
                 float4* o = reinterpret_cast<float4*>(p.out_f32 + pix * p.ld_f32 + col);

@@ -356,6 +356,19 @@ __device__ __forceinline__ float mp_silu_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
   return x * fmaf(t, 0.5f / 0.596f, 0.5f / 0.596f);
 }
+// Packed fp32 arithmetic (sm_100: FMUL2 / FFMA2 do two lanes' worth of fp32 work per instruction — same results as the scalar
+// forms, half the issue slots; the GEMM epilogues are issue- and energy-bound, profiles/r02_energy_note.txt).
+__device__ __forceinline__ void mul2(float& a, float& b, float s0, float s1) {          // a *= s0, b *= s1
+  asm("{\n.reg .b64 x, s, r;\nmov.b64 x, {%0, %1};\nmov.b64 s, {%2, %3};\nmul.rn.f32x2 r, x, s;\nmov.b64 {%0, %1}, r;\n}"
+      : "+f"(a), "+f"(b)
+      : "f"(s0), "f"(s1));
+}
+__device__ __forceinline__ void fma2(float& c0, float& c1, float a0, float a1, float s0, float s1) {   // c = a * s + c
+  asm("{\n.reg .b64 x, s, c, r;\nmov.b64 x, {%2, %3};\nmov.b64 s, {%4, %5};\nmov.b64 c, {%0, %1};\nfma.rn.f32x2 r, x, s, c;\n"
+      "mov.b64 {%0, %1}, r;\n}"
+      : "+f"(c0), "+f"(c1)
+      : "f"(a0), "f"(a1), "f"(s0), "f"(s1));
+}
 __device__ __forceinline__ uint32_t pack_op2(float lo, float hi) {
 #ifdef VB_OP_BF16
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
