@@ -1099,18 +1099,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (lane == 0) mbar_arrive(&tmem_empty[sl]);
         }
       }
-      for (;; ++it) {
+      const bool dbg_off = (p.dbg & 1) != 0, dbg_ts = (p.dbg & 32) != 0;       // ablation / time-stamp switches, read once
+      for (it = EG ? group : 0;; it += EG ? 2 : 1) {                // ping-pong: group g takes tiles g, g+2, ...
         const int wi = rowroll ? it / nblk : it;                  // CTA-local work item (tile, or strip of rows)
         const int jb = rowroll ? it - wi * nblk : 0;              // block within the strip: 0,1 carry no output row
         const int q = q0 + wi * qstride;
         if (q >= p.total_q) break;
-        if (EG && (it & 1) != group) continue;
         const int buf = rowroll ? (it & 7) : (it & 1);
         const uint32_t bphase = static_cast<uint32_t>(rowroll ? it >> 3 : it >> 1) & 1u;
         const TileCoord t = rowroll ? strip_tile(p, q, jb - 2) : decode_tile(p, tile_of(p, q, rank));
         const int n = t.n0 + rn;
         const bool valid = n < p.B;
-        const size_t pix = static_cast<size_t>(n) * p.H * p.W + (t.y0 + ry) * p.W + t.x0 + rx;
+        // (pixel index: evaluated where it is used — the per-pixel side channel and the fp32 output — so that variants with
+        //  neither do not carry its 64-bit arithmetic through every tile)
+        auto pix_of = [&]() -> size_t { return static_cast<size_t>(n) * p.H * p.W + (t.y0 + ry) * p.W + t.x0 + rx; };
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                static_cast<uint32_t>((rowroll ? buf * 64 : buf * kAccStride) + half * CW);
         if (rowroll && jb < 2) {                                  // partial sums of rows outside the strip: discard
@@ -1122,9 +1124,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (lane == 0) acc_release(buf);
           continue;
         }
-        if (!(p.dbg & 1)) res_topup();
+        if (!dbg_off) res_topup();
 
-        if (p.dbg & 1) {
+        if (dbg_off) {
           mbar_wait(&tmem_full[buf], bphase);
           tc_fence_after();
           if (rowroll) slot_clear(taddr);
@@ -1136,7 +1138,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
         // ---- pass R: pixel-norm statistic of the residual row (VB_RES_PIXNORM)
         float res_scale = p.res_a;
-        if (res_mode == VB_RES_SCALED) res_scale = p.res_a * __ldg(p.res_rnorm + (valid ? pix : 0));
+        if (res_mode == VB_RES_SCALED) res_scale = p.res_a * __ldg(p.res_rnorm + (valid ? pix_of() : 0));
         if (res_mode == VB_RES_PIXNORM) {
           float ss = 0.f;
           for (int c = 0; c < chunks; ++c) {
@@ -1167,7 +1169,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #ifdef VB_EPI_PROF
         if (ep_on) ep_t = clock64();          // (waiting for the accumulator is not epilogue work)
 #endif
-        if (leader && it == 0) VB_TS(4);
+        if (dbg_ts && leader && it == 0) VB_TS(4);
         tc_fence_after();
 
         // ---- pass M: accumulator -> modulation / mp_silu -> mp_sum with the residual -> clamp; RAW / SILU outputs leave
@@ -1265,7 +1267,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 ssp[hh] += s0 + s1;
               }
               if (p.out_f32 != nullptr && valid) {
-                float4* o = reinterpret_cast<float4*>(p.out_f32 + pix * p.ld_f32 + col);
+                float4* o = reinterpret_cast<float4*>(p.out_f32 + pix_of() * p.ld_f32 + col);
 #pragma unroll
                 for (int j = 0; j < CW / 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
               }
@@ -1355,7 +1357,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int o = 1; o < NP; ++o) ssv += xchg[1][(half + o) % NP][row];
           }
           const float inv_v = 1.0f / (1e-4f + sqrtf(ssv) * p.inv_sqrt_c);
-          if (p.out_rnorm != nullptr && half == 0 && valid) p.out_rnorm[pix] = inv_v;
+          if (p.out_rnorm != nullptr && half == 0 && valid) p.out_rnorm[pix_of()] = inv_v;
 #pragma unroll
           for (int c = 0; c < MAXC; ++c) {
             if (c < chunks) {
