@@ -3,6 +3,7 @@
 Env: VB_B batch, VB_REPS repetitions, VB_ONLY comma list of shape indices, VB_EPI comma list of epilogues:
   simple  one raw output                         mod    conv_res0: modulation + mp_silu -> raw
   r1s     mp_sum(res) + clip -> raw, silu        r2ns   mp_sum(pixel_norm(res)) + clip -> raw, norm_silu
+  r3ns / r3nss  as r2ns / r2nss with the residual scaled per pixel (VB_RES_SCALED, the plans' form), b folded into the weights
   r2nss   ... -> raw, norm_silu, silu            (library knobs: VB_TAP_MODE, VB_DBG, VB_GENERIC_EPI)
   qkv     1x1 only: per-head normalise + scatter to [B,h,S,64] (cout = heads*3*64)          VB_TUNE: vb_conv_desc.tune
 """
@@ -58,6 +59,11 @@ for idx, (R, cin, cout, taps, bn) in enumerate(SHAPES):
         elif epi != "simple":
             d.flags, d.res = L.VB_F_CLIP, res.data_ptr()
             d.res_mode = L.VB_RES_PIXNORM if (epi.startswith("r2") and fullrow) else L.VB_RES_PLAIN
+            if epi.startswith("r3") and fullrow:          # the plans' form: residual scaled by the producer's per-pixel 1/rms side channel
+                d.res_mode = L.VB_RES_SCALED
+                rn = torch.rand(B * R * R, device=dev) + 0.5
+                d.res_rnorm = rn.data_ptr()
+                d.flags |= L.VB_F_RESB_FOLDED
             for ch in epi[2:]:
                 kinds.append(L.VB_OUT_SILU if ch == "s" else (L.VB_OUT_NORM_SILU if fullrow else L.VB_OUT_SILU))
                 if ch == "n":
