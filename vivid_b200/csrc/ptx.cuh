@@ -20,6 +20,20 @@ typedef __half op_t;
 #define VB_OP_DTYPE 1
 #endif
 
+// mbarrier.try_wait suspends the thread until the phase completes OR a time limit passes; with the system's default limit a
+// waiting role polls every few dozen nanoseconds (six instructions per failed poll: 15-20 % of all warp-instructions of the
+// main-loop-bound conv layers were such polls, profiles/r02_conv_icache.txt).  A longer suspend-time hint keeps the wake-up
+// event-driven and removes the polls.  -DVB_WAIT_HINT_NS=0 restores the default limit.
+#ifndef VB_WAIT_HINT_NS
+#define VB_WAIT_HINT_NS 2000
+#endif
+#define VB_STR2(x) #x
+#define VB_STR(x) VB_STR2(x)
+#if VB_WAIT_HINT_NS > 0
+#define VB_WAIT_HINT ", " VB_STR(VB_WAIT_HINT_NS)
+#else
+#define VB_WAIT_HINT ""
+#endif
 #ifndef VB_SPIN_LIMIT
 #define VB_SPIN_LIMIT (1u << 26)   // a stuck pipeline traps instead of hanging the GPU
 #endif
@@ -77,7 +91,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2" VB_WAIT_HINT ";\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
