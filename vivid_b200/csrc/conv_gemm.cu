@@ -200,26 +200,6 @@ __device__ __forceinline__ uint32_t mp_silu_pk(uint32_t x2, float scale) {
   return *reinterpret_cast<uint32_t*>(&y);
 }
 
-// ... with scale == 1 (conv_res0: the modulation has been applied in fp32 already): one packed multiply less per pair.
-__device__ __forceinline__ uint32_t mp_silu_pk1(uint32_t x2) {
-#ifdef VB_OP_BF16
-  const __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&x2);
-  __nv_bfloat162 h = __hmul2(x, __float2bfloat162_rn(0.5f));
-  uint32_t hu = *reinterpret_cast<uint32_t*>(&h), tu;
-  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(tu) : "r"(hu));
-  const __nv_bfloat162 c = __float2bfloat162_rn(0.5f / 0.596f);
-  __nv_bfloat162 y = __hmul2(x, __hfma2(*reinterpret_cast<__nv_bfloat162*>(&tu), c, c));
-#else
-  const __half2 x = *reinterpret_cast<__half2*>(&x2);
-  __half2 h = __hmul2(x, __float2half2_rn(0.5f));
-  uint32_t hu = *reinterpret_cast<uint32_t*>(&h), tu;
-  asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(hu));
-  const __half2 c = __float2half2_rn(0.5f / 0.596f);
-  __half2 y = __hmul2(x, __hfma2(*reinterpret_cast<__half2*>(&tu), c, c));
-#endif
-  return *reinterpret_cast<uint32_t*>(&y);
-}
-
 // Clamp of a packed fp16 pair to [-c, c] (c exactly representable in fp16).
 __device__ __forceinline__ uint32_t clamp_pk(uint32_t x2, float c) {
 #ifdef VB_OP_BF16
@@ -1201,21 +1181,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if (lane == 0) acc_release(buf);
               }
               const int col = t.col0 + c * 64 + part * CW;
-              // conv_res0 (modulation + mp_silu, nothing else): the activation is applied to the packed 16-bit value
-              const bool mod_pk = modsilu && !has_res && !needs_norm && p.out_f32 == nullptr && !(p.flags & VB_F_CLIP);
+              // conv_res0: v = mp_silu(v * mod) in packed fp32 arithmetic — per column PAIR two multiplies, two tanh, one multiply and
+              // one FMA (seven instructions with the pack; the packed-fp16 form needed eight with its half-register shuffle, and
+              // rounded before the activation instead of after it)
               if (modsilu) {
 #pragma unroll
                 for (int j = 0; j < CW / 4; ++j) {
                   const float4 mm = mreg[j];
-                  if (mod_pk) {
-                    mul2(v[4 * j + 0], v[4 * j + 1], mm.x, mm.y);
-                    mul2(v[4 * j + 2], v[4 * j + 3], mm.z, mm.w);
-                  } else {
-                    v[4 * j + 0] = mp_silu_fast(v[4 * j + 0] * mm.x);
-                    v[4 * j + 1] = mp_silu_fast(v[4 * j + 1] * mm.y);
-                    v[4 * j + 2] = mp_silu_fast(v[4 * j + 2] * mm.z);
-                    v[4 * j + 3] = mp_silu_fast(v[4 * j + 3] * mm.w);
-                  }
+                  mul2(v[4 * j + 0], v[4 * j + 1], mm.x, mm.y);
+                  mul2(v[4 * j + 2], v[4 * j + 3], mm.z, mm.w);
+                  mp_silu_f32x2(v[4 * j + 0], v[4 * j + 1]);
+                  mp_silu_f32x2(v[4 * j + 2], v[4 * j + 3]);
                 }
                 if (!EG && c + 1 < chunks) mod_fetch(c + 1, half);
               }
@@ -1281,10 +1257,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               } else {
 #pragma unroll
                 for (int j = 0; j < CW / 2; ++j) r16h[hh][j] = pack_op2_nosat(v[2 * j], v[2 * j + 1]);
-              }
-              if (mod_pk) {
-#pragma unroll
-                for (int j = 0; j < CW / 2; ++j) r16h[hh][j] = mp_silu_pk1(r16h[hh][j]);
               }
               if (needs_norm) {
 #pragma unroll

@@ -383,6 +383,16 @@ __device__ __forceinline__ void fma2(float& c0, float& c1, float a0, float a1, f
       : "+f"(c0), "+f"(c1)
       : "f"(a0), "f"(a1), "f"(s0), "f"(s1));
 }
+// mp_silu of two fp32 values in place: x c (1 + tanh(x/2)), c = 0.5/0.596 (reference training/models.py:66-67)
+__device__ __forceinline__ void mp_silu_f32x2(float& a, float& b) {
+  float h0 = a, h1 = b;
+  mul2(h0, h1, 0.5f, 0.5f);
+  float t0, t1;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+  mul2(a, b, 0.5f / 0.596f, 0.5f / 0.596f);
+  fma2(a, b, a, b, t0, t1);
+}
 __device__ __forceinline__ uint32_t pack_op2(float lo, float hi) {
 #ifdef VB_OP_BF16
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
