@@ -35,7 +35,13 @@ typedef __half op_t;
 #define VB_WAIT_HINT ""
 #endif
 #ifndef VB_SPIN_LIMIT
-#define VB_SPIN_LIMIT (1u << 26)   // a stuck pipeline traps instead of hanging the GPU
+// a stuck pipeline traps instead of hanging the GPU: with the suspend-time hint a failed poll takes up to VB_WAIT_HINT_NS, so
+// 2^23 polls bound a genuine deadlock at ~17 s (without the hint, 2^26 polls of a few dozen nanoseconds each)
+#if VB_WAIT_HINT_NS > 0
+#define VB_SPIN_LIMIT (1u << 23)
+#else
+#define VB_SPIN_LIMIT (1u << 26)
+#endif
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
