@@ -61,7 +61,11 @@ for i, name in enumerate(("vivid-base", "vivid-uncond", "vivid-sr")):
                 break
     finally:
         L.lib().vb_set_pdl(prev)
-    assert good > 0
+    if good == 0:       # every replay lost an activity record (seen on some boxes for the 150-launch SR plan): no table for this net
+        print(f"== {name} B={B}: no complete set of activity records in {REPS + 2} replays; graph replay {graph_ms:.2f} ms/call")
+        del net, p
+        torch.cuda.empty_cache()
+        continue
     ms = [m / good for m in ms]
     tot = sum(ms)
     fl = sum(o[2] for o in p.op_info)
