@@ -140,11 +140,20 @@ typedef struct vb_conv_desc {
                         * bits 2-3: 1 per-tap operand boxes, 2 shared haloed boxes wherever they fit;
                         * bits 4-5: 1 row-rolling input-stationary layout (3x3, 64 -> 64 channels, rows >= 128 px);
                         * bit 6: ping-pong epilogue (two groups of four warps on alternate tiles; block_n == 64);
-                        * bit 7: 1x1 layers keep their N tile's weights resident in shared memory */
+                        * bit 7: 1x1 layers keep their N tile's weights resident in shared memory;
+                        * bit 8: K-split — the two CTAs of a cluster share a tile, each summing half of the 64-channel blocks of
+                        *        every tap; the second CTA's fp32 partial goes through ks_ws and is added as (first + second) by
+                        *        the first.  For layers with fewer tiles than SMs and long K loops (the 8x8 level).  Unlike
+                        *        bits 0-7 this changes the summation order: decide it from the layer's geometry, never from the
+                        *        batch size, or results stop being identical across batch splits. */
   int32_t part_ld;     /* QKVNORM: elements per destination row; 0 = head_dim.  64 with head_dim 32: the rows are written into
                         * zero-initialised 64-element rows (the upper half is never touched), see vb_attn_desc.ld */
+  void* ks_ws;         /* tune bit 8: fp32 workspace of vb_conv_ksplit_ws_bytes(B, H, W, cout_pad) bytes; may be shared by all
+                        * K-split convs launched in order on one stream */
 } vb_conv_desc;
 int vb_conv(const vb_conv_desc* d, void* stream);
+/* Bytes of K-split workspace a conv over [B][H][W] pixels with cout_pad output channels needs (whole 128-pixel tiles). */
+int64_t vb_conv_ksplit_ws_bytes(int32_t B, int32_t H, int32_t W, int32_t cout_pad);
 /* Diagnostics (micro-benchmarks only): with the environment variable VB_DBG & 16 set when an op is prepared, the conv
  * kernel records the longest CTA lifetime in SM cycles; this call synchronises, returns the maximum since the last
  * call (HOST pointer) and resets it. */

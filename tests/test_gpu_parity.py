@@ -182,6 +182,65 @@ def test_conv_gemm_vs_conv2d(env, B, R, cin, cout, taps, bn, modsilu, res_mode, 
         assert torch.equal(o2, o32 * 2)
 
 
+KSPLIT_CASES = [
+    # B, R, cin, cin2, cout, block_n, modsilu, res_mode
+    (9, 8, 512, 0, 512, 256, 0, 1),       # the 8x8 level's conv_res1: 5 tiles x 2 N tiles, K = 72 blocks -> 36 per CTA
+    (9, 8, 512, 0, 512, 128, 1, 0),       # conv_res0 (modulation + mp_silu), 4 N tiles
+    (3, 8, 256, 128, 256, 256, 1, 0),     # two sources, 4 + 2 K blocks per tap: CTA 0 takes a[0:3], CTA 1 a[3:4] + b[0:2]
+    (3, 8, 128, 256, 128, 128, 0, 1),     # ... split point inside the second source
+    (300, 8, 128, 0, 128, 128, 0, 1),     # 150 tiles on 74 clusters: the counters run over several tiles per CTA
+    (2, 16, 128, 0, 128, 128, 0, 1),      # multi-row tiles (haloed boxes shared by three taps)
+    (1, 128, 128, 0, 64, 64, 1, 0),       # 128-pixel rows
+    (5, 4, 128, 0, 64, 64, 0, 1),         # 8 images per tile, ragged batch
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,R,cin,cin2,cout,bn,modsilu,res_mode", KSPLIT_CASES)
+def test_conv_ksplit(env, B, R, cin, cin2, cout, bn, modsilu, res_mode):
+    """vb_conv_desc.tune bit 8 (K-split over the two CTAs of a cluster, SURVEY 7.3 / 8(d) split-K for the 8x8 level): parity with
+    F.conv2d semantics, agreement with the unsplit kernel, and the properties the plans rely on — bits do not depend on the
+    batch the layer is launched with, nor on block_n."""
+    L, lib, dev = env
+    dt = L.operand_torch_dtype()
+    g = torch.Generator().manual_seed(B * 7 + R + cin + cout)
+    a = torch.randn(B, R, R, cin, generator=g).to(dev).to(dt)
+    b = torch.randn(B, R, R, cin2, generator=g).to(dev).to(dt) if cin2 else None
+    w = torch.randn(cout, cin + cin2, 3, 3, generator=g).to(dev)
+    wp = prep_weight(L, lib, w, cout_pad=cout, split=cin if cin2 else None)
+    mod = (torch.randn(B, cout, generator=g) * 0.3 + 1).to(dev) if modsilu else None
+    res = (torch.randn(B, R, R, cout, generator=g) * 1.7).to(dev).to(dt) if res_mode else None
+    ws = torch.full((lib.vb_conv_ksplit_ws_bytes(B, R, R, cout) // 4,), float("nan"), device=dev)
+
+    def run(nb, tune, block_n):
+        out = torch.full((nb, R, R, cout), float("nan"), dtype=dt, device=dev)
+        d = L.ConvDesc(x=a.data_ptr(), x2=L.ptr(b), w=wp.data_ptr(), mod=L.ptr(mod), res=L.ptr(res), B=nb, H=R, W=R, cin_pad=cin,
+                       cin2_pad=cin2, cout_pad=cout, taps=9, block_n=block_n, epi_mode=L.VB_EPI_PLAIN,
+                       flags=(L.VB_F_MODSILU if modsilu else 0) | (L.VB_F_CLIP if res_mode else 0), mod_stride=cout,
+                       res_mode=res_mode, res_t=0.3, clip=1.5, tune=tune, ks_ws=ws.data_ptr() if tune & 256 else None)
+        d.out[0], d.out_kind[0] = out.data_ptr(), L.VB_OUT_RAW
+        L.check(lib.vb_conv(C.byref(d), stream()), "vb_conv")
+        torch.cuda.synchronize()
+        return out
+
+    x = a.float() if b is None else torch.cat([a.float(), b.float()], dim=-1)
+    y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), ref_weight(w), padding=1)
+    if modsilu:
+        y = mp_silu(y * mod[:, :, None, None])
+    if res_mode:
+        y = ((res.float().permute(0, 3, 1, 2) * 0.7 + y * 0.3) / math.sqrt(0.7 ** 2 + 0.3 ** 2)).clamp(-1.5, 1.5)
+    split = run(B, 256, bn)
+    assert rel(split.float().permute(0, 3, 1, 2), y) < (2e-3 if dt == torch.float16 else 8e-3)
+    whole = run(B, 1, bn)
+    assert rel(split.float(), whole.float()) < 1e-3                      # same sum, other association: last-bit differences only
+    assert torch.equal(split, run(B, 256, bn))                          # deterministic
+    if B > 1:                                                            # bits independent of the batch it is launched with
+        nb = (B + 1) // 2
+        assert torch.equal(run(nb, 256, bn), split[:nb])
+    if bn > 64:                                                          # ... and of the N tile
+        assert torch.equal(run(B, 256, bn // 2), split)
+
+
 def test_conv_two_source_and_narrow_output(env):
     """mp_cat folded into the K loop (models.py:78-84,403): conv(cat(wa*a, wb*b)) with the weights split over two tensors;
     and the 3-channel out_conv (padded to 16 columns, fp32 direct stores)."""

@@ -65,6 +65,14 @@ def test_argument_validation_returns_error_codes(lib):
     assert lib.vb_conv(ctypes.byref(d), None) == -1 and b"power of two" in lib.vb_last_error()
     d = L.ConvDesc(x=1 << 20, w=1 << 20, B=1, H=16, W=16, cin_pad=60, cout_pad=64, taps=9, block_n=64)
     assert lib.vb_conv(ctypes.byref(d), None) == -1 and b"multiples of 64" in lib.vb_last_error()
+    # K-split (tune bit 8) needs its workspace and an even number of 64-channel K blocks per tap
+    d = L.ConvDesc(x=1 << 20, w=1 << 20, B=2, H=8, W=8, cin_pad=128, cout_pad=64, taps=9, block_n=64, tune=256)
+    assert lib.vb_conv(ctypes.byref(d), None) == -1 and b"K-split" in lib.vb_last_error()
+    d = L.ConvDesc(x=1 << 20, w=1 << 20, ks_ws=1 << 20, B=2, H=8, W=8, cin_pad=192, cout_pad=64, taps=9, block_n=64, tune=256)
+    assert lib.vb_conv(ctypes.byref(d), None) == -1 and b"K-split" in lib.vb_last_error()
+    assert lib.vb_conv_ksplit_ws_bytes(9, 8, 8, 512) == 5 * 128 * 512 * 4          # 2 images per tile -> 5 tiles
+    assert lib.vb_conv_ksplit_ws_bytes(2, 16, 16, 128) == 4 * 128 * 128 * 4
+    assert lib.vb_conv_ksplit_ws_bytes(0, 8, 8, 64) == 0
     a = L.AttnDesc(q=1, k=1, v=1, y=1, B=1, heads=1, sq=16, sk=16, head_dim=48)
     assert lib.vb_attn(ctypes.byref(a), None) == -1 and b"head_dim" in lib.vb_last_error()
     assert lib.vb_plan_run(None, 0, -1, None) == -1

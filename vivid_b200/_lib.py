@@ -33,7 +33,7 @@ class ConvDesc(C.Structure):
                 ("cout_pad", i32), ("taps", i32), ("block_n", i32), ("epi_mode", i32), ("flags", i32),
                 ("mod_stride", i32), ("ld_f32", i32), ("res_mode", i32), ("out_kind", i32 * 3), ("head_dim", i32),
                 ("parts", i32), ("seg_div", i32), ("part_seq", i32 * 3), ("part_off", i32 * 3),
-                ("out_scale", f32 * 3), ("res_t", f32), ("clip", f32), ("tune", i32), ("part_ld", i32)]
+                ("out_scale", f32 * 3), ("res_t", f32), ("clip", f32), ("tune", i32), ("part_ld", i32), ("ks_ws", vp)]
 
 
 class AttnDesc(C.Structure):
@@ -105,6 +105,7 @@ SIGNATURES = {
     "vb_operand_dtype": (C.c_int, []),
     "vb_weight_prep": (C.c_int, [C.POINTER(WeightPrepDesc), vp]),
     "vb_conv": (C.c_int, [C.POINTER(ConvDesc), vp]),
+    "vb_conv_ksplit_ws_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "vb_attn": (C.c_int, [C.POINTER(AttnDesc), vp]),
     "vb_eltwise": (C.c_int, [C.POINTER(EwDesc), vp]),
     "vb_embed": (C.c_int, [C.POINTER(EmbDesc), vp]),

@@ -133,6 +133,13 @@ struct ConvKernelParams {
                       // TMA stores (map_out.m[part]: {64, rows} 2-D maps of the three destinations) instead of per-thread stores
   int qkv_rows;       // ... rows per store box = min(128, H*W)
   int wgt_nowait;     // set per launch: the weight producer need not wait for the previous kernel (see the PDL note in the kernel)
+  // K-split (tune bit 8): the two CTAs of a cluster work on the SAME tile, each over half of the input-channel blocks of
+  // every tap.  Rank 1 writes its fp32 partial accumulator to ks_ws ([tile][block_n/4][128 rows][4], L2-resident) and
+  // publishes a per-warp tile counter in rank 0's shared memory; rank 0 adds the partial to its own accumulator values
+  // (always own + partner: a fixed order) and runs the normal epilogue.  For layers with fewer tiles than SMs and long K
+  // loops (the 8x8 level).
+  int ksplit;
+  float* ks_ws;
 };
 
 struct TileCoord {
@@ -333,6 +340,8 @@ struct RoleCtx {
   uint32_t tmem_base;
   uint32_t rank;
   int q0, qstride;
+  int k_lo, k_hi;                 // this CTA's range of 64-channel K blocks within every tap (K-split: half of them)
+  int ka_lo, ka_hi, kb_lo, kb_hi; // ... as ranges of the first / second channel-concatenated source
 };
 
 // Pins a computed address in a register: without it the compiler re-derives every barrier address from the shared
@@ -403,6 +412,24 @@ __device__ __forceinline__ void umma_commit_addr(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// K-split hand-over (see ConvKernelParams::ksplit): the partner's epilogue warp w publishes "partials of my first n tiles are in
+// the workspace" by a release store into THIS CTA's shared memory; warp w here polls its own counter.  A counter instead of an
+// mbarrier: the producer may run several tiles ahead and a phase bit would wrap.
+__device__ __forceinline__ void ks_publish(uint32_t counter_cluster_addr, uint32_t n) {
+  asm volatile("st.release.cluster.shared::cluster.u32 [%0], %1;" ::"r"(counter_cluster_addr), "r"(n) : "memory");
+}
+__device__ __forceinline__ void ks_wait(const uint32_t* counter, uint32_t n) {
+  const uint32_t a = smem_u32(counter);
+  uint32_t spins = 0;
+  while (true) {
+    uint32_t v;
+    asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    if (v >= n) return;
+    __nanosleep(64);
+    if (++spins > (1u << 24)) __trap();          // a stuck partner traps instead of hanging the GPU
+  }
+}
+
 // Activation producer (warp 0).  Simple mode: one {64 ch, tile} box per (tap, K chunk) stage; it also arms the stage's
 // barrier for the weight tile the other producer sends.  Tap mode: one haloed box per (tap group, K chunk).
 template <bool PAIR>
@@ -445,8 +472,8 @@ __device__ __forceinline__ void producer_act(const ConvKernelParams& p, const Ro
         const int cy = p.tap_mode == 1 ? t.y0 + g - 1 : t.y0 - 1;
         for (int half = 0; half < 2; ++half) {
           const CUtensorMap* m = half == 0 ? map_a : map_a2;
-          const int n = half == 0 ? p.kc_a : p.kc_b;
-          for (int kc = 0; kc < n; ++kc) {
+          const int n = half == 0 ? c.ka_hi : c.kb_hi;
+          for (int kc = half == 0 ? c.ka_lo : c.kb_lo; kc < n; ++kc) {
             mbar_wait_addr(c.empty + slot * 8, phase ^ 1u);
             if (lead) mbar_expect_tx_addr(c.full + slot * 8, tx);
             tma_act<PAIR>(m, c.full_dst + slot * 8, dst, kc * kBlockK, cx, cy, t.n0);
@@ -471,8 +498,8 @@ __device__ __forceinline__ void producer_act(const ConvKernelParams& p, const Ro
       for (int tap = 0; tap < p.taps; ++tap) {
         for (int half = 0; half < 2; ++half) {
           const CUtensorMap* m = half == 0 ? map_a : map_a2;
-          const int n = half == 0 ? p.kc_a : p.kc_b;
-          for (int kc = 0; kc < n; ++kc) {
+          const int n = half == 0 ? c.ka_hi : c.kb_hi;
+          for (int kc = half == 0 ? c.ka_lo : c.kb_lo; kc < n; ++kc) {
             mbar_wait_addr(c.empty + slot * 8, phase ^ 1u);
             if (lead) mbar_expect_tx_addr(c.full + slot * 8, tx);
             tma_act<PAIR>(m, c.full_dst + slot * 8, dst, kc * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
@@ -528,7 +555,7 @@ __device__ __forceinline__ void producer_wgt(const ConvKernelParams& p, const Ro
     for (int q = c.q0; q < p.total_q; q += c.qstride) {
       const int col = decode_tile(p, tile_of(p, q, c.rank)).col0 + wrow;
       for (int g = 0; g < 3; ++g) {
-        for (int kc = 0; kc < kct; ++kc) {
+        for (int kc = c.k_lo; kc < c.k_hi; ++kc) {
           int kcol = g * g_step + kc * kBlockK;
 #pragma unroll
           for (int i = 0; i < 3; ++i, kcol += i_step) {
@@ -555,18 +582,20 @@ __device__ __forceinline__ void producer_wgt(const ConvKernelParams& p, const Ro
     for (int i = 0; i < kct; ++i, dst += b_bytes) tma_wgt<PAIR>(map_w, c.bfull_dst, dst, i * kBlockK, col);
   } else {
     const uint32_t nslots = p.num_stages, slot_bytes = p.stage_bytes, base = c.smem + kAStageBytes;
-    const int k_blocks = p.taps * kct;
+    const int k_end = p.taps * kct;
     uint32_t slot = 0, phase = 0, dst = base;
     for (int q = c.q0; q < p.total_q; q += c.qstride) {
       const int col = decode_tile(p, tile_of(p, q, c.rank)).col0 + wrow;
-      for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait_addr(c.empty + slot * 8, phase ^ 1u);
-        tma_wgt<PAIR>(map_w, c.full_dst + slot * 8, dst, kb * kBlockK, col);
-        dst += slot_bytes;
-        if (++slot == nslots) {
-          slot = 0;
-          phase ^= 1u;
-          dst = base;
+      for (int kb0 = 0; kb0 < k_end; kb0 += kct) {             // per tap: this CTA's K blocks (all of them unless K-split)
+        for (int kb = kb0 + c.k_lo; kb < kb0 + c.k_hi; ++kb) {
+          mbar_wait_addr(c.empty + slot * 8, phase ^ 1u);
+          tma_wgt<PAIR>(map_w, c.full_dst + slot * 8, dst, kb * kBlockK, col);
+          dst += slot_bytes;
+          if (++slot == nslots) {
+            slot = 0;
+            phase ^= 1u;
+            dst = base;
+          }
         }
       }
     }
@@ -582,6 +611,7 @@ __device__ __forceinline__ void mma_role(const ConvKernelParams& p, const RoleCt
     else umma_f16_ss(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, acc);
   };
   const int kct = p.kc_a + p.kc_b;
+  const int kcl = c.k_hi - c.k_lo;               // K blocks per tap this CTA multiplies (kct unless K-split; never with resident weights)
   const uint32_t b_tile_lo = static_cast<uint32_t>(p.b_bytes) >> 4;
   int it = 0;
   if (p.rowroll) {
@@ -670,7 +700,7 @@ __device__ __forceinline__ void mma_role(const ConvKernelParams& p, const RoleCt
       uint32_t accumulate = 0;
       for (int g = 0; g < 3; ++g) {
         uint32_t b_gk = b_base + static_cast<uint32_t>(g) * b_g_lo;
-        for (int kc = 0; kc < kct; ++kc, b_gk += b_tile_lo) {
+        for (int kc = 0; kc < kcl; ++kc, b_gk += b_tile_lo) {
           mbar_wait_addr(c.full + as * 8, aph);
           if (it == 0 && g == 0 && kc == 0) VB_TS(2);
           tc_fence_after();
@@ -719,7 +749,7 @@ __device__ __forceinline__ void mma_role(const ConvKernelParams& p, const RoleCt
     const uint32_t stage_lo = static_cast<uint32_t>(p.stage_bytes) >> 4;
     const uint32_t nstages = p.num_stages;
     uint32_t stage = 0, phase = 0, a_lo = s_base;
-    const int k_blocks = p.taps * kct;
+    const int k_blocks = p.taps * kcl;
     const bool resident = p.b_resident != 0;
     const uint32_t b_res = umma_desc_lo(c.smem + p.b_off);
     if (resident && c.q0 < p.total_q) {
@@ -766,7 +796,9 @@ __device__ __forceinline__ bool kind_norm(int k) { return k == VB_OUT_NORM || k 
 
 // Template arguments >= 0 fix the epilogue variant at compile time; -1 reads it from the parameters (generic
 // fallback for combinations the plans never emit).  STAGED = 0 is the QKVNORM / narrow fp32 epilogue.
-template <int STAGED, int RES_T, int MOD_T, int K0_T, int K1_T, int K2_T, int PARTS>
+// KS: the variant carries the K-split epilogue paths (only the variants the 8x8-level 3x3 layers use are instantiated with it;
+// the others stay instruction-for-instruction what they were — several sit at the 168-register limit).
+template <int STAGED, int RES_T, int MOD_T, int K0_T, int K1_T, int K2_T, int PARTS, bool KS = false>
 __global__ void __launch_bounds__(PARTS == 1 ? 384 : 128 + 128 * PARTS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_res,
@@ -798,6 +830,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __shared__ __align__(8) uint64_t res_empty[kMaxResSlots];
   __shared__ float xchg[2][NP][kBlockM];     // [residual | result statistic][column part][row]
   __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t ks_count[8];           // K-split: tiles whose partial the partner's epilogue warp i has published
 
   // SWIZZLE_128B tiles need 1024-byte alignment.
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -810,8 +843,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // cta_group::2 MMA for both, so every CTA reads (128 + block_n/2) operand rows per K step from its shared memory
   // instead of (128 + block_n) — the SS-mode MMA is shared-memory-bandwidth bound below N=256 (tools/exp/umma_rate.cu).
   const uint32_t rank = p.pair ? cluster_ctarank() : 0u;
-  const int q0 = p.pair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int qstride = p.pair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // K-split: the two CTAs of a cluster take the SAME work items and half of every tap's K blocks each (otherwise independent:
+  // own operands, own MMA issuer, own accumulator)
+  const uint32_t krank = p.ksplit ? cluster_ctarank() : 0u;
+  const bool shared_items = p.pair || p.ksplit;
+  const int q0 = shared_items ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int qstride = shared_items ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -837,6 +874,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_init(&res_full[b], 1);
       mbar_init(&res_empty[b], kTileWarps);
     }
+    for (int b = 0; b < 8; ++b) ks_count[b] = 0;
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -849,7 +887,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   }
   tc_fence_before();
-  if (p.pair) cluster_sync_all(); else __syncthreads();
+  if (shared_items) cluster_sync_all(); else __syncthreads();      // (K-split: the partner's counters are zeroed before it publishes)
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   // Everything above overlapped the previous kernel's tail; dependent global memory is touched from here on.  The weight
@@ -878,6 +916,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       c.rank = rank;
       c.q0 = q0;
       c.qstride = qstride;
+      {
+        const int kct = p.kc_a + p.kc_b;
+        c.k_lo = p.ksplit ? static_cast<int>(krank) * (kct >> 1) : 0;
+        c.k_hi = p.ksplit ? c.k_lo + (kct >> 1) : kct;
+        c.ka_lo = min(c.k_lo, p.kc_a);
+        c.ka_hi = min(c.k_hi, p.kc_a);
+        c.kb_lo = max(c.k_lo - p.kc_a, 0);
+        c.kb_hi = max(c.k_hi - p.kc_a, 0);
+      }
       if (warp == 0) {
         if (p.pair) producer_act<true>(p, c, &map_a, &map_a2); else producer_act<false>(p, c, &map_a, &map_a2);
       } else if (warp == 3) {
@@ -969,6 +1016,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (lane == 0) acc_release(buf);
       }
       if (p.qkv_stg && leader) bulk_wait_read<0>();      // staging smem must outlive the last TMA store's read
+    } else if (KS && !EG && p.ksplit && krank == 1) {
+      // K-split, second half of K: this CTA's accumulator is a PARTIAL sum.  Each epilogue thread writes its row's columns as
+      // fp32 into the tile's workspace block — laid out [column / 4][row][4] so that a warp's 16-byte stores (32 consecutive
+      // rows) are one contiguous 512-byte run — and the warp then publishes its tile count to the partner warp of rank 0,
+      // which owns exactly the same rows and columns.
+      const uint32_t counter = mapa_u32(smem_u32(&ks_count[warp - kFirstEpiWarp]), 0);
+      const int chunks = p.block_n >> 6;
+      for (it = 0;; ++it) {
+        const int q = q0 + it * qstride;
+        if (q >= p.total_q) break;
+        const int buf = it & 1;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * kAccStride + half * CW);
+        float4* ws = reinterpret_cast<float4*>(p.ks_ws + static_cast<size_t>(q) * (kBlockM * p.block_n)) + half * (CW / 4) * kBlockM + row;
+        mbar_wait(&tmem_full[buf], static_cast<uint32_t>(it >> 1) & 1u);
+        tc_fence_after();
+        for (int c = 0; c < chunks; ++c) {
+          float v[CW];
+          if (CW == 32) tmem_ld32(taddr + c * 64, v); else tmem_ld16(taddr + c * 64, v);
+          tmem_ld_wait();
+          if (c == chunks - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) acc_release(buf);
+          }
+          float4* o = ws + c * 16 * kBlockM;
+#pragma unroll
+          for (int j = 0; j < CW / 4; ++j) __stcg(o + j * kBlockM, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) ks_publish(counter, static_cast<uint32_t>(it + 1));
+      }
     } else {
       const int res_mode = RES_T >= 0 ? RES_T : p.res_mode;
       const bool rowroll = !EG && p.rowroll != 0;          // (the ping-pong variants never run the row-rolling layout: compile-time false)
@@ -1173,6 +1252,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               float v[CW];
               if (CW == 32) tmem_ld32(ta, v); else tmem_ld16(ta, v);
               tmem_ld_wait();
+              if (KS && !EG && p.ksplit) {
+                // K-split: add the partner CTA's partial sum of this tile (second half of K; L2-resident workspace) — as own + partner
+                // in every launch alike.  (Fetched after the accumulator read, not prefetched into registers beside it: these
+                // variants sit at the 168-register limit, and the layers that use this are main-loop bound.)
+                if (c == 0) {
+                  if (lane == 0) ks_wait(&ks_count[warp - kFirstEpiWarp], static_cast<uint32_t>(it + 1));
+                  __syncwarp();
+                  __threadfence();
+                }
+                const float4* w4 = reinterpret_cast<const float4*>(p.ks_ws + static_cast<size_t>(q) * (kBlockM * p.block_n)) +
+                                   (c * 16 + part * (CW / 4)) * kBlockM + row;
+#pragma unroll
+                for (int j = 0; j < CW / 4; ++j) {
+                  const float4 a = __ldcg(w4 + j * kBlockM);
+                  v[4 * j + 0] += a.x;
+                  v[4 * j + 1] += a.y;
+                  v[4 * j + 2] += a.z;
+                  v[4 * j + 3] += a.w;
+                }
+              }
               VB_EP(1);
               if (c == chunks - 1 && hh == HH - 1) {   // accumulator fully read: the MMA warp may start the tile after next
                 if (rowroll) slot_clear(taddr);
@@ -1392,16 +1491,20 @@ typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtenso
 struct Variant {
   int staged, res, mod, k0, k1, k2;     // -1 = any (run-time switch inside the kernel)
   int parts;                            // epilogue warps per TMEM lane quadrant (2, or 4 as a plan-time tuning choice)
+  int ks;                               // carries the K-split paths
   ConvKernelFn fn;
   unsigned long long attr_done;   // bit per device ordinal: the opt-in shared-memory attribute is per device
 };
-#define VB_VARIANT(S, R, M, A, B, C, P) {S, R, M, A, B, C, P, conv_gemm_kernel<S, R, M, A, B, C, P>, 0ull}
+#define VB_VARIANT(S, R, M, A, B, C, P) {S, R, M, A, B, C, P, 0, conv_gemm_kernel<S, R, M, A, B, C, P>, 0ull}
+#define VB_VARIANT_KS(S, R, M, A, B, C) {S, R, M, A, B, C, 2, 1, conv_gemm_kernel<S, R, M, A, B, C, 2, true>, 0ull}
 // (the 16-warp form, PARTS = 4, is kept compilable — add VB_VARIANT(..., 4) here — but not instantiated: measured on B200 it
 //  was 1-5 % SLOWER on every epilogue-bound layer, profiles/r01_conv_epilogue_notes.txt, so the epilogue is not bound by
 //  per-warp latency)
 #define VB_VARIANT24(S, R, M, A, B, C) VB_VARIANT(S, R, M, A, B, C, 2), VB_VARIANT(S, R, M, A, B, C, 1)
 // The epilogue combinations the plans emit (engine.py) get straight-line code; anything else runs the generic one.
 static Variant g_variants[] = {
+    VB_VARIANT_KS(1, 0, 1, VB_OUT_RAW, 0, 0),                              // K-split conv_res0 / conv_res1 of the 8x8 level
+    VB_VARIANT_KS(1, 1, 0, VB_OUT_RAW, 0, 0),
     VB_VARIANT(0, -1, -1, -1, -1, -1, 2),                                  // QKVNORM / narrow fp32
     VB_VARIANT24(1, 0, 1, VB_OUT_RAW, 0, 0),                               // conv_res0: modulation + mp_silu
     VB_VARIANT24(1, 0, 0, VB_OUT_RAW, 0, 0),                               // conv_skip, first conv
@@ -1422,14 +1525,20 @@ static Variant g_variants[] = {
     VB_VARIANT(1, -1, -1, -1, -1, -1, 2),                                  // generic staged epilogue (must stay last)
 };
 #undef VB_VARIANT24
+#undef VB_VARIANT_KS
 #undef VB_VARIANT
 
-static Variant* find_variant(int staged, int res, int mod, const int* kinds, int parts) {
+static Variant* find_variant(int staged, int res, int mod, const int* kinds, int parts, int ks = 0) {
   static const bool generic_only = getenv("VB_GENERIC_EPI") != nullptr;       // A/B testing
+  if (ks) {                                           // K-split: exact matches only
+    for (Variant& v : g_variants)
+      if (v.ks && v.staged == staged && v.res == res && v.mod == mod && v.k0 == kinds[0] && v.k1 == kinds[1] && v.k2 == kinds[2]) return &v;
+    return nullptr;
+  }
   for (int pass = 0; pass < 2; ++pass) {              // second pass: the 8-warp form of whatever was asked for
     const int want = pass == 0 ? parts : 2;
     for (Variant& v : g_variants) {
-      if (v.staged != staged || v.parts != want) continue;
+      if (v.ks || v.staged != staged || v.parts != want) continue;
       if (!staged) return &v;
       if (v.res < 0) return &v;
       if (generic_only) continue;
@@ -1469,6 +1578,7 @@ static bool plan_mainloop(ConvKernelParams& p, int budget, bool want_good) {
   p.tap_mode = 0;
   p.b_resident = 0;
   const int kct = p.kc_a + p.kc_b;
+  if (p.ksplit && p.want_res1) return false;          // K-split streams its half of the weights: no resident layouts
   if (p.taps == 1 && p.want_res1) {
     // 1x1 layer with its N tile's weights resident: K x block_n slab + a ring of activation boxes.  The L2 -> shared-memory
     // fill per tile drops from (128 + block_n) x K x 2 bytes to 128 x K x 2 (the fill rate, ~69 B/clk/SM, is what bounds
@@ -1489,7 +1599,7 @@ static bool plan_mainloop(ConvKernelParams& p, int budget, bool want_good) {
     const int a_slot = (a_tx + 1023) / 1024 * 1024;
     const int resident = 9 * kct * p.b_bytes;
     bool ok = false;
-    if (p.n_tiles == 1 && budget - resident >= 3 * a_slot) {
+    if (p.n_tiles == 1 && !p.ksplit && budget - resident >= 3 * a_slot) {
       p.b_resident = 1;
       p.a_slots = std::min(kMaxStages, (budget - resident) / a_slot);
       p.b_slots = 0;
@@ -1573,7 +1683,15 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
   const bool want_rowroll = ((d->tune >> 4) & 3) == 1 || (env_rowroll && ((d->tune >> 4) & 3) == 0 && d->taps == 9 && p.bh == 1 &&
                             p.bw == kBlockM && d->cin_pad == 64 && d->cin2_pad == 0 && d->block_n == 64 && d->cout_pad == 64 &&
                             d->H % 16 == 0 && d->epi_mode == VB_EPI_PLAIN);
-  const int forced_pair = want_rowroll ? 0 : ((d->tune & 3) == 1 ? 0 : ((d->tune & 3) == 2 ? 1 : env_pair));
+  // tune bit 8: K-split over the two CTAs of a cluster (see ConvKernelParams::ksplit).  NOT bitwise-neutral (the K sum is formed as
+  // two partial sums), so callers must decide it from the layer's geometry alone — never from the batch size or a timing.
+  const bool want_ksplit = ((d->tune >> 8) & 1) != 0;
+  VB_REQUIRE(!want_ksplit || (d->ks_ws != nullptr && (p.kc_a + p.kc_b) % 2 == 0 && !want_rowroll && (d->tune & 3) != 2 &&
+                              !((d->tune >> 6) & 1) && d->epi_mode == VB_EPI_PLAIN),
+             "vb_conv: K-split needs ks_ws, an even number of 64-channel blocks, a plain epilogue, and no pair / ping-pong / row-rolling layout");
+  p.ksplit = want_ksplit ? 1 : 0;
+  p.ks_ws = static_cast<float*>(d->ks_ws);
+  const int forced_pair = (want_rowroll || want_ksplit) ? 0 : ((d->tune & 3) == 1 ? 0 : ((d->tune & 3) == 2 ? 1 : env_pair));
   p.tune_tap = want_rowroll ? 0 : (d->tune >> 2) & 3;
   static const int env_res1 = getenv("VB_RES1") ? atoi(getenv("VB_RES1")) : 0;                   // A/B testing
   p.want_res1 = (d->taps == 1 && (((d->tune >> 7) & 1) || env_res1)) ? 1 : 0;
@@ -1657,6 +1775,7 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
                    "vb_conv: the fp32-only epilogue is plain (no residual/modulation/clip)");
     }
     VB_REQUIRE_L(d->out_rnorm == nullptr || needs_norm, "vb_conv: out_rnorm needs a NORM output kind");
+    VB_REQUIRE_L(!want_ksplit || staged, "vb_conv: K-split needs 16-bit staged outputs");
     if (needs_norm || d->res_mode == VB_RES_PIXNORM)
       VB_REQUIRE_L(p.n_tiles == 1, "vb_conv: pixel-norm fusion needs the whole channel extent in one tile (cout_pad %d, block_n %d)",
                    d->cout_pad, d->block_n);
@@ -1673,7 +1792,7 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
       const int opts[4][2] = {{4, 3}, {4, 2}, {2, 3}, {2, 2}};      // {residual ring slots, staging regions}
       // tune bit 6: ping-pong epilogue (two groups, each with its own rings): one-chunk tiles only, two residual slots each
       Variant* egv = find_variant(1, d->res_mode, (d->flags & VB_F_MODSILU) ? 1 : 0, kinds, 1);
-      const bool eg_ok = egv != nullptr && egv->parts == 1 && d->block_n <= 128 && !want_rowroll && d->res_mode != VB_RES_PIXNORM;
+      const bool eg_ok = egv != nullptr && egv->parts == 1 && d->block_n <= 128 && !want_rowroll && !want_ksplit && d->res_mode != VB_RES_PIXNORM;
       VB_REQUIRE_L(eg_ok || !((d->tune >> 6) & 1), "vb_conv: no ping-pong epilogue for this layer (needs block_n == 64 and a specialised variant)");
       const int gslots_all = p.gslots;
       bool want_eg = (((d->tune >> 6) & 1) || env_epi_pp) && eg_ok;
@@ -1688,7 +1807,7 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
       if (want_eg) p.gslots = 1;            // one output per staging slot and commit
       int best[2] = {-1, -1};
       ConvKernelParams best_p[2] = {p, p};
-      for (int pair = 0; pair <= (pair_possible ? 1 : 0); ++pair) {
+      for (int pair = 0; pair <= ((pair_possible && !want_ksplit) ? 1 : 0); ++pair) {
         for (int o = 0; o < 4; ++o) {
           if (forced_regions == 2 && opts[o][1] != 2) continue;
           if (!has_res && opts[o][0] != 4) continue;               // no residual: the ring size is moot
@@ -1782,8 +1901,9 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
 
   // tune bit 6: sixteen epilogue warps (the specialised staged variants only; the row-rolling layout keeps eight)
   const int want_parts = p.eg ? 1 : 2;
-  Variant* var = find_variant(staged ? 1 : 0, p.res_mode, (d->flags & VB_F_MODSILU) ? 1 : 0, kinds, want_parts);
-  VB_REQUIRE_L(var != nullptr, "vb_conv: no kernel variant");
+  Variant* var = find_variant(staged ? 1 : 0, p.res_mode, (d->flags & VB_F_MODSILU) ? 1 : 0, kinds, want_parts, p.ksplit);
+  VB_REQUIRE_L(var != nullptr, p.ksplit ? "vb_conv: K-split is built for single-output (RAW) conv_res0 / conv_res1 epilogues only"
+                                        : "vb_conv: no kernel variant");
   VB_REQUIRE_L(var->parts == want_parts || !((d->tune >> 6) & 1), "vb_conv: no ping-pong epilogue variant for this output combination");
   VB_REQUIRE_L(var->parts == want_parts, "vb_conv: ping-pong epilogue unavailable for this output combination");
   l->fn = var->fn;
@@ -1834,8 +1954,8 @@ int conv_prepare(const vb_conv_desc* d, ConvLaunch** out) {
 
   // The kernel contains cta_group::2 instructions, so the driver only accepts it in clusters of two even when the CTAs work
   // independently (pair == 0): the grid is kept even, a surplus CTA finds no work item and exits.
-  l->grid = p.pair ? std::min(2 * p.total_q, num_sms() & ~1)
-                   : std::min(((p.rowroll ? p.total_q : p.total_tiles) + 1) & ~1, num_sms() & ~1);
+  l->grid = (p.pair || p.ksplit) ? std::min(2 * p.total_q, num_sms() & ~1)
+                                 : std::min(((p.rowroll ? p.total_q : p.total_tiles) + 1) & ~1, num_sms() & ~1);
   if (p.tap_mode == 0 && p.b_resident) {
     // resident 1x1 weights: every CTA must keep ONE N tile -> the work-item stride (CTAs, or pairs) is a multiple of n_tiles
     const int unit = p.n_tiles * (p.pair ? 2 : 1);
@@ -1900,6 +2020,13 @@ extern "C" int vb_debug_conv_stamps(long long* out8) {
   VB_REQUIRE(out8 != nullptr, "vb_debug_conv_stamps: null out");
   VB_CHECK_CUDA(cudaMemcpyFromSymbol(out8, vb::g_conv_ts, 8 * sizeof(long long)));
   return VB_OK;
+}
+
+extern "C" int64_t vb_conv_ksplit_ws_bytes(int32_t B, int32_t H, int32_t W, int32_t cout_pad) {
+  if (B <= 0 || H <= 0 || W <= 0 || cout_pad <= 0) return 0;
+  const int64_t bw = std::min(W, vb::kBlockM), bh = std::min<int64_t>(H, vb::kBlockM / bw), bn = vb::kBlockM / (bw * bh);
+  const int64_t m_tiles = (W / bw) * (H / bh) * ((B + bn - 1) / bn);
+  return m_tiles * vb::kBlockM * cout_pad * 4;
 }
 
 extern "C" int vb_conv(const vb_conv_desc* d, void* stream) {

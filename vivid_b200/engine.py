@@ -54,6 +54,13 @@ AUTOTUNE = os.environ.get("VB_AUTOTUNE", "1") != "0"    # plan-time layout tunin
 _TUNE_CACHE = {}
 FOLD_RES = os.environ.get("VB_FOLD_RES", "1") != "0"    # mp_sum's coefficient of the GEMM result folded into the prepared weights
 FULLROW_MAX = 256          # widest channel count one GEMM tile (and TMEM accumulator buffer) can hold
+# K-split (vb_conv_desc.tune bit 8) for the 3x3 convs of the 8x8 level: two CTAs per tile, each over half of the K loop (72-144
+# blocks).  It changes the summation order, so the rule below looks at the LAYER only (never the batch size or a timing): results
+# stay identical across batch splits and ranks.  Built, parity-tested and measured (profiles/r02_ksplit.txt): the tuner's narrow N
+# tiles already fill the chip at batch >= 32 and the hand-over through L2 costs what the shorter loop saves, so it is faster only
+# at batch <= 8 and 1.1 % SLOWER per vivid-base call at batch 128 — off unless VB_KSPLIT=1.
+KSPLIT = os.environ.get("VB_KSPLIT", "0") == "1"
+KSPLIT_MAX_RES = 8
 
 
 class Plan:
@@ -79,6 +86,7 @@ class Plan:
         self.sm_count = torch.cuda.get_device_properties(device).multi_processor_count
         self.alg_flops = 0.0            # algorithmic (unpadded) FLOPs of one call
         self.weight_versions = None
+        self.ks_ws = None               # fp32 workspace of the K-split convs
         self._build()
 
     def __del__(self):
@@ -229,6 +237,16 @@ class Plan:
                 d.part_out[j] = qkv["out"][j].data_ptr()
                 d.part_seq[j] = qkv["seq"][j]
                 d.part_off[j] = qkv["off"][j]
+        ks = (KSPLIT and taps == 9 and R <= KSPLIT_MAX_RES and ((cin_pad + cin2_pad) // 64) % 2 == 0 and qkv is None
+              and out_f32 is None and len(outs) == 1 and outs[0][1] == L.VB_OUT_RAW and out_rnorm is None
+              and ((res_mode == L.VB_RES_NONE and (flags & L.VB_F_MODSILU))
+                   or (res_mode == L.VB_RES_PLAIN and not (flags & L.VB_F_MODSILU))))
+        if ks:
+            need = self.lib.vb_conv_ksplit_ws_bytes(B, R, R, cout_pad)
+            if self.ks_ws is None or self.ks_ws.numel() * 4 < need:
+                self.ks_ws = self.buf((need // 4,), torch.float32)       # shared by the plan's K-split convs (they replay in order)
+            d.ks_ws = self.ks_ws.data_ptr()
+            d.tune = 256
         if AUTOTUNE:
             key = (B, R, cin_pad, cin2_pad, cout_pad, taps, flags, res_mode, tuple(k for _, k, _ in outs), out_f32 is not None,
                    (qkv["D"], qkv["parts"], qkv.get("seg_div", 1)) if qkv else None, mod is not None)
@@ -243,6 +261,8 @@ class Plan:
                 cands = [(n, t) for n in ns for t in (0, 1, 2)]
                 # ping-pong epilogue (tune bit 6, block_n <= 128): same arithmetic per element, other schedule
                 cands += [(n, t | 64) for n in ns if n <= 128 and outs for t in (0, 1, 2)]
+                if ks:          # K-split layers: single-CTA tiles of either width (the split point does not depend on block_n)
+                    cands = [(n, 256) for n in ns]
                 if taps == 1:
                     # 1x1 layers: the N tile's weights resident per CTA (tune bit 7) — the K order is unchanged as well
                     cands += [(n, t | 128) for n in ns for t in (0, 1, 2)]
