@@ -52,7 +52,7 @@ int vb_spin(int microseconds, void* stream);
  * the previous setting.  Affects launches and graph captures made AFTER the call (measurement aid: with it off, kernel
  * activity records of consecutive kernels do not overlap). */
 int vb_set_pdl(int on);
-/* sizeof() of the descriptor structs below, in declaration order (0 = vb_weight_prep_desc ... 7 = vb_heun_desc, 8 = vb_stats_desc, 9 = vb_f32_conv_desc, 10 = vb_f32_op_desc);
+/* sizeof() of the descriptor structs below, in declaration order (0 = vb_weight_prep_desc ... 7 = vb_heun_desc, 8 = vb_stats_desc, 9 = vb_f32_conv_desc, 10 = vb_f32_op_desc, 11 = vb_io_desc, 12 = vb_sample_desc);
  * lets a foreign-language binding verify its mirror of the layout.  -1 for an unknown index. */
 int vb_struct_size(int which);
 /* vb_dtype of GEMM operands / stream in this build (VB_F16 unless built with -DVB_OP_BF16). */
@@ -417,6 +417,38 @@ int vb_plan_bind_io(vb_plan* p, const vb_io_desc* io);
 int vb_denoise(vb_plan* p, const float* src, const float* x, const float* sigma, int32_t sigma_n, const float* geometry,
                int32_t geometry_rows, const float* cond, const float* noise, float* D_out, void* stream);
 int64_t vb_workspace_bytes(const vb_plan* p);
+
+/* ------------------------------------------------------------------------
+ * Whole-sampler entry point — the Heun loop of edm_sampler (generate_images.py:72-118, deterministic branch: S_churn = 0;
+ * snapshot experiments/code/generate_images.py:58-91) over plans with bound I/O, for any host:
+ *   x = noise * t_0;  per step:  d = (x - D(x; t_i)) / t_i,  x' = x + (t_{i+1} - t_i) d,  and unless t_{i+1} = 0 the 2nd-order
+ *   correction with D(x'; t_{i+1});  D = lerp(D_gnet, D_net, guidance) when guidance != 1 (autoguidance, :57-62).
+ * vb_plan_set_inputs uploads what stays constant over a sampler call (source views, pose vectors, SR conditioning image) into
+ * the plan's buffers once; vb_sample then enqueues 2*num_steps - 1 graph replays per net with a vb_heun pass after each, whose
+ * outputs are the next replay's x / sigma inputs.  Nothing synchronises with the host.
+ * ------------------------------------------------------------------------ */
+int vb_plan_set_inputs(vb_plan* p, const float* src, const float* geometry /* or NULL: zeros */, int32_t geometry_rows /* 1 or n_x */,
+                       const float* cond /* super_res only */, void* stream);
+/* super_res plans: fills dst[0..n) with N(0,1) samples on `stream` before every call of the net (the reference draws them
+ * with torch.randn_like from the global generator, experiments/code/training/models.py:608-611); returns 0 on success. */
+typedef int (*vb_noise_fn)(void* user, float* dst, int64_t n, void* stream);
+typedef struct vb_sample_desc {
+  vb_plan* net;           /* plan of the main net */
+  vb_plan* gnet;          /* plan of the guiding net (same batch / resolution, not super_res); ignored when guidance == 1 */
+  const float* noise;     /* DEVICE [B,3,R,R]: N(0,1) latents (generate_images.py:299-300) */
+  const float* t_steps;   /* HOST [num_steps + 1]: the noise levels, t_steps[num_steps] = 0 (generate_images.py:68-70) */
+  float* workspace;       /* DEVICE, vb_sample_workspace_bytes(net) bytes */
+  float* x_out;           /* DEVICE [B,3,R,R]: the sample */
+  vb_noise_fn sr_noise;   /* required for super_res plans */
+  void* sr_noise_user;
+  void* side_stream;      /* optional second stream for the guiding net's replays (joined before every update) */
+  int32_t num_steps;
+  int32_t net_first_op;   /* 0, or the first op after the source-view encoder when the caller has run it once (no_time_enc nets,
+                           * generate_images.py:52-57) */
+  float guidance;
+} vb_sample_desc;
+int64_t vb_sample_workspace_bytes(const vb_plan* p);
+int vb_sample(const vb_sample_desc* d, void* stream);
 
 #ifdef __cplusplus
 }

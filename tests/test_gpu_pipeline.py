@@ -390,3 +390,84 @@ def test_vb_denoise_whole_call_entry_point(env, name, B):
     assert lib.vb_denoise(plan.handle, src.data_ptr(), x.data_ptr(), sigma.data_ptr(), n_x + 1, None, 0, L.ptr(cond), L.ptr(noise),
                           out.data_ptr(), st) != 0
     assert b"sigma_n" in lib.vb_last_error()
+
+
+# ------------------------------------------------------------------------------- whole-sampler C entry point
+def _small_net(case, dev):
+    import vivid_b200
+    cfg = cases.CASES[case]["cfg"]
+    net = vivid_b200.NVPrecond(**cfg)
+    net.load_state_dict(cases.synth_state_dict([(k, tuple(v.shape)) for k, v in net.state_dict().items()]))
+    return net.to(dev).eval()
+
+
+@pytest.mark.parametrize("kind", ["guided", "guided_one_stream", "unguided", "sr", "two_steps"])
+def test_vb_sample_whole_sampler_entry_point(env, monkeypatch, kind):
+    """vb_sample (include/vivid_b200.h; SURVEY.md 8(b) `vb_sample`) enqueues the Heun loop of edm_sampler
+    (generate_images.py:72-118) from C over bound plans.  edm_sampler routes through it; it must be bit-identical to the
+    Python loop (VB_C_SAMPLER=0: the same replays and vb_heun passes issued from Python), incl. the guiding net on a second
+    stream and the SR net's per-call draw from the global generator (experiments/code/training/models.py:608-611) — and
+    callable with plain device pointers after vb_plan_set_inputs."""
+    import ctypes as C
+    import vivid_b200
+    L, lib, dev = env
+    B, steps = 2, 2 if kind == "two_steps" else 4        # (num_steps = 1 is 0/0 in the reference's schedule, generate_images.py:69)
+    sr = kind == "sr"
+    net = _small_net("v_sr" if sr else "v_cond", dev)
+    gnet = _small_net("v_uncond", dev) if kind.startswith("guided") else None
+    inp = {k: v.to(dev) for k, v in cases.synth_inputs("v_sr" if sr else "v_cond", B).items()}
+    kw = dict(labels=inp["geometry"], num_steps=steps, guidance=1.7 if gnet is not None else 1,
+              conditioning_image=inp["tgt"] if sr else None, gnet=gnet)
+    if kind == "guided_one_stream":
+        monkeypatch.setenv("VB_DUAL_STREAM", "0")
+
+    def run(c_loop):
+        monkeypatch.setenv("VB_C_SAMPLER", "1" if c_loop else "0")
+        torch.manual_seed(21)
+        return vivid_b200.edm_sampler(net, inp["src"], inp["noise"], **kw).clone()
+
+    want = run(False)
+    got = run(True)
+    assert torch.isfinite(got).all() and torch.equal(got, want)
+    # the traced Python loop (what the per-step parity tests observe) is the same computation
+    trace = []
+    torch.manual_seed(21)
+    assert torch.equal(vivid_b200.edm_sampler(net, inp["src"], inp["noise"], _trace=trace, **kw), want)
+    assert len(trace) == 2 * steps - 1
+
+    # raw-pointer call, as a non-Python host would make it
+    from vivid_b200.sampler import sigma_steps
+    plan = net.plan(B, dev)
+    st = torch.cuda.current_stream().cuda_stream
+    geom = inp["geometry"].to(torch.float32).contiguous()
+    L.check(lib.vb_plan_set_inputs(plan.handle, inp["src"].data_ptr(), geom.data_ptr(), B, inp["tgt"].data_ptr() if sr else None, st),
+            "vb_plan_set_inputs")
+    gplan = gnet.plan(B, dev) if gnet is not None else None
+    if gplan is not None:
+        L.check(lib.vb_plan_set_inputs(gplan.handle, inp["src"].data_ptr(), None, 0, None, st), "vb_plan_set_inputs")
+    t = sigma_steps(steps, 0.002, 80, 7, dev).tolist()
+    ws = torch.empty(lib.vb_sample_workspace_bytes(plan.handle) // 4, device=dev)
+    assert ws.numel() == 3 * inp["noise"].numel()
+    out = torch.full_like(inp["noise"], float("nan"))
+    draws = []
+
+    def draw(user, dst, n, stream):
+        draws.append(n)
+        plan.in_noise.normal_()
+        return 0
+    d = L.SampleDesc(net=plan.handle, gnet=gplan.handle if gplan is not None else None, noise=inp["noise"].data_ptr(),
+                     t_steps=(C.c_float * len(t))(*t), workspace=ws.data_ptr(), x_out=out.data_ptr(), num_steps=steps,
+                     net_first_op=0, guidance=kw["guidance"])
+    if sr:
+        d.sr_noise = L.NOISE_FN(draw)
+    torch.manual_seed(21)
+    L.check(lib.vb_sample(C.byref(d), st), "vb_sample")
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+    assert len(draws) == (2 * steps - 1 if sr else 0)
+    # argument errors come back as codes
+    d.num_steps = 0
+    assert lib.vb_sample(C.byref(d), st) != 0 and b"num_steps" in lib.vb_last_error()
+    if sr:
+        d.num_steps, d.sr_noise = steps, L.NOISE_FN(0)
+        assert lib.vb_sample(C.byref(d), st) != 0 and b"sr_noise" in lib.vb_last_error()

@@ -293,5 +293,21 @@ def test_whole_call_entry_point_argument_validation(lib):
         assert lib.vb_denoise(plan, None, None, None, 1, None, 0, None, None, None, None) != 0
         assert b"required" in lib.vb_last_error()
         assert lib.vb_plan_bind_io(None, C.byref(io)) != 0
+        # whole-sampler entry point: same rules
+        assert lib.vb_sample_workspace_bytes(plan) == 3 * 2 * 12 * 4 and lib.vb_sample_workspace_bytes(None) == 0
+        unbound = C.c_void_p()
+        assert lib.vb_plan_create(C.byref(unbound)) == 0
+        d = L.SampleDesc(net=unbound, noise=8, workspace=8, x_out=8, num_steps=2, guidance=1.0)
+        assert lib.vb_sample(C.byref(d), None) != 0 and b"bound I/O" in lib.vb_last_error()
+        assert lib.vb_plan_set_inputs(unbound, None, None, 0, None, None) != 0 and b"bound" in lib.vb_last_error()
+        lib.vb_plan_destroy(unbound)
+        d.net = plan
+        assert lib.vb_sample(C.byref(d), None) != 0 and b"t_steps" in lib.vb_last_error()
+        d.t_steps = (C.c_float * 3)(80.0, 1.0, 0.0)
+        d.guidance = 2.0
+        assert lib.vb_sample(C.byref(d), None) != 0 and b"gnet" in lib.vb_last_error()
+        d.guidance, d.num_steps = 1.0, 0
+        assert lib.vb_sample(C.byref(d), None) != 0 and b"num_steps" in lib.vb_last_error()
+        assert lib.vb_plan_set_inputs(plan, None, 8, 3, None, None) != 0 and b"geometry_rows" in lib.vb_last_error()
     finally:
         lib.vb_plan_destroy(plan)

@@ -1,6 +1,6 @@
-"""Per-denoiser-call latency inside edm_sampler at small batch: the zero-copy loop (plan buffers written
-by vb_heun, constant inputs uploaded once) against the generic loop (host copies + clone per call), guided base stage and SR
-stage, 32 Heun steps.  usage: python tools/sampler_latency.py [batches=2,8]"""
+"""Per-denoiser-call latency inside edm_sampler at small batch: the whole loop enqueued from C (vb_sample),
+the zero-copy Python loop (plan buffers written by vb_heun, constant inputs uploaded once) and the generic loop (host copies +
+clone per call), guided base stage and SR stage, 32 Heun steps.  usage: python tools/sampler_latency.py [batches=2,8]"""
 import os
 import sys
 import time
@@ -17,7 +17,7 @@ dev = torch.device("cuda")
 net, gnet, sr = (bench.make_net(n, i, dev) for i, n in enumerate(("vivid-base", "vivid-uncond", "vivid-sr")))
 print("# ms per denoiser call inside edm_sampler (32 Heun steps = 63 calls; guided: net + gnet per call), wall clock around a "
       "synchronised sampler call, best of 3")
-print(f"{'stage':22s} {'B':>3s} {'zero-copy loop':>15s} {'generic loop':>13s} {'graph replay only':>18s}")
+print(f"{'stage':22s} {'B':>3s} {'vb_sample (C loop)':>19s} {'zero-copy loop (Python)':>24s} {'generic loop':>13s} {'graph replay only':>18s}")
 for B in [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "2,8").split(",")]:
     lo, hi = synth_batch(range(B), 64), synth_batch(range(B), 256)
     src, geom = (lo["src_image"] / 127.5 - 1).to(dev), lo["geometry"].to(dev)
@@ -33,8 +33,9 @@ for B in [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "2,8").split(",
     }
     for name, (fn, plans) in stages.items():
         res = []
-        for bound in ("1", "0"):
+        for bound, c_loop in (("1", "1"), ("1", "0"), ("0", "0")):
             os.environ["VB_BOUND_SAMPLER"] = bound
+            os.environ["VB_C_SAMPLER"] = c_loop
             fn()
             best = 1e9
             for _ in range(3):
@@ -51,5 +52,6 @@ for B in [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "2,8").split(",
                 p.run(graph=True)
         e1.record()
         torch.cuda.synchronize()
-        print(f"{name:22s} {B:3d} {res[0]:15.3f} {res[1]:13.3f} {e0.elapsed_time(e1) / 20:18.3f}")
+        print(f"{name:22s} {B:3d} {res[0]:19.3f} {res[1]:24.3f} {res[2]:13.3f} {e0.elapsed_time(e1) / 20:18.3f}")
 os.environ.pop("VB_BOUND_SAMPLER", None)
+os.environ.pop("VB_C_SAMPLER", None)

@@ -97,6 +97,15 @@ class IoDesc(C.Structure):
                 ("n_x", i64), ("n_out", i64), ("img_elems", i64), ("geom_dim", i64), ("workspace_bytes", i64)]
 
 
+NOISE_FN = C.CFUNCTYPE(C.c_int, vp, vp, i64, vp)      # vb_noise_fn(user, dst, n, stream)
+
+
+class SampleDesc(C.Structure):
+    _fields_ = [("net", vp), ("gnet", vp), ("noise", vp), ("t_steps", C.POINTER(C.c_float)), ("workspace", vp), ("x_out", vp),
+                ("sr_noise", NOISE_FN), ("sr_noise_user", vp), ("side_stream", vp), ("num_steps", i32), ("net_first_op", i32),
+                ("guidance", f32)]
+
+
 SIGNATURES = {
     "vb_last_error": (C.c_char_p, []),
     "vb_abi_version": (C.c_int, []),
@@ -142,9 +151,12 @@ SIGNATURES = {
     "vb_plan_bind_io": (C.c_int, [vp, C.POINTER(IoDesc)]),
     "vb_denoise": (C.c_int, [vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, vp]),
     "vb_workspace_bytes": (C.c_int64, [vp]),
+    "vb_plan_set_inputs": (C.c_int, [vp, vp, vp, i32, vp, vp]),
+    "vb_sample_workspace_bytes": (C.c_int64, [vp]),
+    "vb_sample": (C.c_int, [C.POINTER(SampleDesc), vp]),
 }
 
-STRUCTS = [WeightPrepDesc, ConvDesc, AttnDesc, EwDesc, EmbDesc, PrecondInDesc, PrecondOutDesc, HeunDesc, StatsDesc, F32ConvDesc, F32OpDesc, IoDesc]
+STRUCTS = [WeightPrepDesc, ConvDesc, AttnDesc, EwDesc, EmbDesc, PrecondInDesc, PrecondOutDesc, HeunDesc, StatsDesc, F32ConvDesc, F32OpDesc, IoDesc, SampleDesc]
 
 _lib = None
 

@@ -161,6 +161,7 @@ extern "C" int vb_struct_size(int which) {
     case 9: return static_cast<int>(sizeof(vb_f32_conv_desc));
     case 10: return static_cast<int>(sizeof(vb_f32_op_desc));
     case 11: return static_cast<int>(sizeof(vb_io_desc));
+    case 12: return static_cast<int>(sizeof(vb_sample_desc));
     default: return -1;
   }
 }

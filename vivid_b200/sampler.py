@@ -118,6 +118,35 @@ class _Bound:
         return self.p.out_d
 
 
+def _sample_c(lib, bn, bg, noise, t_steps, guidance, side, cur):
+    """vb_sample over the bound plans.  SR nets draw their per-call conditioning noise through a callback that runs the
+    reference's own draw (normal_() on the plan's buffer == torch.randn_like from the global generator)."""
+    p = bn.p
+    ws = torch.empty(lib.vb_sample_workspace_bytes(p.handle) // 4, dtype=torch.float32, device=noise.device)
+    out = torch.empty_like(noise)
+    failure = []
+
+    def draw(user, dst, n, stream):
+        try:
+            assert dst == p.in_noise.data_ptr() and n == p.in_noise.numel()
+            p.in_noise.normal_()
+            return 0
+        except BaseException as e:      # never let an exception cross the C frame
+            failure.append(e)
+            return -1
+    d = L.SampleDesc(net=p.handle, gnet=bg.p.handle if bg is not None else None, noise=noise.data_ptr(),
+                     t_steps=(C.c_float * len(t_steps))(*t_steps), workspace=ws.data_ptr(), x_out=out.data_ptr(),
+                     side_stream=side.cuda_stream if side is not None else None, num_steps=len(t_steps) - 1,
+                     net_first_op=p.enc_ops if bn.section == "unet" else 0, guidance=float(guidance))
+    if bn.net.super_res:
+        d.sr_noise = L.NOISE_FN(draw)
+    rc = lib.vb_sample(C.byref(d), cur.cuda_stream)
+    if failure:
+        raise failure[0]
+    L.check(rc, "vb_sample")
+    return out
+
+
 def _edm_sampler_bound(net, src, noise, labels, gnet, cond, num_steps, sigma_min, sigma_max, rho, guidance, dtype, trace):
     lib = L.lib()
     dev = noise.device
@@ -132,13 +161,17 @@ def _edm_sampler_bound(net, src, noise, labels, gnet, cond, num_steps, sigma_min
     bounds = [bn] + ([bg] if guided else [])
     x_in = [b.p.in_x for b in bounds]
     sig_in = [b.p.in_sigma for b in bounds]
+    side = _side_stream(dev) if guided and os.environ.get("VB_DUAL_STREAM", "1") != "0" else None
+    cur = torch.cuda.current_stream(dev)
+    if trace is None and os.environ.get("VB_C_SAMPLER", "1") != "0" and all(b.net.use_graph for b in bounds):
+        # the whole loop in the library (vb_sample: the same graph replays and vb_heun passes, enqueued from C) — what a
+        # non-Python host would call; the Python loop below is the same sequence and stays for tracing / eager replay
+        return _sample_c(lib, bn, bg, noise.to(dtype).contiguous(), t_steps, guidance, side, cur)
     x_hat = (noise.to(dtype) * t_dev[0]).contiguous()
     x_next, d_cur = torch.empty_like(x_hat), torch.empty_like(x_hat)
     for b in bounds:
         b.p.in_x.copy_(x_hat)
         b.p.in_sigma.fill_(t_steps[0])
-    side = _side_stream(dev) if guided and os.environ.get("VB_DUAL_STREAM", "1") != "0" else None
-    cur = torch.cuda.current_stream(dev)
 
     def denoise():
         if side is None:
