@@ -52,7 +52,7 @@ int vb_spin(int microseconds, void* stream);
  * the previous setting.  Affects launches and graph captures made AFTER the call (measurement aid: with it off, kernel
  * activity records of consecutive kernels do not overlap). */
 int vb_set_pdl(int on);
-/* sizeof() of the descriptor structs below, in declaration order (0 = vb_weight_prep_desc ... 7 = vb_heun_desc, 8 = vb_stats_desc, 9 = vb_f32_conv_desc, 10 = vb_f32_op_desc, 11 = vb_io_desc, 12 = vb_sample_desc);
+/* sizeof() of the descriptor structs below, in declaration order (0 = vb_weight_prep_desc ... 7 = vb_heun_desc, 8 = vb_stats_desc, 9 = vb_f32_conv_desc, 10 = vb_f32_op_desc, 11 = vb_io_desc, 12 = vb_sample_desc, 13 = vb_unet_desc, 14 = vb_net_desc, 15 = vb_param);
  * lets a foreign-language binding verify its mirror of the layout.  -1 for an unknown index. */
 int vb_struct_size(int which);
 /* vb_dtype of GEMM operands / stream in this build (VB_F16 unless built with -DVB_OP_BF16). */
@@ -449,6 +449,62 @@ typedef struct vb_sample_desc {
 } vb_sample_desc;
 int64_t vb_sample_workspace_bytes(const vb_plan* p);
 int vb_sample(const vb_sample_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Plan recording inside the library (a plan created from a net description plus a name -> pointer table of
+ * the weights).
+ * vb_net_plan_create walks the reference's network topology itself — UNet / XAttnUNet / SRXAttnUNet / UNetEncoder
+ * constructors, training/models.py:340-383, 438-480, 523-534, 575-582; NVPrecond.forward :628-689 (snapshot
+ * experiments/code/training/models.py:581-638) — from a description of the constructor arguments and a table of the
+ * parameters under their reference state_dict names, prepares the weights (vb_weight_prep), allocates every buffer,
+ * tunes and records the ops and binds the I/O, so that a host without Python can go from a checkpoint to vb_denoise /
+ * vb_sample.  It records the same op sequence as vivid_b200/engine.py (tests/test_netplan.py compares the two op for op).
+ * ------------------------------------------------------------------------ */
+typedef struct vb_unet_desc {
+  int32_t img_resolution;
+  int32_t in_channels;    /* img_channels + 1 (the ones channel), + img_channels more for the SR UNet's conditioning image */
+  int32_t out_channels;   /* 3; 0 = UNetEncoder (no out_conv, trailing decoder blocks without attention dropped, :523-534) */
+  int32_t model_channels;
+  int32_t num_levels;
+  int32_t channel_mult[8];
+  int32_t num_blocks;
+  int32_t num_attn_res;
+  int32_t attn_resolutions[8];
+  int32_t extra_attn;     /* block slot that gets attention on every level but the first; -1 = none */
+  int32_t channels_per_head;
+  int32_t xattn;          /* attention blocks also attend to the source-view features (XAttnBlock) */
+  int32_t label_dim;
+  int32_t cnoise, cemb;   /* widths of the noise embedding and of the block modulation vector */
+  double label_balance, concat_balance, res_balance, attn_balance;
+  double clip_act;        /* < 0: no clipping */
+} vb_unet_desc;
+typedef struct vb_net_desc {
+  vb_unet_desc unet;      /* parameters under "unet." */
+  vb_unet_desc encoder;   /* parameters under "encoder."; ignored unless has_encoder */
+  int32_t has_encoder;    /* 0 for uncond nets */
+  int32_t img_resolution;
+  int32_t uncond, super_res, dual_source, no_time_enc;
+  double sigma_data, noisy_sr;
+} vb_net_desc;
+typedef struct vb_param {
+  const char* name;       /* reference state_dict key, e.g. "unet.enc.64x64_block0.conv_res0.weight" */
+  const void* data;       /* DEVICE pointer, contiguous */
+  int32_t dtype;          /* VB_F32 or VB_F16 (persisted EMA snapshots are fp16) */
+  int32_t ndim;
+  int64_t shape[4];
+} vb_param;
+/* Records the plan of one denoiser call for `batch` target images.  The plan owns its device buffers (freed by
+ * vb_plan_destroy); the parameter tensors are read once (weights are normalised, scaled, rounded and repacked into the plan) and
+ * need not outlive the call.  Synchronises `stream` (layout tuning times candidate launches). */
+int vb_net_plan_create(const vb_net_desc* net, const vb_param* params, int32_t n_params, int32_t batch, void* stream, vb_plan** out);
+/* The plan's persistent I/O buffers (vb_plan_bind_io's descriptor) and the index of the first op after the source-view encoder. */
+int vb_plan_get_io(const vb_plan* p, vb_io_desc* out, int32_t* enc_ops);
+/* Dry run of the recording, with no device: writes one text line per buffer allocation, weight preparation and recorded op —
+ * pointers canonicalised as buffer-id/offset and parameter-index/offset — into buf (NUL-terminated, truncated to cap) and returns
+ * the full length, or a negative status.  vb_trace_desc formats one descriptor the same way (kind: 0 weight_prep, 1 conv,
+ * 2 attn, 3 eltwise, 4 embed, 5 precond_in, 6 precond_out, 7 io): the op-for-op comparison with another recorder. */
+int64_t vb_net_plan_trace(const vb_net_desc* net, const vb_param* params, int32_t n_params, int32_t batch, char* buf, int64_t cap);
+int64_t vb_trace_desc(int32_t kind, const void* desc, char* buf, int64_t cap);
 
 #ifdef __cplusplus
 }

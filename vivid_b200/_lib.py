@@ -106,6 +106,23 @@ class SampleDesc(C.Structure):
                 ("guidance", f32)]
 
 
+class UNetDesc(C.Structure):
+    _fields_ = [("img_resolution", i32), ("in_channels", i32), ("out_channels", i32), ("model_channels", i32), ("num_levels", i32),
+                ("channel_mult", i32 * 8), ("num_blocks", i32), ("num_attn_res", i32), ("attn_resolutions", i32 * 8),
+                ("extra_attn", i32), ("channels_per_head", i32), ("xattn", i32), ("label_dim", i32), ("cnoise", i32), ("cemb", i32),
+                ("label_balance", C.c_double), ("concat_balance", C.c_double), ("res_balance", C.c_double),
+                ("attn_balance", C.c_double), ("clip_act", C.c_double)]
+
+
+class NetDesc(C.Structure):
+    _fields_ = [("unet", UNetDesc), ("encoder", UNetDesc), ("has_encoder", i32), ("img_resolution", i32), ("uncond", i32),
+                ("super_res", i32), ("dual_source", i32), ("no_time_enc", i32), ("sigma_data", C.c_double), ("noisy_sr", C.c_double)]
+
+
+class Param(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", vp), ("dtype", i32), ("ndim", i32), ("shape", i64 * 4)]
+
+
 SIGNATURES = {
     "vb_last_error": (C.c_char_p, []),
     "vb_abi_version": (C.c_int, []),
@@ -154,9 +171,13 @@ SIGNATURES = {
     "vb_plan_set_inputs": (C.c_int, [vp, vp, vp, i32, vp, vp]),
     "vb_sample_workspace_bytes": (C.c_int64, [vp]),
     "vb_sample": (C.c_int, [C.POINTER(SampleDesc), vp]),
+    "vb_net_plan_create": (C.c_int, [C.POINTER(NetDesc), C.POINTER(Param), i32, i32, vp, C.POINTER(vp)]),
+    "vb_plan_get_io": (C.c_int, [vp, C.POINTER(IoDesc), C.POINTER(i32)]),
+    "vb_net_plan_trace": (C.c_int64, [C.POINTER(NetDesc), C.POINTER(Param), i32, i32, C.c_char_p, i64]),
+    "vb_trace_desc": (C.c_int64, [i32, vp, C.c_char_p, i64]),
 }
 
-STRUCTS = [WeightPrepDesc, ConvDesc, AttnDesc, EwDesc, EmbDesc, PrecondInDesc, PrecondOutDesc, HeunDesc, StatsDesc, F32ConvDesc, F32OpDesc, IoDesc, SampleDesc]
+STRUCTS = [WeightPrepDesc, ConvDesc, AttnDesc, EwDesc, EmbDesc, PrecondInDesc, PrecondOutDesc, HeunDesc, StatsDesc, F32ConvDesc, F32OpDesc, IoDesc, SampleDesc, UNetDesc, NetDesc, Param]
 
 _lib = None
 

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvividb200.so")
-SOURCES = ["core.cu", "weights.cu", "conv_gemm.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "metrics.cu", "f32path.cu", "plan.cu"]
+SOURCES = ["core.cu", "weights.cu", "conv_gemm.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "metrics.cu", "f32path.cu", "plan.cu", "netplan.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

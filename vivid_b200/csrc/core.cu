@@ -162,6 +162,9 @@ extern "C" int vb_struct_size(int which) {
     case 10: return static_cast<int>(sizeof(vb_f32_op_desc));
     case 11: return static_cast<int>(sizeof(vb_io_desc));
     case 12: return static_cast<int>(sizeof(vb_sample_desc));
+    case 13: return static_cast<int>(sizeof(vb_unet_desc));
+    case 14: return static_cast<int>(sizeof(vb_net_desc));
+    case 15: return static_cast<int>(sizeof(vb_param));
     default: return -1;
   }
 }

@@ -5,42 +5,10 @@
 #include <vector>
 
 #include "common.h"
+#include "plan.h"
 
-namespace {
-
-enum OpKind { OP_CONV, OP_ATTN, OP_EW, OP_EMB, OP_PIN, OP_POUT, OP_HEUN };
-
-struct Op {
-  OpKind kind;
-  vb::ConvLaunch* conv = nullptr;
-  union {
-    vb_attn_desc attn;
-    vb_ew_desc ew;
-    vb_emb_desc emb;
-    vb_precond_in_desc pin;
-    vb_precond_out_desc pout;
-    vb_heun_desc heun;
-  };
-  Op() { memset(&emb, 0, sizeof(emb)); }
-};
-
-}  // namespace
-
-struct vb_plan {
-  std::vector<Op> ops;
-  double flops = 0.0;
-  int launches = 0;
-  // one instantiated graph per replayed op range: the whole plan, and -- for no_time_enc feature caching
-  // (generate_images.py:52-57) -- the source-view encoder and the denoising UNet on their own
-  struct Range {
-    int first, last;
-    cudaGraph_t graph;
-    cudaGraphExec_t exec;
-  };
-  std::vector<Range> graphs;
-  vb_io_desc io;
-  bool io_bound = false;
-};
+typedef vb_op Op;
+typedef vb_op_kind OpKind;
 
 // chained: op i-1 of the same plan was launched into the stream right before (see vb::conv_launch)
 static int run_op(const Op& op, cudaStream_t s, bool chained) {
@@ -76,6 +44,7 @@ extern "C" void vb_plan_destroy(vb_plan* p) {
   drop_graph(p);
   for (Op& op : p->ops)
     if (op.conv) vb::conv_free(op.conv);
+  for (void* b : p->owned) cudaFree(b);
   delete p;
 }
 

@@ -111,6 +111,13 @@ class Plan:
         t = free.pop() if free else self.buf((rows * ch,), self.op_dtype)
         return t.view(rows, ch)
 
+    def to_f32(self, dst, src):
+        """dst = float(src): the MPFourier buffers (fp16 in persisted snapshots)."""
+        dst.copy_(src.detach().float())
+
+    def fill(self, dst, value):
+        dst.fill_(value)
+
     def release(self, *tensors):
         for t in tensors:
             if t is not None:
@@ -120,8 +127,9 @@ class Plan:
         return self.act(B * R * R, ch)
 
     # ------------------------------------------------------------------ weights
-    def prep_weight(self, w, gain=1.0, cout_pad=None, perm=(0, 0), split=None, scales=(1.0, 1.0), fp32=False):
-        """vb_weight_prep: normalise (fp32) + gain + pack; returns the device tensor."""
+    def prep_weight(self, w, gain=1.0, cout_pad=None, perm=(0, 0), split=None, scales=(1.0, 1.0), fp32=False, dst=None):
+        """vb_weight_prep: normalise (fp32) + gain + pack; returns the device tensor.  dst (fp32 only): write there instead of
+        into a new buffer (the rows of a stacked matrix)."""
         w = w.detach()
         if not w.is_contiguous():
             w = w.contiguous()
@@ -129,7 +137,9 @@ class Plan:
         taps = w.shape[2] * w.shape[3] if w.ndim == 4 else 1
         split = cin if split is None else split
         if fp32:
-            dst = self.buf((cout, cin * taps), torch.float32)
+            if dst is None:
+                dst = self.buf((cout, cin * taps), torch.float32)
+            assert dst.dtype == torch.float32 and dst.is_contiguous() and dst.numel() == cout * cin * taps
             d = L.WeightPrepDesc(src=w.data_ptr(), dst=dst.data_ptr(), src_dtype=_DT[w.dtype], dst_dtype=L.VB_F32,
                                  cout=cout, cin=cin, taps=taps, cout_pad=cout, split=cin, seg_a_pad=cin, seg_b_pad=0,
                                  perm_parts=0, perm_dim=0, gain=float(gain), scale_a=1.0, scale_b=1.0)
@@ -311,14 +321,13 @@ class Plan:
         w_mod = self.buf((total, unet.cemb), torch.float32)
         for s, m in blocks:
             o = offs[(s.group, s.name)]
-            wp = self.prep_weight(m.emb_linear.weight, gain=float(m.emb_gain.detach().float().item()), fp32=True)
-            w_mod[o:o + s.cout].copy_(wp)
+            self.prep_weight(m.emb_linear.weight, gain=float(m.emb_gain.detach().float().item()), fp32=True, dst=w_mod[o:o + s.cout])
         w_noise = self.prep_weight(unet.emb_noise.weight, fp32=True)
         w_label = self.prep_weight(unet.emb_label.weight, fp32=True) if unet.emb_label is not None else None
         freqs = self.buf((unet.cnoise,), torch.float32)
         phases = self.buf((unet.cnoise,), torch.float32)
-        freqs.copy_(unet.emb_fourier.freqs.detach().float())
-        phases.copy_(unet.emb_fourier.phases.detach().float())
+        self.to_f32(freqs, unet.emb_fourier.freqs)
+        self.to_f32(phases, unet.emb_fourier.phases)
         emb = self.buf((B, unet.cemb), torch.float32)
         mod = self.buf((B, total), torch.float32)
         d = L.EmbDesc(sigma=sigma.data_ptr(), geom=L.ptr(geom), freqs=freqs.data_ptr(), phases=phases.data_ptr(),
@@ -549,7 +558,7 @@ class Plan:
         self.in_x = self.buf((Bx, 3, R, R), torch.float32, zero=True)
         self.in_src = self.buf((Bx, 3, R, R), torch.float32, zero=True) if net.encoder is not None else None
         self.in_sigma = self.buf((Bx,), torch.float32)
-        self.in_sigma.fill_(1.0)
+        self.fill(self.in_sigma, 1.0)
         ldim_enc = net.encoder.label_dim if net.encoder is not None else 0
         ldim_unet = net.unet.label_dim
         self.in_geom = self.buf((Bx, max(ldim_enc, ldim_unet // (2 if self.dual else 1), 1)), torch.float32, zero=True)

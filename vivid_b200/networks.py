@@ -151,6 +151,8 @@ class UNet(torch.nn.Module):
                                        channels_per_head, xattn)
         self.img_resolution = img_resolution
         self.label_dim = label_dim
+        self.model_channels, self.channel_mult, self.num_blocks = model_channels, list(channel_mult), num_blocks
+        self.attn_resolutions, self.extra_attn = list(attn_resolutions), extra_attn
         self.cnoise = model_channels * channel_mult_noise if channel_mult_noise is not None else widths[0]
         self.cemb = model_channels * channel_mult_emb if channel_mult_emb is not None else max(widths)
         self.label_balance = label_balance
