@@ -311,3 +311,21 @@ def test_whole_call_entry_point_argument_validation(lib):
         assert lib.vb_plan_set_inputs(plan, None, 8, 3, None, None) != 0 and b"geometry_rows" in lib.vb_last_error()
     finally:
         lib.vb_plan_destroy(plan)
+
+
+def test_c_host_example_compiles_against_the_header():
+    """examples/sample_from_c.c (the INTEGRATION.md snippet: checkpoint -> vb_net_plan_create -> vb_plan_set_inputs -> vb_sample)
+    is valid C against include/vivid_b200.h — the header is plain C: no torch, no C++ in the signatures."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    cuda_inc = "/usr/local/cuda/include"
+    if gcc is None or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("gcc or the CUDA headers are not installed")
+    snippet = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    src = open(os.path.join(ROOT, "examples", "sample_from_c.c")).read()
+    body = src[src.index('#include "vivid_b200.h"'):]
+    assert body.strip() in snippet, "examples/sample_from_c.c and the INTEGRATION.md snippet have diverged"
+    r = subprocess.run([gcc, "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-I", cuda_inc,
+                        os.path.join(ROOT, "examples", "sample_from_c.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
