@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -341,7 +342,8 @@ struct ConvArgs {
 };
 
 typedef std::vector<long long> TuneKey;
-std::map<TuneKey, std::pair<int, int>> g_tune_cache;
+std::map<TuneKey, std::pair<int, int>> g_tune_cache;      // process-wide, like engine._TUNE_CACHE; guarded: plans may be recorded
+std::mutex g_tune_mutex;                                  // from several host threads (one per device) at once
 
 struct Recorder {
   const vb_net_desc& net;
@@ -706,8 +708,15 @@ struct Recorder {
         key.push_back(a.qkv->parts);
         key.push_back(a.qkv->seg_div);
       }
+      key.push_back(vb::current_device());                 // a timing belongs to the device it was taken on
+      std::unique_lock<std::mutex> lock(g_tune_mutex);
       auto it = g_tune_cache.find(key);
-      if (it == g_tune_cache.end()) {
+      std::pair<int, int> choice;
+      if (it != g_tune_cache.end()) {
+        choice = it->second;
+        lock.unlock();
+      } else {
+        lock.unlock();                                     // (timing runs unlocked: another thread may time the same layer; both results are legal)
         std::vector<int> ns = {bn};
         if (!fullrow)
           for (int n : {256, 192, 128, 64, 32, 16})
@@ -733,10 +742,13 @@ struct Recorder {
               if (n <= 128)
                 for (int t = 0; t < 3; ++t) cands.emplace_back(n, t | 64 | 128);
         }
-        it = g_tune_cache.emplace(key, tune_conv(d, cands)).first;
+        choice = tune_conv(d, cands);
+        lock.lock();
+        g_tune_cache.emplace(key, choice);
+        lock.unlock();
       }
-      d.block_n = it->second.first;
-      d.tune = it->second.second;
+      d.block_n = choice.first;
+      d.tune = choice.second;
     }
     emit(1, &d);
   }
