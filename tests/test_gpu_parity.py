@@ -241,6 +241,43 @@ def test_conv_ksplit(env, B, R, cin, cin2, cout, bn, modsilu, res_mode):
         assert torch.equal(run(B, 256, bn // 2), split)
 
 
+@pytest.mark.parametrize("cemb,cnoise,total", [(512, 128, 11904), (96, 64, 200), (100, 32, 64)])
+def test_embed_modulation_bits_do_not_depend_on_the_batch(env, cemb, cnoise, total):
+    """vb_embed (MPFourier models.py:96-101, emb linears + mp_sum + mp_silu :388-391, every block's emb_linear(emb) + 1 :175)
+    against fp32 torch, and — the two modulation GEMM kernels (batch <= 32 / wider) sum each output's K terms in the same order —
+    bit-identical rows whatever batch the plan was built for (ragged batches, channel counts off the tile sizes)."""
+    L, lib, dev = env
+    g = torch.Generator().manual_seed(cemb + total)
+    Bmax, ld, t = 128, 20, 0.5
+    sigma = (torch.rand(Bmax, generator=g) * 5 + 0.05).to(dev)
+    geom = torch.randn(Bmax, ld, generator=g).to(dev)
+    freqs, phases = torch.randn(cnoise, generator=g).to(dev) * 6.28, torch.rand(cnoise, generator=g).to(dev) * 6.28
+    wn = (torch.randn(cemb, cnoise, generator=g) / math.sqrt(cnoise)).to(dev)
+    wl = (torch.randn(cemb, ld, generator=g) / math.sqrt(ld)).to(dev)
+    wm = (torch.randn(total, cemb, generator=g) / math.sqrt(cemb)).to(dev)
+
+    def run(B):
+        emb = torch.full((B, cemb), float("nan"), device=dev)
+        mod = torch.full((B, total), float("nan"), device=dev)
+        d = L.EmbDesc(sigma=sigma.data_ptr(), geom=geom.data_ptr(), freqs=freqs.data_ptr(), phases=phases.data_ptr(),
+                      w_noise=wn.data_ptr(), w_label=wl.data_ptr(), w_mod=wm.data_ptr(), emb=emb.data_ptr(), mod=mod.data_ptr(), B=B,
+                      sigma_n=B, sigma_stride=1, cnoise=cnoise, cemb=cemb, label_dim=ld, mod_total=total, geom_rows=B, label_balance=t,
+                      noise_scale=1.0, geom_scale=1.0)
+        L.check(lib.vb_embed(C.byref(d), stream()), "vb_embed")
+        torch.cuda.synchronize()
+        return emb, mod
+
+    emb, mod = run(Bmax)
+    four = torch.cos((sigma.log() / 4)[:, None].double() * freqs.double() + phases.double()) * math.sqrt(2)
+    e = ((four @ wn.double().T) * (1 - t) + (geom.double() @ wl.double().T) * t) / math.sqrt((1 - t) ** 2 + t ** 2)
+    e = torch.nn.functional.silu(e) / 0.596
+    assert rel(emb, e) < 1e-5
+    assert rel(mod, emb.double() @ wm.double().T + 1) < 1e-5
+    for B in (1, 7, 32, 33, 40, 64, 100):
+        eb, mb = run(B)
+        assert torch.equal(eb, emb[:B]) and torch.equal(mb, mod[:B]), B
+
+
 def test_conv_two_source_and_narrow_output(env):
     """mp_cat folded into the K loop (models.py:78-84,403): conv(cat(wa*a, wb*b)) with the weights split over two tensors;
     and the 3-channel out_conv (padded to 16 columns, fp32 direct stores)."""

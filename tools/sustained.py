@@ -36,4 +36,4 @@ clk = sorted(float(r.split(",")[0]) for r in rows[3:] if "," in r)
 pw = sorted(float(r.split(",")[1]) for r in rows[3:] if "," in r)
 print(f"{name} B={B}: {ms:.2f} ms/call over {n} replays, median SM clock {clk[len(clk)//2] if clk else 0:.0f} MHz, "
       f"median power {pw[len(pw)//2] if pw else 0:.0f} W, env ROWROLL={os.environ.get('VB_ROWROLL','0')} "
-      f"AUTOTUNE={os.environ.get('VB_AUTOTUNE','1')} EPI_PP={os.environ.get('VB_EPI_PP','-')} KSPLIT={os.environ.get('VB_KSPLIT','1')}")
+      f"AUTOTUNE={os.environ.get('VB_AUTOTUNE','1')} EPI_PP={os.environ.get('VB_EPI_PP','-')} KSPLIT={os.environ.get('VB_KSPLIT','0')} MOD_WIDE={os.environ.get('VB_MOD_WIDE','1')}")

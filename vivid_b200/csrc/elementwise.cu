@@ -511,6 +511,82 @@ int eltwise_launch(const vb_ew_desc* d, cudaStream_t s) {
   return VB_OK;
 }
 
+// The same GEMM for batches above 32: block = 64 channels x 64 batch rows, thread = 4 x 4 outputs, both operands K-major in
+// shared memory (two 16-byte shared loads per 16 FMAs instead of three loads per 8), the next K slice prefetched into registers
+// while the current one is multiplied.  Every output is still the sum over k = 0 .. cemb-1 in ascending order in one fp32
+// accumulator, so the bits equal the 32-row kernel's — a plan gives the same modulation whatever batch it is built for
+// (tests/test_gpu_parity.py::test_embed_modulation_bits_do_not_depend_on_the_batch).  profiles/r02_step_timeline.txt: the 32-row
+// kernel took 112 us per launch at batch 128 against a 29 us fp32-FMA floor, 0.5 % of the step; profiles/r02_embed_micro.txt: A/B.
+constexpr int kModWBN = 64, kModWLd = kModBM + 4;
+__global__ void __launch_bounds__(256) mod_wide_kernel(const vb_emb_desc d) {
+  pdl_grid_sync();
+  __shared__ __align__(16) float s_w[kModBK][kModWLd];     // [k][channel]
+  __shared__ __align__(16) float s_e[kModBK][kModWLd];     // [k][batch row]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * kModBM, b0 = blockIdx.y * kModWBN;
+  // global -> shared: a thread moves two float4 (4 consecutive k) of each operand per slice: rows lr and lr + 32, k = 4 kq .. 4 kq + 3
+  const int lr = tid >> 3, kq = tid & 7;
+  const bool vec_ok = (d.cemb & 3) == 0;
+  auto fetch = [&](const float* base, int row, int rows, int k0) -> float4 {
+    const int k = k0 + kq * 4;
+    if (row >= rows) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* p = base + static_cast<size_t>(row) * d.cemb + k;
+    if (vec_ok && k + 3 < d.cemb) return __ldg(reinterpret_cast<const float4*>(p));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < d.cemb) v.x = __ldg(p);
+    if (k + 1 < d.cemb) v.y = __ldg(p + 1);
+    if (k + 2 < d.cemb) v.z = __ldg(p + 2);
+    if (k + 3 < d.cemb) v.w = __ldg(p + 3);
+    return v;
+  };
+  auto stash = [&](float (*dst)[kModWLd], int row, const float4& v) {
+    dst[kq * 4 + 0][row] = v.x;
+    dst[kq * 4 + 1][row] = v.y;
+    dst[kq * 4 + 2][row] = v.z;
+    dst[kq * 4 + 3][row] = v.w;
+  };
+  float4 pw0 = fetch(d.w_mod, m0 + lr, d.mod_total, 0), pw1 = fetch(d.w_mod, m0 + lr + 32, d.mod_total, 0);
+  float4 pe0 = fetch(d.emb, b0 + lr, d.B, 0), pe1 = fetch(d.emb, b0 + lr + 32, d.B, 0);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < d.cemb; k0 += kModBK) {
+    stash(s_w, lr, pw0);
+    stash(s_w, lr + 32, pw1);
+    stash(s_e, lr, pe0);
+    stash(s_e, lr + 32, pe1);
+    __syncthreads();
+    if (k0 + kModBK < d.cemb) {
+      pw0 = fetch(d.w_mod, m0 + lr, d.mod_total, k0 + kModBK);
+      pw1 = fetch(d.w_mod, m0 + lr + 32, d.mod_total, k0 + kModBK);
+      pe0 = fetch(d.emb, b0 + lr, d.B, k0 + kModBK);
+      pe1 = fetch(d.emb, b0 + lr + 32, d.B, k0 + kModBK);
+    }
+#pragma unroll
+    for (int k = 0; k < kModBK; ++k) {
+      const float4 w = *reinterpret_cast<const float4*>(&s_w[k][ty * 4]);
+      const float4 e = *reinterpret_cast<const float4*>(&s_e[k][tx * 4]);
+      const float wv[4] = {w.x, w.y, w.z, w.w}, ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wv[i], ev[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int b = b0 + tx * 4 + j;
+    if (b >= d.B) continue;
+    float* o = d.mod + static_cast<size_t>(b) * d.mod_total + m0 + ty * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (m0 + ty * 4 + i < d.mod_total) o[i] = acc[i][j] + 1.0f;
+  }
+}
+
 int embed_launch(const vb_emb_desc* d, cudaStream_t s) {
   VB_REQUIRE(d != nullptr && d->sigma && d->freqs && d->phases && d->w_noise && d->emb, "vb_embed: null argument");
   VB_REQUIRE(d->B > 0 && d->cnoise > 0 && d->cemb > 0, "vb_embed: empty problem");
@@ -519,8 +595,16 @@ int embed_launch(const vb_emb_desc* d, cudaStream_t s) {
   VB_CHECK_CUDA(launch_pdl(emb_kernel, dim3(d->B, 4), dim3(256), smem, s, *d));
   VB_CHECK_CUDA(cudaGetLastError());
   if (d->mod_total > 0) {
-    const dim3 grid((d->mod_total + kModBM - 1) / kModBM, (d->B + 31) / 32);
-    VB_CHECK_CUDA(launch_pdl(mod_kernel, grid, dim3(256), 0, s, *d));
+    static const bool wide_off = getenv("VB_MOD_WIDE") != nullptr && atoi(getenv("VB_MOD_WIDE")) == 0;      // A/B testing
+    // the 64 x 64 tiles pay once they fill the chip (vivid-base at batch 128: 372 CTAs, vb_embed 147 -> 103 us; the SR UNet's 3 712
+    // channels give 116 and run 44 -> 57 us, so they stay with the 32-row kernel); the choice never changes a bit
+    const dim3 wide((d->mod_total + kModBM - 1) / kModBM, (d->B + kModWBN - 1) / kModWBN);
+    if (d->B > 32 && !wide_off && static_cast<int>(wide.x * wide.y) >= num_sms()) {
+      VB_CHECK_CUDA(launch_pdl(mod_wide_kernel, wide, dim3(256), 0, s, *d));
+    } else {
+      const dim3 grid((d->mod_total + kModBM - 1) / kModBM, (d->B + 31) / 32);
+      VB_CHECK_CUDA(launch_pdl(mod_kernel, grid, dim3(256), 0, s, *d));
+    }
     VB_CHECK_CUDA(cudaGetLastError());
   }
   return VB_OK;
