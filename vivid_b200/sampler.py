@@ -163,7 +163,10 @@ def _edm_sampler_bound(net, src, noise, labels, gnet, cond, num_steps, sigma_min
     sig_in = [b.p.in_sigma for b in bounds]
     side = _side_stream(dev) if guided and os.environ.get("VB_DUAL_STREAM", "1") != "0" else None
     cur = torch.cuda.current_stream(dev)
-    if trace is None and os.environ.get("VB_C_SAMPLER", "1") != "0" and all(b.net.use_graph for b in bounds):
+    # (a degenerate schedule — num_steps = 1 is 0/0 in the reference's formula, generate_images.py:69 — takes the Python loop and
+    #  yields the reference's NaNs instead of vb_sample's argument error)
+    if (trace is None and os.environ.get("VB_C_SAMPLER", "1") != "0" and all(b.net.use_graph for b in bounds)
+            and all(t > 0 for t in t_steps[:-1])):
         # the whole loop in the library (vb_sample: the same graph replays and vb_heun passes, enqueued from C) — what a
         # non-Python host would call; the Python loop below is the same sequence and stays for tracing / eager replay
         return _sample_c(lib, bn, bg, noise.to(dtype).contiguous(), t_steps, guidance, side, cur)
