@@ -499,6 +499,12 @@ typedef struct vb_param {
 int vb_net_plan_create(const vb_net_desc* net, const vb_param* params, int32_t n_params, int32_t batch, void* stream, vb_plan** out);
 /* The plan's persistent I/O buffers (vb_plan_bind_io's descriptor) and the index of the first op after the source-view encoder. */
 int vb_plan_get_io(const vb_plan* p, vb_io_desc* out, int32_t* enc_ops);
+/* The source-view encoder's cross-attention feature maps of a library-recorded plan, in consumption order: 16-bit NHWC
+ * [B][R][R][C] device buffers that ops [0, enc_ops) write and the denoising UNet's K/V GEMMs read — what the reference's
+ * return_features / inject_features hand around (training/models.py:664-672; edm_sampler's no_time_enc caching,
+ * generate_images.py:52-57: run vb_plan_launch_graph_range(p, 0, enc_ops) once, then (enc_ops, -1) per step). */
+int vb_plan_num_features(const vb_plan* p);
+int vb_plan_get_feature(const vb_plan* p, int32_t i, void** ptr, int32_t* B, int32_t* R, int32_t* C);
 /* Dry run of the recording, with no device: writes one text line per buffer allocation, weight preparation and recorded op —
  * pointers canonicalised as buffer-id/offset and parameter-index/offset — into buf (NUL-terminated, truncated to cap) and returns
  * the full length, or a negative status.  vb_trace_desc formats one descriptor the same way (kind: 0 weight_prep, 1 conv,

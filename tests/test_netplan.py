@@ -190,3 +190,39 @@ def test_library_recorded_plans_run_the_whole_sampler():
     L.check(lib.vb_sample(C.byref(d), st), "vb_sample")
     torch.cuda.synchronize()
     assert torch.equal(out, want)
+
+
+@pytest.mark.gpu
+def test_python_surface_runs_on_library_recorded_plans(monkeypatch):
+    """VB_LIB_PLAN=1: NVPrecond.plan() hands out plans recorded by the library (netplan.LibPlan: torch views of the plan's own
+    device buffers) — forward, return_features / inject_features and the guided sampler give the bits of the engine.py plans.
+    (The whole `-m gpu` suite passes under this switch; this test keeps the switch itself covered.)"""
+    import vivid_b200
+    from vivid_b200 import netplan
+    L, lib, dev = _gpu_env()
+    B = 2
+    net, gnet = small_net("v_cond", dev), small_net("v_uncond", dev)
+    inp = {k: v.to(dev) for k, v in cases.synth_inputs("v_cond", B).items()}
+    x = inp["tgt"] + 2.0 * inp["noise"]
+    sigma = torch.full((B,), 2.0, device=dev)
+
+    def everything():
+        d = net(inp["src"], x, sigma, inp["geometry"])
+        feats = net(inp["src"], x, sigma, inp["geometry"], return_features=True)
+        d2 = net(inp["src"], x, sigma, inp["geometry"], inject_features=feats)
+        s = vivid_b200.edm_sampler(net, inp["src"], inp["noise"], labels=inp["geometry"], gnet=gnet, num_steps=3, guidance=1.5)
+        return [d.clone(), d2.clone(), s.clone()] + [f.clone() for f in feats]
+
+    want = everything()
+    assert type(net.plan(B, dev)).__name__ == "Plan"
+    monkeypatch.setenv("VB_LIB_PLAN", "1")
+    net.invalidate_plans()
+    gnet.invalidate_plans()
+    got = everything()
+    assert isinstance(net.plan(B, dev), netplan.LibPlan) and isinstance(gnet.plan(B, dev), netplan.LibPlan)
+    assert len(got) == len(want) > 3
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    assert torch.equal(want[0], want[1])            # injected features == recomputed features
+    net.invalidate_plans()
+    gnet.invalidate_plans()

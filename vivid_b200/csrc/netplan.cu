@@ -1268,6 +1268,8 @@ struct Recorder {
                          geom_scale);
       run_unet(net.encoder, "encoder.", enc, src16, Bx, e, nullptr, 1, false, true, &features);
       feat_seg = net.dual_source ? 2 : 1;
+      if (!dry)
+        for (const Act& f : features) plan->features.push_back({f.raw.ptr, f.B, f.R, f.C});
     }
     // ops [0, enc_ops) are the source-view encoder; its outputs are what the reference's return_features / inject_features hand
     // around (training/models.py:664-672, snapshot :612-626)
@@ -1384,6 +1386,19 @@ extern "C" int vb_plan_get_io(const vb_plan* p, vb_io_desc* out, int32_t* enc_op
   VB_REQUIRE(p != nullptr && p->io_bound && out != nullptr, "vb_plan_get_io: the plan has no bound I/O buffers");
   *out = p->io;
   if (enc_ops != nullptr) *enc_ops = p->enc_ops;
+  return VB_OK;
+}
+
+extern "C" int vb_plan_num_features(const vb_plan* p) { return p ? static_cast<int>(p->features.size()) : 0; }
+
+extern "C" int vb_plan_get_feature(const vb_plan* p, int32_t i, void** ptr, int32_t* B, int32_t* R, int32_t* C) {
+  VB_REQUIRE(p != nullptr && ptr != nullptr && B != nullptr && R != nullptr && C != nullptr, "vb_plan_get_feature: null argument");
+  VB_REQUIRE(i >= 0 && i < static_cast<int>(p->features.size()), "vb_plan_get_feature: the plan has %d feature maps", static_cast<int>(p->features.size()));
+  const vb_plan::Feature& f = p->features[i];
+  *ptr = f.ptr;
+  *B = f.B;
+  *R = f.R;
+  *C = f.C;
   return VB_OK;
 }
 

@@ -38,4 +38,10 @@ struct vb_plan {
   // plans recorded by the library itself (vb_net_plan_create) own their device buffers: prepared weights, activations, I/O
   std::vector<void*> owned;
   int enc_ops = 0;            // ops [0, enc_ops) are the source-view encoder
+  // the encoder's cross-attention feature maps (16-bit NHWC [B][R][R][C]): what return_features / inject_features hand around
+  struct Feature {
+    void* ptr;
+    int B, R, C;
+  };
+  std::vector<Feature> features;
 };

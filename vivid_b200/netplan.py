@@ -75,12 +75,31 @@ def param_table(net):
     return arr, keep
 
 
+class _DeviceMemory:
+    """A library-owned device buffer as seen by torch (CUDA array interface): torch.as_tensor(...) wraps it without a copy."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(int(s) for s in shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def _view(ptr, shape, dtype, device):
+    if not ptr:
+        return None
+    if dtype == torch.float32:
+        return torch.as_tensor(_DeviceMemory(ptr, shape, "<f4"), device=device)
+    return torch.as_tensor(_DeviceMemory(ptr, shape, "<i2"), device=device).view(dtype)      # fp16 / bf16 operands
+
+
 class LibPlan:
-    """A denoiser plan recorded by the library from (net description, parameter table): vb_net_plan_create."""
+    """A denoiser plan recorded by the library from (net description, parameter table): vb_net_plan_create.  Offers what
+    NVPrecond.forward / edm_sampler use of engine.Plan (I/O tensors — views of the plan's own device buffers —, run, feature
+    maps), so `VB_LIB_PLAN=1` makes the whole Python surface run on library-recorded plans."""
 
     def __init__(self, net, batch, device):
         self.lib = L.lib()
         self.handle = C.c_void_p()
+        self.net, self.B, self.device = net, int(batch), torch.device(device)
         desc = net_desc(net)
         params, keep = param_table(net)
         stream = torch.cuda.current_stream(device).cuda_stream
@@ -94,6 +113,34 @@ class LibPlan:
         self.enc_ops = enc_ops.value
         self.num_ops = self.lib.vb_plan_num_ops(self.handle)
         self.launches = int(self.lib.vb_plan_query(self.handle, 1))
+        self.padded_flops = self.lib.vb_plan_query(self.handle, 0)
+        self.owned_bytes = int(self.io.workspace_bytes)
+        self.weight_versions = None
+        io, R, f32 = self.io, net.img_resolution, torch.float32
+        self.in_x = _view(io.in_x, (io.n_x, 3, R, R), f32, device)
+        self.in_src = _view(io.in_src, (io.n_x, 3, R, R), f32, device)
+        self.in_sigma = _view(io.in_sigma, (io.n_x,), f32, device)
+        self.in_geom = _view(io.in_geom, (io.n_x, io.geom_dim), f32, device)
+        self.in_cond = _view(io.in_cond, (io.n_out, 3, R, R), f32, device)
+        self.in_noise = _view(io.in_noise, (io.n_out, 3, R, R), f32, device)
+        self.out_d = _view(io.out_d, (io.n_out, 3, R, R), f32, device)
+        self._features = []
+        op_dtype = L.operand_torch_dtype()
+        for i in range(self.lib.vb_plan_num_features(self.handle)):
+            ptr, fb, fr, fc = C.c_void_p(), C.c_int32(), C.c_int32(), C.c_int32()
+            L.check(self.lib.vb_plan_get_feature(self.handle, i, C.byref(ptr), C.byref(fb), C.byref(fr), C.byref(fc)), "vb_plan_get_feature")
+            self._features.append(_view(ptr.value, (fb.value, fr.value, fr.value, fc.value), op_dtype, device))
+
+    def run(self, graph=True, section="all"):
+        """engine.Plan.run: everything, the source-view encoder alone ('enc') or the denoising UNet alone ('unet')."""
+        first, last = {"all": (0, -1), "enc": (0, self.enc_ops), "unet": (self.enc_ops, -1)}[section]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        fn = self.lib.vb_plan_launch_graph_range if graph else self.lib.vb_plan_run
+        L.check(fn(self.handle, first, last, stream), "vb_plan_run")
+
+    def feature_views(self):
+        """The encoder's cross-attention feature maps as logical NCHW views of the plan's 16-bit NHWC buffers."""
+        return [f.permute(0, 3, 1, 2) for f in self._features]
 
     def __del__(self):
         try:

@@ -12,6 +12,8 @@ the reference's module-level VANILLA_MODE global:
   label_dim=...                               -> vanilla: B inputs, B outputs, geometry may be None
   source_label_dim=..., target_label_dim=...  -> dual-source: 2B interleaved inputs, B outputs
 """
+import os
+
 import torch
 
 from . import _lib as L
@@ -115,6 +117,11 @@ class NVPrecond(torch.nn.Module):
         if fp32:
             from .engine_f32 import PlanF32
             p = PlanF32(self, int(batch), device)
+        elif os.environ.get("VB_LIB_PLAN") == "1":
+            # the plan is recorded by the library itself (vb_net_plan_create) instead of engine.py: same ops, op for op
+            # (tests/test_netplan.py) — the switch exists so that the whole parity suite can be run on that recorder
+            from .netplan import LibPlan
+            p = LibPlan(self, int(batch), device)
         else:
             p = engine.Plan(self, int(batch), device)
         p.weight_versions = sig
