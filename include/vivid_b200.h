@@ -497,6 +497,11 @@ typedef struct vb_param {
  * vb_plan_destroy); the parameter tensors are read once (weights are normalised, scaled, rounded and repacked into the plan) and
  * need not outlive the call.  Synchronises `stream` (layout tuning times candidate launches). */
 int vb_net_plan_create(const vb_net_desc* net, const vb_param* params, int32_t n_params, int32_t batch, void* stream, vb_plan** out);
+/* Re-prepares every weight of a plan recorded by vb_net_plan_create from another parameter table of the SAME architecture (the
+ * next checkpoint, updated EMA weights): normalise / scale / round / repack into the plan's existing buffers, on `stream`.
+ * Nothing is re-recorded or re-tuned and captured graphs stay valid.  All or nothing: the table is validated before the first
+ * launch. */
+int vb_net_plan_set_weights(vb_plan* p, const vb_param* params, int32_t n_params, void* stream);
 /* The plan's persistent I/O buffers (vb_plan_bind_io's descriptor) and the index of the first op after the source-view encoder. */
 int vb_plan_get_io(const vb_plan* p, vb_io_desc* out, int32_t* enc_ops);
 /* The source-view encoder's cross-attention feature maps of a library-recorded plan, in consumption order: 16-bit NHWC

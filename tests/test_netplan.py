@@ -226,3 +226,61 @@ def test_python_surface_runs_on_library_recorded_plans(monkeypatch):
     assert torch.equal(want[0], want[1])            # injected features == recomputed features
     net.invalidate_plans()
     gnet.invalidate_plans()
+
+
+def test_weight_refresh_rejects_foreign_plans():
+    from vivid_b200 import _lib as L
+    from vivid_b200 import netplan
+    lib = L.lib()
+    net = small_net("v_uncond")
+    params, keep = netplan.param_table(net)
+    plan = C.c_void_p()
+    assert lib.vb_plan_create(C.byref(plan)) == 0
+    try:
+        assert lib.vb_net_plan_set_weights(plan, params, len(params), None) != 0 and b"not recorded by vb_net_plan_create" in lib.vb_last_error()
+        assert lib.vb_net_plan_set_weights(None, params, len(params), None) != 0
+        assert lib.vb_plan_num_features(plan) == 0 and lib.vb_plan_num_features(None) == 0
+    finally:
+        lib.vb_plan_destroy(plan)
+    del keep
+
+
+@pytest.mark.gpu
+def test_library_plan_weight_refresh():
+    """vb_net_plan_set_weights: a recorded plan takes the next checkpoint's weights in place (fp32, then the fp16-persisted form) and
+    gives the bits of a plan recorded from scratch; a bad table changes nothing."""
+    from vivid_b200 import netplan
+    L, lib, dev = _gpu_env()
+    B = 2
+    net = small_net("v_cond", dev)
+    inp = {k: v.to(dev) for k, v in cases.synth_inputs("v_cond", B).items()}
+    x = (inp["tgt"] + 2.0 * inp["noise"]).contiguous()
+    sigma = torch.full((B,), 2.0, device=dev)
+    geom = inp["geometry"].to(torch.float32).contiguous()
+    st = torch.cuda.current_stream().cuda_stream
+    lp = netplan.LibPlan(net, B, dev)
+
+    def lib_call():
+        out = torch.full_like(x, float("nan"))
+        L.check(lib.vb_denoise(lp.handle, inp["src"].data_ptr(), x.data_ptr(), sigma.data_ptr(), B, geom.data_ptr(), B, None, None,
+                               out.data_ptr(), st), "vb_denoise")
+        torch.cuda.synchronize()
+        return out
+
+    ref1 = net(inp["src"], x, sigma, inp["geometry"]).clone()
+    assert torch.equal(lib_call(), ref1)
+    shapes = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+    net.load_state_dict(cases.synth_state_dict(shapes, salt=1))              # "the next checkpoint"
+    ref2 = net(inp["src"], x, sigma, inp["geometry"]).clone()
+    assert not torch.equal(ref2, ref1)
+    assert torch.equal(lib_call(), ref1)                                     # the plan still holds the old weights
+    lp.set_weights(net)
+    assert torch.equal(lib_call(), ref2)
+    params, keep = netplan.param_table(net)
+    assert lib.vb_net_plan_set_weights(lp.handle, params, len(params) - 40, st) != 0 and b"is missing" in lib.vb_last_error()
+    assert torch.equal(lib_call(), ref2)                                     # all or nothing
+    del keep
+    net = net.half()                                                         # fp16-persisted parameters and buffers
+    ref3 = net(inp["src"], x, sigma, inp["geometry"]).clone()
+    lp.set_weights(net)
+    assert torch.equal(lib_call(), ref3)

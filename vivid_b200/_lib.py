@@ -172,6 +172,7 @@ SIGNATURES = {
     "vb_sample_workspace_bytes": (C.c_int64, [vp]),
     "vb_sample": (C.c_int, [C.POINTER(SampleDesc), vp]),
     "vb_net_plan_create": (C.c_int, [C.POINTER(NetDesc), C.POINTER(Param), i32, i32, vp, C.POINTER(vp)]),
+    "vb_net_plan_set_weights": (C.c_int, [vp, C.POINTER(Param), i32, vp]),
     "vb_plan_get_io": (C.c_int, [vp, C.POINTER(IoDesc), C.POINTER(i32)]),
     "vb_plan_num_features": (C.c_int, [vp]),
     "vb_plan_get_feature": (C.c_int, [vp, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),

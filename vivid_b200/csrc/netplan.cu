@@ -510,10 +510,14 @@ struct Recorder {
 
   // vb_weight_prep of parameter `name` viewed as [cout][cin][taps]: normalise (fp32) + gain + pack.  fp32: the plain fp32 matrix
   // (embedding linears), optionally straight into `dst`.
+  // gain_param: a 0-dim parameter (emb_gain, out_gain) the constant `gain` is multiplied with.
   Buf prep_weight(const std::string& name, int cout, int cin, int taps, double gain = 1.0, int cout_pad = 0, int perm_parts = 0,
-                  int perm_dim = 0, int split = -1, double scale_a = 1.0, double scale_b = 1.0, bool fp32 = false, void* dst = nullptr) {
+                  int perm_dim = 0, int split = -1, double scale_a = 1.0, double scale_b = 1.0, bool fp32 = false, void* dst = nullptr,
+                  const std::string& gain_param = std::string()) {
     const vb_param* p = find(name);
     if (p == nullptr) return Buf();
+    const double gain_const = gain;
+    if (!gain_param.empty()) gain *= scalar(gain_param);
     if (numel_of(p) != static_cast<long long>(cout) * cin * taps) {
       fail("vb_net_plan: '%s' has %lld elements, the layer table expects %d x %d x %d", name.c_str(), numel_of(p), cout, cin, taps);
       return Buf();
@@ -560,6 +564,15 @@ struct Recorder {
       d.scale_b = static_cast<float>(scale_b);
     }
     emit(0, &d);
+    if (!dry && ok()) {
+      vb_plan::WeightSlot slot;
+      slot.name = name;
+      slot.d = d;
+      slot.gain_param = gain_param;
+      slot.gain_const = gain_const;
+      slot.numel = numel_of(p);
+      plan->weights.push_back(slot);
+    }
     return out;
   }
 
@@ -808,9 +821,8 @@ struct Recorder {
     for (const Spec& s : specs) {
       if (s.is_conv) continue;
       const std::string base = prefix + (s.enc_group ? "enc." : "dec.") + s.name + ".";
-      const double gain = scalar(base + "emb_gain");
-      prep_weight(base + "emb_linear.weight", s.cout, u.cemb, 1, gain, 0, 0, 0, -1, 1.0, 1.0, true,
-                  static_cast<char*>(w_mod.ptr) + static_cast<size_t>(e.offs[block_key(s)]) * u.cemb * 4);
+      prep_weight(base + "emb_linear.weight", s.cout, u.cemb, 1, 1.0, 0, 0, 0, -1, 1.0, 1.0, true,
+                  static_cast<char*>(w_mod.ptr) + static_cast<size_t>(e.offs[block_key(s)]) * u.cemb * 4, base + "emb_gain");
     }
     Buf w_noise = prep_weight(prefix + "emb_noise.weight", u.cemb, u.cnoise, 1, 1.0, 0, 0, 0, -1, 1.0, 1.0, true);
     Buf w_label;
@@ -861,6 +873,13 @@ struct Recorder {
     } else if (ok()) {
       to_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(p->data, p->dtype, static_cast<float*>(dst.ptr), n);
       check_cuda(cudaGetLastError(), "to_f32_kernel");
+      vb_plan::WeightSlot slot;
+      slot.name = name;
+      memset(&slot.d, 0, sizeof(slot.d));
+      slot.d.dst = dst.ptr;
+      slot.copy = true;
+      slot.numel = n;
+      plan->weights.push_back(slot);
     }
   }
   void fill(const Buf& dst, float v, long long n) {
@@ -1210,7 +1229,7 @@ struct Recorder {
     }
     Buf raw;
     if (ok() && u.out_channels > 0) {
-      Buf wo = prep_weight(prefix + "out_conv.weight", u.out_channels, cur.C, 9, scalar(prefix + "out_gain"), 16);
+      Buf wo = prep_weight(prefix + "out_conv.weight", u.out_channels, cur.C, 9, 1.0, 16, 0, 0, -1, 1.0, 1.0, false, nullptr, prefix + "out_gain");
       raw = buf(static_cast<long long>(Bc) * cur.R * cur.R * 16, 4);
       ConvArgs a;
       a.cout_pad = 16;
@@ -1379,6 +1398,69 @@ extern "C" int vb_net_plan_create(const vb_net_desc* net, const vb_param* params
     return r.rc;
   }
   *out = plan;
+  return VB_OK;
+}
+
+// Refresh every prepared weight of a library-recorded plan from another parameter table of the same architecture.
+extern "C" int vb_net_plan_set_weights(vb_plan* p, const vb_param* params, int32_t n_params, void* stream) {
+  VB_REQUIRE(p != nullptr && params != nullptr && n_params > 0, "vb_net_plan_set_weights: plan and params are required");
+  VB_REQUIRE(!p->weights.empty(), "vb_net_plan_set_weights: the plan was not recorded by vb_net_plan_create");
+  std::unordered_map<std::string, const vb_param*> index;
+  for (int i = 0; i < n_params; ++i) {
+    VB_REQUIRE(params[i].name != nullptr && params[i].data != nullptr && params[i].ndim >= 0 && params[i].ndim <= 4,
+               "vb_net_plan_set_weights: bad entry %d of the parameter table", i);
+    index[params[i].name] = &params[i];
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto lookup = [&](const std::string& name, long long numel) -> const vb_param* {
+    auto it = index.find(name);
+    if (it == index.end()) {
+      vb::set_error("vb_net_plan_set_weights: parameter '%s' is missing", name.c_str());
+      return nullptr;
+    }
+    long long n = 1;
+    for (int i = 0; i < it->second->ndim; ++i) n *= it->second->shape[i];
+    if (n != numel || (it->second->dtype != VB_F32 && it->second->dtype != VB_F16)) {
+      vb::set_error("vb_net_plan_set_weights: '%s' must hold %lld fp32/fp16 values", name.c_str(), numel);
+      return nullptr;
+    }
+    return it->second;
+  };
+  // validate the whole table before the first launch: a refresh is all or nothing
+  for (const vb_plan::WeightSlot& w : p->weights) {
+    if (lookup(w.name, w.numel) == nullptr) return VB_ERR_INVALID;
+    if (!w.gain_param.empty() && lookup(w.gain_param, 1) == nullptr) return VB_ERR_INVALID;
+  }
+  for (const vb_plan::WeightSlot& w : p->weights) {
+    const vb_param* src = lookup(w.name, w.numel);
+    if (w.copy) {
+      to_f32_kernel<<<static_cast<unsigned>((w.numel + 255) / 256), 256, 0, s>>>(src->data, src->dtype, static_cast<float*>(w.d.dst), w.numel);
+      VB_CHECK_CUDA(cudaGetLastError());
+      continue;
+    }
+    vb_weight_prep_desc d = w.d;
+    d.src = src->data;
+    d.src_dtype = src->dtype;
+    double gain = w.gain_const;
+    if (!w.gain_param.empty()) {
+      const vb_param* g = lookup(w.gain_param, 1);
+      unsigned char raw[4] = {0, 0, 0, 0};
+      VB_CHECK_CUDA(cudaMemcpyAsync(raw, g->data, g->dtype == VB_F16 ? 2 : 4, cudaMemcpyDeviceToHost, s));
+      VB_CHECK_CUDA(cudaStreamSynchronize(s));
+      if (g->dtype == VB_F16) {
+        __half h;
+        memcpy(&h, raw, 2);
+        gain *= static_cast<double>(__half2float(h));
+      } else {
+        float f;
+        memcpy(&f, raw, 4);
+        gain *= static_cast<double>(f);
+      }
+    }
+    d.gain = static_cast<float>(gain);
+    const int rc = vb_weight_prep(&d, stream);
+    if (rc != VB_OK) return rc;
+  }
   return VB_OK;
 }
 

@@ -1,6 +1,7 @@
 // The recorded-plan object shared by plan.cu (replay, graphs, whole-call entry points) and netplan.cu (recording a plan from a
 // network description inside the library).
 #pragma once
+#include <string>
 #include <vector>
 
 #include "common.h"
@@ -44,4 +45,15 @@ struct vb_plan {
     int B, R, C;
   };
   std::vector<Feature> features;
+  // how every prepared weight / converted buffer of the plan was produced, so that vb_net_plan_set_weights can refresh them in
+  // place from another parameter table (the next checkpoint of the same architecture) without re-recording or re-tuning
+  struct WeightSlot {
+    std::string name;          // source parameter
+    vb_weight_prep_desc d;     // dst and layout (src / src_dtype / gain are filled per refresh); copy: d.dst only
+    std::string gain_param;    // 0-dim parameter the gain is multiplied with (emb_gain, out_gain), or empty
+    double gain_const = 1.0;
+    bool copy = false;         // plain conversion to fp32 (MPFourier buffers)
+    long long numel = 0;
+  };
+  std::vector<WeightSlot> weights;
 };

@@ -131,6 +131,15 @@ class LibPlan:
             L.check(self.lib.vb_plan_get_feature(self.handle, i, C.byref(ptr), C.byref(fb), C.byref(fr), C.byref(fc)), "vb_plan_get_feature")
             self._features.append(_view(ptr.value, (fb.value, fr.value, fr.value, fc.value), op_dtype, device))
 
+    def set_weights(self, net):
+        """Refresh the plan's prepared weights from `net` (same architecture; e.g. after load_state_dict): vb_net_plan_set_weights."""
+        params, keep = param_table(net)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            L.check(self.lib.vb_net_plan_set_weights(self.handle, params, len(params), stream), "vb_net_plan_set_weights")
+            torch.cuda.current_stream(self.device).synchronize()       # the table's tensors may go away with `keep`
+        del keep
+
     def run(self, graph=True, section="all"):
         """engine.Plan.run: everything, the source-view encoder alone ('enc') or the denoising UNet alone ('unet')."""
         first, last = {"all": (0, -1), "enc": (0, self.enc_ops), "unet": (self.enc_ops, -1)}[section]
