@@ -67,6 +67,53 @@ def test_library_recorder_matches_engine_on_presets(name):
     assert len(ops) == {"vivid-base": 315, "vivid-uncond": 159, "vivid-sr": 150}.get(name, len(ops))
 
 
+def test_library_recorder_matches_engine_on_random_architectures():
+    """Beyond the presets: random constructor arguments (resolution, widths, depth, attention placement, balances, embedding
+    widths; conditional / uncond / super_res / dual-source / no_time_enc nets), random batch sizes — the two recorders stay
+    identical line for line."""
+    import random
+    import vivid_b200
+    from vivid_b200 import netplan
+    rng = random.Random(1234)
+    done = 0
+    while done < 24:
+        R = rng.choice([16, 32, 64])
+        mult = rng.choice([[1, 2], [1, 1], [1, 2, 2], [1, 2, 3], [2, 2], [1, 2, 3, 4]])
+        if R >> (len(mult) - 1) < 4:
+            continue
+        attn = [R >> i for i in range(len(mult)) if (R >> i) <= 32 and rng.random() < 0.5]
+        flavor = rng.choice(["cond", "uncond", "sr", "dual", "no_time_enc"])
+        cfg = dict(img_resolution=R, img_channels=3, model_channels=rng.choice([64, 128]), channel_mult=mult,
+                   num_blocks=rng.choice([1, 2, 3]), attn_resolutions=attn, extra_attn=rng.choice([None, 0, 1]),
+                   res_balance=rng.choice([0.3, 0.5]), attn_balance=rng.choice([0.3, 0.2]), concat_balance=rng.choice([0.5, 0.3]),
+                   label_balance=rng.choice([0.5, 0.25]))
+        if rng.random() < 0.3:
+            cfg["channel_mult_emb"] = rng.choice([2, 4])
+        if rng.random() < 0.3:
+            cfg["channel_mult_noise"] = rng.choice([1, 2])
+        if flavor == "dual":
+            cfg.update(source_label_dim=20, target_label_dim=40)
+        else:
+            cfg.update(label_dim=20)
+        if flavor == "uncond":
+            cfg["uncond"] = True
+        if flavor == "sr":
+            cfg.update(super_res=True, noisy_sr=0.25)
+        if flavor == "no_time_enc":
+            cfg["no_time_enc"] = True
+        net = vivid_b200.NVPrecond(**cfg).eval()
+        with torch.no_grad():
+            for p in net.parameters():
+                if p.ndim == 0:
+                    p.fill_(rng.random() + 0.5)
+        if rng.random() < 0.3:
+            net = net.half()
+        B = rng.choice([1, 2, 5, 33])
+        a, b = netplan.trace_engine(net, B), netplan.trace_library(net, B)
+        assert a == b, f"{cfg} B={B}: " + first_difference(a, b)
+        done += 1
+
+
 def test_library_recorder_rejects_bad_descriptions():
     from vivid_b200 import _lib as L
     from vivid_b200 import netplan
