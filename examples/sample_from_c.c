@@ -25,3 +25,20 @@ int sample_batch(const vb_net_desc* base, const vb_param* base_params, int n_bas
   /* ... cudaStreamSynchronize(stream) before x_out is read; vb_plan_destroy(net/gnet) frees the plans' device buffers */
   return rc;
 }
+
+/* The second stage (generate_images.py:318-331): the 64x64 sample is upscaled x4 (bilinear), the SR net denoises a fresh
+ * 256x256 latent conditioned on it — drawing new N(0,1) conditioning noise before every call through `draw` (the reference
+ * uses torch.randn_like, experiments/code/training/models.py:608-611; a C host plugs in its own generator) — and the result is
+ * quantised to uint8 (training/encoders.py:58-62).  sr: a plan recorded from the SR checkpoint with super_res = 1. */
+int super_resolve(vb_plan* sr, int batch, const float* base_sample /*[batch,3,64,64]*/, const float* sr_src /*[batch,3,256,256]*/,
+                  const float* sr_pose, const float* sr_latent_noise, const float* t_steps, vb_noise_fn draw, void* draw_state,
+                  float* cond /*scratch [batch,3,256,256]*/, float* ws, float* x256, uint8_t* images, cudaStream_t stream) {
+  int rc = vb_resize(base_sample, cond, batch * 3, 64, 64, 256, 256, /*antialias=*/0, stream);
+  if (!rc) rc = vb_plan_set_inputs(sr, sr_src, sr_pose, batch, cond, stream);
+  vb_sample_desc d = {0};
+  d.net = sr; d.noise = sr_latent_noise; d.t_steps = t_steps; d.workspace = ws; d.x_out = x256;
+  d.sr_noise = draw; d.sr_noise_user = draw_state; d.num_steps = 32; d.guidance = 1.0f;      /* the SR stage is unguided */
+  if (!rc) rc = vb_sample(&d, stream);
+  if (!rc) rc = vb_decode_u8(x256, images, (int64_t)batch * 3 * 256 * 256, stream);
+  return rc;
+}
