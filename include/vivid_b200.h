@@ -30,7 +30,9 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 1
+/* 2: vb_conv_desc grew ks_ws; the whole-sampler (vb_sample), library-side plan recording (vb_net_plan_*) and feature / trace
+ * entry points were added.  vb_struct_size() lets a binding verify every descriptor layout. */
+#define VB_ABI_VERSION 2
 
 typedef enum vb_status {
   VB_OK = 0,

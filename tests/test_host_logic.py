@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_abi_version_and_struct_mirror(lib):
     from vivid_b200 import _lib
-    assert lib.vb_abi_version() == 1
+    assert lib.vb_abi_version() == 2
     for i, st in enumerate(_lib.STRUCTS):
         assert lib.vb_struct_size(i) == ctypes.sizeof(st)
     assert lib.vb_struct_size(99) == -1
